@@ -1,0 +1,326 @@
+/*
+ * eosvr_oracle.c -- CPU restatement of the reference's test-time episodic hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product package may import, link or
+ * execute this file; only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs use it, and there only as the checker or
+ * as the reported CPU baseline.
+ *
+ * Parity pin: the reference (lovelyqian/Embodied-One-Shot-Video-Recognition) ships
+ * no tests or golden vectors.  This restatement is pinned instead against outputs of
+ * the reference's own code executed in the build container (oracle/make_golden.py
+ * -> tests/golden/*.npz) and against the third-party calls the reference makes
+ * (scipy 1.18.1 cdist, torch 2.11.0 conv2d/softmax, numpy 2.3.5 argsort/mean).
+ *
+ * Every function cites the reference file:line it follows (paths relative to the
+ * reference checkout).  Build: see oracle/build_oracle.py (gcc -O2 -ffp-contract=off;
+ * no -ffast-math: the fp32 rounding sequence is part of the specification).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ---------------------------------------------------------------------------------
+ * scipy.spatial.distance.cdist(A, B, 'euclidean')  -- network_test.py:208,
+ * classifier.py:63.  Inputs are the reference's float32 feature rows; scipy promotes
+ * them to double and evaluates sqrt(sum_k (a_k - b_k)^2) with direct differences.
+ * out is [P,G] double.
+ * ------------------------------------------------------------------------------- */
+static inline double sqdist_f32(const float *a, const float *b, int D)
+{
+    double s = 0.0;
+    for (int k = 0; k < D; ++k) {
+        double df = (double)a[k] - (double)b[k];
+        s += df * df;
+    }
+    return s;
+}
+
+void eo_cdist_euclid(const float *A, int P, const float *B, int G, int D, double *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int p = 0; p < P; ++p)
+        for (int g = 0; g < G; ++g)
+            out[(size_t)p * G + g] = sqrt(sqdist_f32(A + (size_t)p * D, B + (size_t)g * D, D));
+}
+
+/* ---------------------------------------------------------------------------------
+ * TestNetwork.temporal_convolution_flating_layer -- network_test.py:103-117 with
+ * TemporalLayer, models.py:42-56 (weights [lamda1, lamda2, lamda1], utils.py:43).
+ * The float64 distances are cast to float32 (torch.FloatTensor, :109) and every
+ * gallery column is cross-correlated along the probe axis with zero padding.  The
+ * probe axis is the flattened n_way*k_shot*num_segs axis of ONE episode (:208-209),
+ * so rows_per_episode consecutive rows form one padded signal (smoothing bleeds across
+ * clip boundaries inside an episode).
+ * Evaluation order = fp32 FMA chain, taps left to right.
+ * ------------------------------------------------------------------------------- */
+static inline float smooth_tap(float dl, float dc, float dr, float lam1, float lam2)
+{
+    float acc = lam1 * dl;           /* rounded product            */
+    acc = fmaf(lam2, dc, acc);       /* fused, single rounding     */
+    acc = fmaf(lam1, dr, acc);
+    return acc;
+}
+
+void eo_temporal_smooth(const double *d64, int P, int G, int rows_per_episode,
+                        float lam1, float lam2, float *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int p = 0; p < P; ++p) {
+        int r = p % rows_per_episode;
+        int has_l = r > 0, has_r = (r + 1 < rows_per_episode) && (p + 1 < P);
+        for (int g = 0; g < G; ++g) {
+            float dl = has_l ? (float)d64[(size_t)(p - 1) * G + g] : 0.0f;
+            float dc = (float)d64[(size_t)p * G + g];
+            float dr = has_r ? (float)d64[(size_t)(p + 1) * G + g] : 0.0f;
+            out[(size_t)p * G + g] = smooth_tap(dl, dc, dr, lam1, lam2);
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------------
+ * np.argsort(distance, axis=1)[:, :1] -- network_test.py:211-212.  Only the first
+ * element of the sort is used: the arg-min.  Tie rule fixed by the oracle: lowest
+ * index among exact float32 ties (= kind='stable'); the reference's default unstable
+ * sort may return any member of the tie set.
+ * ------------------------------------------------------------------------------- */
+void eo_argmin_rows(const float *t, int P, int G, int64_t *idx, float *val)
+{
+    for (int p = 0; p < P; ++p) {
+        const float *row = t + (size_t)p * G;
+        int best = 0;
+        for (int g = 1; g < G; ++g)
+            if (row[g] < row[best]) best = g;
+        idx[p] = best;
+        if (val) val[p] = row[best];
+    }
+}
+
+/* ---------------------------------------------------------------------------------
+ * Streaming form of steps cdist -> float32 -> 3-tap -> arg-min for galleries whose
+ * [P,G] matrix cannot be materialised (network_test.py:208-212 restated per gallery
+ * row).  Bit-identical to eo_cdist_euclid + eo_temporal_smooth + eo_argmin_rows.
+ * metric: 0 = euclidean (+ temporal taps), the reference path.
+ * Threads split the gallery; per-thread winners are merged with the lowest-index rule.
+ * ------------------------------------------------------------------------------- */
+void eo_match_stream(const float *A, int P, const float *B, int64_t G, int D,
+                     int rows_per_episode, float lam1, float lam2,
+                     int64_t *idx, float *val)
+{
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+    float *tv = (float *)malloc(sizeof(float) * (size_t)nthreads * P);
+    int64_t *ti = (int64_t *)malloc(sizeof(int64_t) * (size_t)nthreads * P);
+#pragma omp parallel
+    {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        float *bv = tv + (size_t)tid * P;
+        int64_t *bi = ti + (size_t)tid * P;
+        float *d32 = (float *)malloc(sizeof(float) * P);
+        for (int p = 0; p < P; ++p) { bv[p] = INFINITY; bi[p] = -1; }
+        int64_t lo = G * tid / nthreads, hi = G * (tid + 1) / nthreads;
+        for (int64_t g = lo; g < hi; ++g) {
+            const float *b = B + (size_t)g * D;
+            for (int p = 0; p < P; ++p)
+                d32[p] = (float)sqrt(sqdist_f32(A + (size_t)p * D, b, D));
+            for (int p = 0; p < P; ++p) {
+                int r = p % rows_per_episode;
+                float dl = r > 0 ? d32[p - 1] : 0.0f;
+                float dr = (r + 1 < rows_per_episode && p + 1 < P) ? d32[p + 1] : 0.0f;
+                float t = smooth_tap(dl, d32[p], dr, lam1, lam2);
+                if (t < bv[p]) { bv[p] = t; bi[p] = g; }
+            }
+        }
+        free(d32);
+    }
+    for (int p = 0; p < P; ++p) {
+        float best = INFINITY; int64_t bidx = -1;
+        for (int t = 0; t < nthreads; ++t) {      /* ascending gallery ranges */
+            float v = tv[(size_t)t * P + p]; int64_t i = ti[(size_t)t * P + p];
+            if (i >= 0 && (bidx < 0 || v < best)) { best = v; bidx = i; }
+        }
+        idx[p] = bidx; if (val) val[p] = best;
+    }
+    free(tv); free(ti);
+}
+
+/* ---------------------------------------------------------------------------------
+ * numpy float32 mean over axis 0 of a C-contiguous [R,D] block: rows are accumulated
+ * sequentially in float32 (row0 + row1 + ...) and the sum is divided by the row count
+ * with a true float32 division ("Bit-level evaluation orders").
+ * rows[] holds R row pointers.
+ * ------------------------------------------------------------------------------- */
+static void mean_rows_f32(const float *const *rows, int R, int D, float *out)
+{
+    for (int k = 0; k < D; ++k) {
+        float acc = rows[0][k];
+        for (int r = 1; r < R; ++r) acc = acc + rows[r][k];
+        out[k] = acc / (float)R;
+    }
+}
+
+/* ---------------------------------------------------------------------------------
+ * Augmented support-set assembly -- network_test.py:220-250 restated in feature space
+ * (SURVEY section 0 "Feature-space splice is exact", Appendix A step 4).
+ *   probe   [n,S,D]  support segment features of one episode (:201-205)
+ *   gallery [G,D]    gallery segment features (:184-189)
+ *   ids     [n,S]    winning gallery segment per probe segment (:211-214)
+ *   orig_mode 0: "original" row of clip i = flat segment row i (the as-written
+ *                behaviour of :229);  1: mean of clip i's S
+ *                segment rows (the commented intent, :227-228).
+ *   out     [n*(1+S), D]; row order: for each clip i: original, then s = 0..S-1.
+ * ------------------------------------------------------------------------------- */
+void eo_splice(const float *probe, const float *gallery, const int64_t *ids,
+               int n, int S, int D, int orig_mode, float *out)
+{
+    const float **rows = (const float **)malloc(sizeof(float *) * S);
+    for (int i = 0; i < n; ++i) {
+        float *o = out + (size_t)i * (1 + S) * D;
+        if (orig_mode == 0) {
+            memcpy(o, probe + (size_t)i * D, sizeof(float) * D);   /* flat row i */
+        } else {
+            for (int s = 0; s < S; ++s) rows[s] = probe + ((size_t)i * S + s) * D;
+            mean_rows_f32(rows, S, D, o);
+        }
+        for (int s = 0; s < S; ++s) {
+            for (int s2 = 0; s2 < S; ++s2)
+                rows[s2] = (s2 == s) ? gallery + (size_t)ids[i * S + s] * D
+                                     : probe + ((size_t)i * S + s2) * D;
+            mean_rows_f32(rows, S, D, o + (size_t)(1 + s) * D);
+        }
+    }
+    free(rows);
+}
+
+/* ---------------------------------------------------------------------------------
+ * ProtoNet scoring -- classifier.py:9-40 (prototypes) and :43-90 (distances, softmax,
+ * arg-max).  Classes are keyed by the float label in first-appearance order (:21-29);
+ * prototype = float32 sequential mean of the class rows (:32-37); query->prototype
+ * distance = scipy cdist in double (:63) cast to float32 (:66); probability =
+ * softmax(-d) over classes (:67); prediction = first arg-max (:85), which is returned
+ * as the prototype POSITION.
+ * Outputs: protos [n_proto,D], proto_ids [n_proto], dist32 [Q,n_proto],
+ *          prob [Q,n_proto] (expf-based; compare with tolerance), pred [Q].
+ * Returns n_proto.  max_proto bounds the output arrays.
+ * ------------------------------------------------------------------------------- */
+int eo_proto_score(const float *sup, const float *sup_y, int R, int D,
+                   const float *query, int Q, int max_proto,
+                   float *protos, float *proto_ids, float *dist32, float *prob,
+                   int64_t *pred)
+{
+    int n_proto = 0;
+    int *cls = (int *)malloc(sizeof(int) * R);
+    for (int r = 0; r < R; ++r) {
+        int c = -1;
+        for (int j = 0; j < n_proto; ++j) if (proto_ids[j] == sup_y[r]) { c = j; break; }
+        if (c < 0) {
+            if (n_proto == max_proto) { free(cls); return -1; }
+            c = n_proto; proto_ids[n_proto++] = sup_y[r];
+        }
+        cls[r] = c;
+    }
+    const float **rows = (const float **)malloc(sizeof(float *) * R);
+    for (int c = 0; c < n_proto; ++c) {
+        int cnt = 0;
+        for (int r = 0; r < R; ++r) if (cls[r] == c) rows[cnt++] = sup + (size_t)r * D;
+        mean_rows_f32(rows, cnt, D, protos + (size_t)c * D);
+    }
+    for (int q = 0; q < Q; ++q) {
+        float *dq = dist32 + (size_t)q * n_proto;
+        for (int c = 0; c < n_proto; ++c)
+            dq[c] = (float)sqrt(sqdist_f32(query + (size_t)q * D, protos + (size_t)c * D, D));
+        /* softmax(-d) in float32, max-subtracted like torch (classifier.py:67) */
+        float mx = -dq[0];
+        for (int c = 1; c < n_proto; ++c) if (-dq[c] > mx) mx = -dq[c];
+        float sum = 0.0f;
+        for (int c = 0; c < n_proto; ++c) { prob[q * n_proto + c] = expf(-dq[c] - mx); sum += prob[q * n_proto + c]; }
+        for (int c = 0; c < n_proto; ++c) prob[q * n_proto + c] /= sum;
+        /* arg-max of probability == arg-min of the float32 distance, first on ties */
+        int best = 0;
+        for (int c = 1; c < n_proto; ++c) if (dq[c] < dq[best]) best = c;
+        pred[q] = best;
+    }
+    free(rows); free(cls);
+    return n_proto;
+}
+
+/* ---------------------------------------------------------------------------------
+ * Segment features from per-frame features -- network_test.py:187-189, :203-205 with
+ * the per-frame L2 of :79-80 (torch.nn.functional.normalize, p=2, eps=1e-12).
+ *   frames [N*seg_len, D] -> out [N, D]; mean over seg_len consecutive frames
+ *   (np.resize to [N,seg_len,D] + np.mean(axis=1): sequential float32 sum, true divide).
+ * The frame norm is accumulated in double here; torch's float32 vectorised norm differs
+ * in the last bits, so this stage is compared with a 1e-6 tolerance, not bit-exactly.
+ * ------------------------------------------------------------------------------- */
+void eo_segment_features(const float *frames, int64_t N, int seg_len, int D, int l2, float *out)
+{
+#pragma omp parallel
+    {
+        float *tmp = (float *)malloc(sizeof(float) * (size_t)seg_len * D);
+        const float **rows = (const float **)malloc(sizeof(float *) * seg_len);
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < N; ++i) {
+            for (int f = 0; f < seg_len; ++f) {
+                const float *x = frames + ((size_t)i * seg_len + f) * D;
+                float *y = tmp + (size_t)f * D;
+                if (l2) {
+                    double s = 0.0;
+                    for (int k = 0; k < D; ++k) s += (double)x[k] * (double)x[k];
+                    float nrm = (float)sqrt(s);
+                    if (nrm < 1e-12f) nrm = 1e-12f;
+                    for (int k = 0; k < D; ++k) y[k] = x[k] / nrm;
+                } else {
+                    memcpy(y, x, sizeof(float) * D);
+                }
+                rows[f] = y;
+            }
+            mean_rows_f32(rows, seg_len, D, out + (size_t)i * D);
+        }
+        free(tmp); free(rows);
+    }
+}
+
+/* ---------------------------------------------------------------------------------
+ * One whole augmented episode on cached segment embeddings: the loop body of
+ * test_network_aug_segment, network_test.py:195-259, restated (SURVEY Appendix A
+ * steps 1-6).  Returns the predicted prototype position; fills ids [n*S].
+ * ------------------------------------------------------------------------------- */
+int64_t eo_episode(const float *probe, const float *sup_y, int n, int S, int D,
+                   const float *gallery, int64_t G, const float *query,
+                   float lam1, float lam2, int orig_mode, int64_t *ids)
+{
+    int P = n * S, R = n * (1 + S);
+    float *val = (float *)malloc(sizeof(float) * P);
+    eo_match_stream(probe, P, gallery, G, D, P, lam1, lam2, ids, val);
+    float *aug = (float *)malloc(sizeof(float) * (size_t)R * D);
+    float *lab = (float *)malloc(sizeof(float) * R);
+    eo_splice(probe, gallery, ids, n, S, D, orig_mode, aug);
+    for (int i = 0; i < n; ++i) for (int j = 0; j <= S; ++j) lab[i * (1 + S) + j] = sup_y[i];
+    float *protos = (float *)malloc(sizeof(float) * (size_t)n * D);
+    float *pid = (float *)malloc(sizeof(float) * n);
+    float *d32 = (float *)malloc(sizeof(float) * n);
+    float *prob = (float *)malloc(sizeof(float) * n);
+    int64_t pred = -1;
+    eo_proto_score(aug, lab, R, D, query, 1, n, protos, pid, d32, prob, &pred);
+    free(val); free(aug); free(lab); free(protos); free(pid); free(d32); free(prob);
+    return pred;
+}
+
+void eo_set_threads(int n)
+{
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

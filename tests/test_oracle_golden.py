@@ -1,0 +1,142 @@
+"""Pin the oracle (oracle/oracle.py + oracle/eosvr_oracle.c) against the golden vectors
+produced by the reference's own code (oracle/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+import synth
+
+AUGSEG = ["5w_s8", "3w_s4", "5w_s16"]
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def _regen_augseg(fx):
+    seed, n_way, seg_len = int(fx["seed"]), int(fx["n_way"]), int(fx["seg_len"])
+    S, D, NG = 16 // seg_len, 2048, 640
+    cents = synth.hash_normal(seed + 7, (64, D))
+    g_lab = np.repeat((np.arange(NG) * 2654435761 % 64).astype(np.int64), S)
+    gallery = synth.segment_features(seed + 17, NG * S, D, seg_len, cents, g_lab)
+    assert synth.digest(gallery) == str(fx["gallery_digest"]), "synthetic gallery is not reproducible here"
+    eps = []
+    for e in range(int(fx["episodes"])):
+        cls = fx[f"e{e}_cls"]
+        probe = synth.segment_features(seed + 1000 + e, n_way * S, D, seg_len, cents, np.repeat(cls, S))
+        assert synth.digest(probe) == str(fx[f"e{e}_probe_digest"])
+        eps.append(probe.reshape(n_way, S, D))
+    return gallery, eps, n_way, S, D
+
+
+def test_classifier_golden(golden_dir):
+    fx = _load(golden_dir, "golden_classifier.npz")
+    for c in range(int(fx["n_cases"])):
+        sup, y, q = fx[f"c{c}_sup"], fx[f"c{c}_y"], fx[f"c{c}_q"]
+        pred, prob, d32, order, protos = O.lib_protonet(sup, y, q)
+        assert np.array_equal(pred, fx[f"c{c}_pred_protonet"])
+        assert np.array_equal(np.asarray(order, dtype=np.float32), fx[f"c{c}_proto_ids"])
+        assert np.array_equal(protos, fx[f"c{c}_protos"])                 # bit-exact prototypes
+        cpred, cprob, cd32, cpid, cprotos = O.c_protonet(sup, y, q)
+        assert np.array_equal(cpred, fx[f"c{c}_pred_protonet"])
+        assert np.array_equal(cpid, fx[f"c{c}_proto_ids"])
+        assert np.array_equal(cprotos, fx[f"c{c}_protos"])
+        assert np.array_equal(cd32, d32)
+        np.testing.assert_allclose(cprob, prob, rtol=1e-5, atol=1e-7)
+        cos_pred, _ = O.lib_cosine_predict(sup, q)
+        assert np.array_equal(cos_pred, fx[f"c{c}_pred_cosine"])
+
+
+def test_temporal_golden(golden_dir):
+    fx = _load(golden_dir, "golden_temporal.npz")
+    for c in range(int(fx["n_cases"])):
+        A, B, d64, t = fx[f"t{c}_A"], fx[f"t{c}_B"], fx[f"t{c}_d64"], fx[f"t{c}_t"]
+        assert np.array_equal(O.lib_cdist(A, B), d64)
+        cd = O.c_cdist(A, B)
+        np.testing.assert_allclose(cd, d64, rtol=1e-13)
+        assert np.array_equal(cd.astype(np.float32), d64.astype(np.float32))
+        assert np.array_equal(O.lib_temporal_smooth(d64), t)
+        assert np.array_equal(O.c_temporal_smooth(d64), t)               # FMA chain == conv2d, bit-exact
+        idx, val = O.c_match(A, B)
+        assert np.array_equal(idx, np.argsort(t, axis=1, kind="stable")[:, 0])
+        assert np.array_equal(val, t[np.arange(t.shape[0]), idx])
+
+
+@pytest.mark.parametrize("tag", AUGSEG)
+def test_augseg_golden(golden_dir, tag):
+    """The whole reference loop body (network_test.py:195-259), restated on cached embeddings."""
+    fx = _load(golden_dir, f"golden_augseg_{tag}.npz")
+    gallery, eps, n_way, S, D = _regen_augseg(fx)
+    sub = slice(None, None, 16)
+    for e, probe in enumerate(eps):
+        query = fx[f"e{e}_query"]
+        y = np.arange(n_way, dtype=np.float32)
+        r = O.lib_episode(probe, y, query, gallery)
+        ids_stable = fx[f"e{e}_ids_stable"]
+        assert np.array_equal(r["ids"].reshape(-1), ids_stable)
+        # the reference's own (unstable-sort) pick must equal ours unless it is an exact tie
+        ids_ref = fx[f"e{e}_ids_ref"]
+        _, twin, t = O.lib_match(probe.reshape(-1, D), gallery)
+        assert np.array_equal(twin, fx[f"e{e}_t_win"])
+        assert np.array_equal(t[:, sub], fx[f"e{e}_t_sample"])
+        for p in np.nonzero(ids_ref != ids_stable)[0]:
+            assert t[p, ids_ref[p]] == t[p, ids_stable[p]]
+        # classifier input: the reference re-encodes 16 frames (mean of 16), the restatement
+        # averages S segment means; equal up to float32 summation order
+        np.testing.assert_allclose(r["support_feature"][:, sub], fx[f"e{e}_sup_sample"], rtol=2e-6, atol=1e-8)
+        assert np.array_equal(r["support_y"], fx[f"e{e}_sup_y"])
+        assert np.array_equal(r["pred"], fx[f"e{e}_pred"])
+        # C restatement: same winners, same prediction, bit-equal splice to the numpy form
+        pred_c, ids_c = O.c_episode(probe, y, query, gallery)
+        assert np.array_equal(ids_c.reshape(-1), ids_stable)
+        assert pred_c == int(fx[f"e{e}_pred"][0])
+        assert np.array_equal(O.c_splice(probe, gallery, r["ids"]), r["support_feature"])
+        cidx, cval = O.c_match(probe.reshape(-1, D), gallery)
+        assert np.array_equal(cidx, ids_stable)
+        assert np.array_equal(cval, fx[f"e{e}_t_win"])
+
+
+def test_c_vs_lib_random_shapes():
+    """C restatement == third-party-call restatement on shapes the reference cannot run
+    (its 640 / 2048 literals, network_test.py:188): cfg-1 (5w1s, D=512, S=4, G=1000) and a
+    multi-episode batch with rows_per_episode smoothing scope."""
+    for (E, n_way, S, D, G, seed) in [(1, 5, 4, 512, 1000, 1), (3, 5, 4, 64, 333, 2), (2, 14, 8, 128, 257, 3)]:
+        ep = synth.episode_batch(seed, E, n_way, 1, S, D)
+        gal = synth.gallery(seed + 50, G, D, centroid_seed=seed)
+        A = ep["probe"].reshape(-1, D)
+        rpe = n_way * S
+        ids, twin, t = O.lib_match(A, gal, rpe)
+        cidx, cval = O.c_match(A, gal, rpe)
+        assert np.array_equal(cidx, ids) and np.array_equal(cval, twin)
+        assert np.array_equal(O.c_temporal_smooth(O.c_cdist(A, gal), rpe), t)
+        for e in range(E):
+            r = O.lib_episode(ep["probe"][e], ep["support_y"][e], ep["query"][e], gal)
+            pred_c, ids_c = O.c_episode(ep["probe"][e], ep["support_y"][e], ep["query"][e], gal)
+            assert np.array_equal(ids_c, r["ids"]) and pred_c == int(r["pred"][0])
+            assert np.array_equal(r["ids"].reshape(-1), ids[e * rpe:(e + 1) * rpe])
+            for mode in (O.ORIG_REF_QUIRK, O.ORIG_CLIP_MEAN):
+                f, _ = O.lib_splice(ep["probe"][e], gal, r["ids"], mode)
+                assert np.array_equal(O.c_splice(ep["probe"][e], gal, r["ids"], mode), f)
+
+
+def test_tie_rule_lowest_index():
+    """Exact duplicate gallery rows: the oracle picks the lowest index."""
+    ep = synth.episode_batch(9, 1, 5, 1, 4, 64)
+    gal = synth.gallery(59, 200, 64, centroid_seed=9)
+    A = ep["probe"].reshape(-1, 64)
+    ids0, _ = O.c_match(A, gal)
+    gal2 = np.concatenate([gal, gal[ids0]], axis=0)       # duplicates of every winner at the end
+    ids1, _ = O.c_match(A, gal2)
+    assert np.array_equal(ids1, ids0)
+    lids, _, _ = O.lib_match(A, gal2)
+    assert np.array_equal(lids, ids0)
+
+
+def test_segment_features():
+    f = synth.frame_features(5, 64, 96)
+    a = O.lib_segment_features(f, 2, True)
+    b = O.c_segment_features(f, 2, True)
+    np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-8)
+    assert np.array_equal(O.lib_segment_features(f, 4, False), O.c_segment_features(f, 4, False))
