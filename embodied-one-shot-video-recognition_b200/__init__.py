@@ -1,0 +1,16 @@
+"""B200-native test-time episodic hot path of Embodied-One-Shot-Video-Recognition.
+
+Segment matching (tcgen05 screening + exact re-rank), augmented-clip assembly and ProtoNet
+episode scoring behind a C ABI (include/eosvr.h), with a PyTorch/ctypes host layer.
+Import as ``eosvr_b200``.
+"""
+from eosvr_b200._lib import (EosvrError, lib, lib_path, load_library, ORIG_CLIP_MEAN,  # noqa: F401
+                             ORIG_REF_QUIRK, SCREEN_BF16, SCREEN_F16)
+from eosvr_b200.matcher import (EpisodePipeline, GalleryFeatureCache, MatchWorkspace,  # noqa: F401
+                                match_segments, match_segments_exact, merge_top1, proto_score,
+                                segment_features, splice_augmented)
+
+__all__ = ["EosvrError", "lib", "lib_path", "load_library", "GalleryFeatureCache", "MatchWorkspace",
+           "EpisodePipeline", "match_segments", "match_segments_exact", "merge_top1", "proto_score",
+           "segment_features", "splice_augmented", "ORIG_REF_QUIRK", "ORIG_CLIP_MEAN", "SCREEN_F16",
+           "SCREEN_BF16"]

@@ -1,0 +1,287 @@
+// eosvr_api.cu -- the extern "C" surface declared in include/eosvr.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+
+#include "eosvr_internal.h"
+
+namespace eosvr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// 2-D row-major [rows, cols] 16-bit tensor, box = box_rows x box_cols, 128-byte swizzle.
+int encode_tmap_2d(CUtensorMap *m, const void *base, int fmt, uint64_t rows, uint64_t cols,
+                   uint32_t box_rows, uint32_t box_cols)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return EOSVR_ECUDA; }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {cols * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, fmt == EOSVR_SCREEN_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                     2, const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return EOSVR_ECUDA; }
+    return EOSVR_OK;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace eosvr
+
+using namespace eosvr;
+
+extern "C" {
+
+int eosvr_version(void) { return EOSVR_VERSION; }
+
+const char *eosvr_last_error(void) { return g_err; }
+
+int eosvr_device_check(void)
+{
+    int dev = 0;
+    EOSVR_CUDA(cudaGetDevice(&dev));
+    int major = 0, minor = 0;
+    EOSVR_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    EOSVR_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    if (major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, major, minor);
+        return EOSVR_EUNSUPPORTED;
+    }
+    return EOSVR_OK;
+}
+
+int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtype, int64_t global_offset,
+                         int32_t screen_fmt, void *stream, eosvr_gallery_t **out)
+{
+    if (!out) { set_error("gallery_create: out is NULL"); return EOSVR_EINVAL; }
+    *out = nullptr;
+    if (!d_feats || G < 1 || D < 1) { set_error("gallery_create: need d_feats != NULL, G >= 1, D >= 1"); return EOSVR_EINVAL; }
+    if (dtype != EOSVR_F32) { set_error("gallery_create: unsupported dtype %d", dtype); return EOSVR_EINVAL; }
+    if (screen_fmt != EOSVR_SCREEN_F16 && screen_fmt != EOSVR_SCREEN_BF16) { set_error("gallery_create: bad screen_fmt %d", screen_fmt); return EOSVR_EINVAL; }
+    if (global_offset < 0 || global_offset + G > 0xFFFFFFFFll) { set_error("gallery_create: global indices must fit 32 bits"); return EOSVR_EINVAL; }
+    if (G > 0x7FFFFF00ll) { set_error("gallery_create: shard too large"); return EOSVR_EINVAL; }
+    int rc = eosvr_device_check();
+    if (rc) return rc;
+    eosvr_gallery *g = new (std::nothrow) eosvr_gallery();
+    if (!g) { set_error("out of host memory"); return EOSVR_ENOMEM; }
+    memset(g, 0, sizeof(*g));
+    g->feats = static_cast<const float *>(d_feats);
+    g->G = G; g->D = D; g->Dp = (D + kBK - 1) / kBK * kBK;
+    g->offset = global_offset; g->screen_fmt = screen_fmt;
+    cudaGetDevice(&g->device);
+    const int64_t Gpad = (G + kBM - 1) / kBM * kBM;
+    if (cudaMalloc(&g->h16, static_cast<size_t>(Gpad) * g->Dp * 2) != cudaSuccess ||
+        cudaMalloc(&g->gnorm, static_cast<size_t>(Gpad) * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&g->scalars, 4 * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("gallery_create: device allocation failed (%lld rows x %d)", (long long)Gpad, g->Dp);
+        eosvr_gallery_destroy(g);
+        return EOSVR_ENOMEM;
+    }
+    rc = launch_gallery_prep(g, static_cast<cudaStream_t>(stream));
+    if (!rc) rc = encode_tmap_2d(&g->tmapA, g->h16, screen_fmt, static_cast<uint64_t>(Gpad), static_cast<uint64_t>(g->Dp), kBM, kBK);
+    if (rc) { eosvr_gallery_destroy(g); return rc; }
+    *out = g;
+    return EOSVR_OK;
+}
+
+int eosvr_gallery_destroy(eosvr_gallery_t *g)
+{
+    if (!g) return EOSVR_OK;
+    if (g->h16) cudaFree(g->h16);
+    if (g->gnorm) cudaFree(g->gnorm);
+    if (g->scalars) cudaFree(g->scalars);
+    delete g;
+    return EOSVR_OK;
+}
+
+int eosvr_gallery_rows(const eosvr_gallery_t *g, int64_t *G, int32_t *D, int64_t *global_offset)
+{
+    if (!g) { set_error("gallery_rows: NULL handle"); return EOSVR_EINVAL; }
+    if (G) *G = g->G;
+    if (D) *D = g->D;
+    if (global_offset) *global_offset = g->offset;
+    return EOSVR_OK;
+}
+
+int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capacity, eosvr_workspace_t **out)
+{
+    if (!out) { set_error("workspace_create: out is NULL"); return EOSVR_EINVAL; }
+    *out = nullptr;
+    if (max_probe_rows < 1 || D < 1 || cand_capacity < 0) { set_error("workspace_create: bad sizes"); return EOSVR_EINVAL; }
+    if (max_probe_rows > 0x7FFFFFF0ll) { set_error("workspace_create: max_probe_rows too large"); return EOSVR_EINVAL; }
+    int rc = eosvr_device_check();
+    if (rc) return rc;
+    eosvr_workspace *ws = new (std::nothrow) eosvr_workspace();
+    if (!ws) { set_error("out of host memory"); return EOSVR_ENOMEM; }
+    memset(ws, 0, sizeof(*ws));
+    ws->maxP = max_probe_rows; ws->D = D; ws->Dp = (D + kBK - 1) / kBK * kBK;
+    ws->cap_rows = max_probe_rows + max_probe_rows / 4 + 4 * kMaxBN;
+    ws->cand_cap = cand_capacity ? cand_capacity : (max_probe_rows * 64 > (1ll << 20) ? max_probe_rows * 64 : (1ll << 20));
+    cudaGetDevice(&ws->device);
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_q = carve(static_cast<size_t>(ws->cap_rows) * ws->Dp * 2);
+    const size_t o_na = carve(ws->cap_rows * 4), o_wl = carve(ws->cap_rows * 4), o_wr = carve(ws->cap_rows * 4);
+    const size_t o_mg = carve(ws->cap_rows * 4), o_ep = carve(ws->cap_rows * 4), o_rm = carve(ws->cap_rows * 4);
+    const size_t o_thr = carve(ws->maxP * 4), o_best = carve(ws->maxP * 8), o_rf = carve(ws->maxP * 4);
+    const size_t o_fl = carve(ws->maxP * 4), o_ds = carve(static_cast<size_t>(ws->maxP) * kSeedSamples * 4);
+    const size_t o_cd = carve(static_cast<size_t>(ws->cand_cap) * sizeof(Cand)), o_ct = carve(sizeof(Counters));
+    if (cudaMalloc(&ws->slab, off) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("workspace_create: device allocation of %zu bytes failed", off);
+        delete ws;
+        return EOSVR_ENOMEM;
+    }
+    cudaMemset(ws->slab, 0, off);
+    char *b = static_cast<char *>(ws->slab);
+    ws->q16 = b + o_q;
+    ws->na = reinterpret_cast<float *>(b + o_na); ws->wl = reinterpret_cast<float *>(b + o_wl);
+    ws->wr = reinterpret_cast<float *>(b + o_wr); ws->margin = reinterpret_cast<float *>(b + o_mg);
+    ws->epsd = reinterpret_cast<float *>(b + o_ep); ws->rowmap = reinterpret_cast<int32_t *>(b + o_rm);
+    ws->gthr = reinterpret_cast<unsigned int *>(b + o_thr); ws->best = reinterpret_cast<unsigned long long *>(b + o_best);
+    ws->rowflag = reinterpret_cast<int32_t *>(b + o_rf); ws->flaglist = reinterpret_cast<int32_t *>(b + o_fl);
+    ws->dsamp = reinterpret_cast<float *>(b + o_ds); ws->cand = reinterpret_cast<Cand *>(b + o_cd);
+    ws->counters = reinterpret_cast<Counters *>(b + o_ct);
+    *out = ws;
+    return EOSVR_OK;
+}
+
+int eosvr_workspace_destroy(eosvr_workspace_t *ws)
+{
+    if (!ws) return EOSVR_OK;
+    if (ws->slab) cudaFree(ws->slab);
+    delete ws;
+    return EOSVR_OK;
+}
+
+// Test hook (not part of the reference-facing surface): dump the screening values t~[P,G] of the
+// next eosvr_match calls into a caller-owned device buffer (NULL disables).
+int eosvr_workspace_set_debug(eosvr_workspace_t *ws, float *d_dump, int64_t elems)
+{
+    if (!ws) { set_error("set_debug: NULL workspace"); return EOSVR_EINVAL; }
+    ws->dbg = d_dump; ws->dbg_elems = d_dump ? elems : 0;
+    return EOSVR_OK;
+}
+
+static int check_match_args(const eosvr_gallery_t *g, eosvr_workspace_t *ws, const float *d_probes, int64_t P,
+                            int32_t rpe, int32_t metric, float lam1, float lam2, uint64_t *d_out_packed)
+{
+    if (!g || !ws) { set_error("match: NULL handle"); return EOSVR_EINVAL; }
+    if (P < 0 || (P > 0 && !d_probes)) { set_error("match: bad probes"); return EOSVR_EINVAL; }
+    if (P > ws->maxP) { set_error("match: P=%lld exceeds workspace max_probe_rows=%lld", (long long)P, (long long)ws->maxP); return EOSVR_EINVAL; }
+    if (ws->D != g->D) { set_error("match: workspace D=%d != gallery D=%d", ws->D, g->D); return EOSVR_EINVAL; }
+    if (rpe < 1) { set_error("match: rows_per_episode must be >= 1"); return EOSVR_EINVAL; }
+    if (metric != EOSVR_METRIC_EUCLID_TEMPORAL) { set_error("match: unsupported metric %d", metric); return EOSVR_EINVAL; }
+    if (!(lam2 > 0.f) || !(lam1 >= 0.f)) { set_error("match: need lam2 > 0 and lam1 >= 0"); return EOSVR_EINVAL; }
+    if (P > 0 && !d_out_packed) { set_error("match: d_out_packed is required"); return EOSVR_EINVAL; }
+    return EOSVR_OK;
+}
+
+int eosvr_match(const eosvr_gallery_t *g, eosvr_workspace_t *ws, const float *d_probes, int64_t P,
+                int32_t rows_per_episode, int32_t metric, float lam1, float lam2, uint64_t *d_out_packed,
+                float *d_out_score, int64_t *d_out_idx, void *stream)
+{
+    int rc = check_match_args(g, ws, d_probes, P, rows_per_episode, metric, lam1, lam2, d_out_packed);
+    if (rc) return rc;
+    return launch_match(g, ws, d_probes, P, rows_per_episode, lam1, lam2, false, d_out_packed, d_out_score,
+                        d_out_idx, static_cast<cudaStream_t>(stream));
+}
+
+int eosvr_match_exact(const eosvr_gallery_t *g, eosvr_workspace_t *ws, const float *d_probes, int64_t P,
+                      int32_t rows_per_episode, int32_t metric, float lam1, float lam2, uint64_t *d_out_packed,
+                      float *d_out_score, int64_t *d_out_idx, void *stream)
+{
+    int rc = check_match_args(g, ws, d_probes, P, rows_per_episode, metric, lam1, lam2, d_out_packed);
+    if (rc) return rc;
+    return launch_match(g, ws, d_probes, P, rows_per_episode, lam1, lam2, true, d_out_packed, d_out_score,
+                        d_out_idx, static_cast<cudaStream_t>(stream));
+}
+
+int eosvr_match_stats(eosvr_workspace_t *ws, void *stream, int64_t out[8])
+{
+    if (!ws || !out) { set_error("match_stats: NULL argument"); return EOSVR_EINVAL; }
+    Counters c;
+    EOSVR_CUDA(cudaMemcpyAsync(&c, ws->counters, sizeof(c), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    EOSVR_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    out[0] = static_cast<int64_t>(c.cand_count);
+    out[1] = static_cast<int64_t>(c.n_exact);
+    out[2] = c.n_flag_rows;
+    out[3] = ws->cand_cap;
+    out[4] = ws->last_tiles;
+    out[5] = ws->last_bn;
+    out[6] = static_cast<int64_t>(c.n_unsafe);
+    out[7] = c.overflow;
+    return EOSVR_OK;
+}
+
+int eosvr_merge_top1(const uint64_t *d_gathered, int32_t nshards, int64_t P, uint64_t *d_out_packed,
+                     float *d_out_score, int64_t *d_out_idx, void *stream)
+{
+    if (nshards < 1 || P < 0 || (P > 0 && !d_gathered)) { set_error("merge_top1: bad arguments"); return EOSVR_EINVAL; }
+    return launch_merge(d_gathered, nshards, P, d_out_packed, d_out_score, d_out_idx, static_cast<cudaStream_t>(stream));
+}
+
+int eosvr_gather_rows(const eosvr_gallery_t *g, const int64_t *d_idx, int64_t P, float *d_out_rows, void *stream)
+{
+    if (!g || P < 0 || (P > 0 && (!d_idx || !d_out_rows))) { set_error("gather_rows: bad arguments"); return EOSVR_EINVAL; }
+    return launch_gather_rows(g, d_idx, P, d_out_rows, static_cast<cudaStream_t>(stream));
+}
+
+int eosvr_splice(const float *d_probes, const float *d_winner_rows, int64_t E, int32_t n, int32_t S, int32_t D,
+                 int32_t orig_mode, float *d_out, void *stream)
+{
+    if (E < 0 || n < 1 || S < 1 || D < 1 || (E > 0 && (!d_probes || !d_winner_rows || !d_out))) { set_error("splice: bad arguments"); return EOSVR_EINVAL; }
+    if (orig_mode != EOSVR_ORIG_REF_QUIRK && orig_mode != EOSVR_ORIG_CLIP_MEAN) { set_error("splice: bad orig_mode %d", orig_mode); return EOSVR_EINVAL; }
+    if (orig_mode == EOSVR_ORIG_REF_QUIRK && n > n * S) { set_error("splice: internal"); return EOSVR_EINVAL; }
+    if (1 + S > 65535) { set_error("splice: S too large"); return EOSVR_EINVAL; }
+    return launch_splice(d_probes, d_winner_rows, E, n, S, D, orig_mode, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int eosvr_proto_score(const float *d_support, const float *d_support_y, const float *d_query, int64_t E, int32_t R,
+                      int32_t Q, int32_t D, int32_t max_proto, float *d_dist, float *d_prob, int64_t *d_pred,
+                      int32_t *d_nproto, void *stream)
+{
+    if (E < 0 || D < 1 || (E > 0 && (!d_support || !d_support_y || !d_query))) { set_error("proto_score: bad arguments"); return EOSVR_EINVAL; }
+    return launch_proto_score(d_support, d_support_y, d_query, E, R, Q, D, max_proto, d_dist, d_prob, d_pred, d_nproto,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int eosvr_segment_features(const float *d_frames, int64_t N, int32_t seg_len, int32_t D, int32_t l2, float *d_out,
+                           void *stream)
+{
+    if (N < 0 || D < 1 || (N > 0 && (!d_frames || !d_out))) { set_error("segment_features: bad arguments"); return EOSVR_EINVAL; }
+    return launch_segment_features(d_frames, N, seg_len, D, l2, d_out, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,209 @@
+// eosvr_episode.cu -- augmented-clip assembly and ProtoNet scoring (bandwidth kernels).
+//
+//   k_splice          replaces network_test.py:220-250 (+ video_segment_augmentation :119-129 and
+//                     the backbone re-encode :239-245) in feature space;
+//   k_proto_score     replaces classifier.py:9-90 (prototypes, cdist, softmax, arg-max);
+//   k_segment_features replaces network_test.py:188-189 / :204-205 (+ per-frame L2, :79-80).
+//
+// The float32 evaluation orders are numpy's (sequential row accumulation, one true division), so
+// given equal winners the results are bit-equal to the reference's, not merely close
+// ("Bit-level evaluation orders").
+#include <math.h>
+
+#include "eosvr_internal.h"
+
+namespace eosvr {
+
+// grid: (E*n, 1+S); block: 128 threads striding D.
+// out[e, i*(1+S) + j, :]:  j = 0 "original" row, j = 1+s the clip with segment s replaced.
+__global__ void k_splice(const float *__restrict__ probes, const float *__restrict__ wrows,
+                         int n, int S, int D, int orig_mode, float *__restrict__ out)
+{
+    const int64_t clip = blockIdx.x;              // e*n + i
+    const int j = blockIdx.y;
+    const int64_t e = clip / n;
+    const int i = static_cast<int>(clip % n);
+    const float *pc = probes + clip * S * D;      // the clip's S segment rows
+    float *o = out + (clip * (1 + S) + j) * D;
+    if (j == 0 && orig_mode == EOSVR_ORIG_REF_QUIRK) {
+        // network_test.py:229: support_seg_features[i] = flat segment row i of the episode
+        const float *src = probes + (e * n * S + i) * D;
+        for (int k = threadIdx.x; k < D; k += blockDim.x) o[k] = src[k];
+        return;
+    }
+    const int s_rep = j - 1;                       // -1: no replacement (clip mean)
+    const float *wr = s_rep >= 0 ? wrows + (clip * S + s_rep) * D : nullptr;
+    const float fS = static_cast<float>(S);
+    for (int k = threadIdx.x; k < D; k += blockDim.x) {
+        float acc = (s_rep == 0) ? wr[k] : pc[k];
+        for (int s = 1; s < S; ++s) {
+            const float v = (s == s_rep) ? wr[k] : pc[static_cast<int64_t>(s) * D + k];
+            acc = __fadd_rn(acc, v);
+        }
+        o[k] = __fdiv_rn(acc, fS);
+    }
+}
+
+int launch_splice(const float *probes, const float *wrows, int64_t E, int32_t n, int32_t S, int32_t D,
+                  int32_t orig_mode, float *out, cudaStream_t st)
+{
+    if (E == 0) return EOSVR_OK;
+    dim3 grid(static_cast<unsigned>(E * n), static_cast<unsigned>(1 + S));
+    k_splice<<<grid, 128, 0, st>>>(probes, wrows, n, S, D, orig_mode, out);
+    EOSVR_CUDA(cudaGetLastError());
+    return EOSVR_OK;
+}
+
+// One block per episode.
+constexpr int kProtoThreads = 256;
+constexpr int kMaxRows = 1024;     // support rows per episode
+constexpr int kMaxProto = 64;
+constexpr int kMaxQ = 8;
+
+__global__ void __launch_bounds__(kProtoThreads)
+k_proto_score(const float *__restrict__ sup, const float *__restrict__ sup_y, const float *__restrict__ query,
+              int R, int Q, int D, int max_proto, float *__restrict__ dist, float *__restrict__ prob,
+              int64_t *__restrict__ pred, int32_t *__restrict__ nproto_out)
+{
+    __shared__ int16_t s_cls[kMaxRows];
+    __shared__ float s_pid[kMaxProto];
+    __shared__ int s_np;
+    __shared__ double s_red[kProtoThreads / 32][kMaxQ];
+    __shared__ float s_d[kMaxQ][kMaxProto];
+
+    const int64_t e = blockIdx.x;
+    const float *S0 = sup + e * R * D;
+    const float *Y = sup_y + e * R;
+    const float *Qp = query + e * Q * D;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        // classifier.py:21-29: classes keyed by label value, first-appearance order
+        int np = 0;
+        for (int r = 0; r < R; ++r) {
+            const float y = Y[r];
+            int c = -1;
+            for (int j = 0; j < np; ++j) if (s_pid[j] == y) { c = j; break; }
+            if (c < 0) { if (np < max_proto) { c = np; s_pid[np++] = y; } else c = -1; }
+            s_cls[r] = static_cast<int16_t>(c);
+        }
+        s_np = np;
+    }
+    __syncthreads();
+    const int np = s_np;
+
+    for (int c = 0; c < np; ++c) {
+        double part[kMaxQ];
+#pragma unroll
+        for (int q = 0; q < kMaxQ; ++q) part[q] = 0.0;
+        for (int k = tid; k < D; k += kProtoThreads) {
+            // classifier.py:34-35: float32 mean over the class rows, sequential, true division
+            float acc = 0.f; int cnt = 0;
+            for (int r = 0; r < R; ++r) {
+                if (s_cls[r] != c) continue;
+                const float v = S0[static_cast<int64_t>(r) * D + k];
+                acc = cnt ? __fadd_rn(acc, v) : v;
+                ++cnt;
+            }
+            const float pk = __fdiv_rn(acc, static_cast<float>(cnt));
+            // classifier.py:63: cdist in double, direct differences
+#pragma unroll
+            for (int q = 0; q < kMaxQ; ++q) {
+                if (q < Q) {
+                    const double df = static_cast<double>(Qp[static_cast<int64_t>(q) * D + k]) - static_cast<double>(pk);
+                    part[q] += df * df;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kMaxQ; ++q) {
+            double v = part[q];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_red[warp][q] = v;
+        }
+        __syncthreads();
+        if (tid < Q) {
+            double v = 0.0;
+            for (int w = 0; w < kProtoThreads / 32; ++w) v += s_red[w][tid];
+            s_d[tid][c] = static_cast<float>(sqrt(v));       // classifier.py:66 float32 cast
+        }
+        __syncthreads();
+    }
+
+    if (tid < Q) {
+        const int q = tid;
+        // classifier.py:67 softmax(-d); :85 first arg-max == first arg-min of the float32 distance
+        float mx = -s_d[q][0]; int best = 0;
+        for (int c = 1; c < np; ++c) { if (-s_d[q][c] > mx) mx = -s_d[q][c]; if (s_d[q][c] < s_d[q][best]) best = c; }
+        float sum = 0.f;
+        for (int c = 0; c < np; ++c) sum += expf(-s_d[q][c] - mx);
+        for (int c = 0; c < max_proto; ++c) {
+            const int64_t o = (e * Q + q) * max_proto + c;
+            if (dist) dist[o] = c < np ? s_d[q][c] : INFINITY;
+            if (prob) prob[o] = c < np ? expf(-s_d[q][c] - mx) / sum : 0.f;
+        }
+        if (pred) pred[e * Q + q] = best;
+    }
+    if (tid == 0 && nproto_out) nproto_out[e] = np;
+}
+
+int launch_proto_score(const float *sup, const float *sup_y, const float *query, int64_t E, int32_t R,
+                       int32_t Q, int32_t D, int32_t max_proto, float *dist, float *prob, int64_t *pred,
+                       int32_t *nproto, cudaStream_t st)
+{
+    if (E == 0) return EOSVR_OK;
+    if (R < 1 || R > kMaxRows || Q < 1 || Q > kMaxQ || max_proto < 1 || max_proto > kMaxProto) {
+        set_error("proto_score: need 1<=R<=%d, 1<=Q<=%d, 1<=max_proto<=%d (got R=%d Q=%d max_proto=%d)",
+                  kMaxRows, kMaxQ, kMaxProto, R, Q, max_proto);
+        return EOSVR_EINVAL;
+    }
+    k_proto_score<<<static_cast<unsigned>(E), kProtoThreads, 0, st>>>(sup, sup_y, query, R, Q, D, max_proto,
+                                                                     dist, prob, pred, nproto);
+    EOSVR_CUDA(cudaGetLastError());
+    return EOSVR_OK;
+}
+
+// One warp per output segment row.
+__global__ void k_segment_features(const float *__restrict__ frames, int64_t N, int seg_len, int D, int l2,
+                                   float *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= N) return;
+    float inv[16];
+    const int sl = seg_len < 16 ? seg_len : 16;
+    for (int f = 0; f < sl; ++f) {
+        float nrm = 1.f;
+        if (l2) {
+            const float *x = frames + (row * seg_len + f) * D;
+            double s = 0.0;
+            for (int k = lane; k < D; k += 32) s += static_cast<double>(x[k]) * static_cast<double>(x[k]);
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            nrm = fmaxf(static_cast<float>(sqrt(s)), 1e-12f);      // F.normalize eps
+        }
+        inv[f] = nrm;
+    }
+    for (int k = lane; k < D; k += 32) {
+        float acc = 0.f;
+        for (int f = 0; f < sl; ++f) {
+            float v = frames[(row * seg_len + f) * D + k];
+            if (l2) v = __fdiv_rn(v, inv[f]);
+            acc = f ? __fadd_rn(acc, v) : v;
+        }
+        out[row * D + k] = __fdiv_rn(acc, static_cast<float>(seg_len));
+    }
+}
+
+int launch_segment_features(const float *frames, int64_t N, int32_t seg_len, int32_t D, int32_t l2,
+                            float *out, cudaStream_t st)
+{
+    if (N == 0) return EOSVR_OK;
+    if (seg_len < 1 || seg_len > 16) { set_error("segment_features: 1 <= seg_len <= 16"); return EOSVR_EINVAL; }
+    const int threads = 256;
+    k_segment_features<<<static_cast<unsigned>((N * 32 + threads - 1) / threads), threads, 0, st>>>(
+        frames, N, seg_len, D, l2, out);
+    EOSVR_CUDA(cudaGetLastError());
+    return EOSVR_OK;
+}
+
+}  // namespace eosvr

@@ -1,0 +1,125 @@
+// eosvr_internal.h -- handle layouts and launch prototypes shared by the translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/eosvr.h"
+
+namespace eosvr {
+
+// ---- tiling constants of the screening kernel ----------------------------------------
+constexpr int kBM = 128;          // gallery rows per tile  (UMMA M, one TMEM lane per row)
+constexpr int kBK = 64;           // K elements per pipeline stage (128-byte rows, SWIZZLE_128B)
+constexpr int kMaxBN = 256;       // probe columns per tile (UMMA N), multiple of 16
+constexpr int kStages = 4;        // TMA -> MMA smem ring
+constexpr int kAccStages = 2;     // TMEM accumulator double buffer (2 x 256 columns)
+constexpr int kTmemCols = 512;
+constexpr int kEpiWarps = 8;      // warps 4..11
+constexpr int kThreads = 128 + 32 * kEpiWarps;
+constexpr int kChunk = 16;        // TMEM columns per tcgen05.ld
+constexpr int kSeedSamples = 16;  // gallery rows sampled to seed the per-probe thresholds
+constexpr float kPadNorm = 1.0e30f;
+
+void set_error(const char *fmt, ...);
+
+#define EOSVR_CUDA(call)                                                                     \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            ::eosvr::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),      \
+                               __FILE__, __LINE__);                                          \
+            return EOSVR_ECUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+// near-minimum candidate handed from the tensor-core screening pass to the exact re-rank
+struct Cand {
+    int32_t p;        // probe row
+    int32_t g;        // gallery row, local to the shard
+    uint32_t tbits;   // screening value (float bits)
+    uint32_t unsafe;  // 1 = inside the cancellation guard (always re-ranked)
+};
+
+struct Counters {
+    unsigned long long cand_count;   // appended (may exceed capacity)
+    unsigned long long n_exact;      // evaluated exactly by the re-rank
+    unsigned long long n_unsafe;
+    unsigned int overflow;           // appends dropped
+    unsigned int n_flag_rows;        // rows sent to the exact fallback
+    unsigned int xfloor_bits;        // max over columns of the cancellation guard (x domain)
+    unsigned int pad;
+};
+
+}  // namespace eosvr
+
+struct eosvr_gallery {
+    const float *feats;      // [G,D] float32, caller-owned
+    int64_t G;
+    int32_t D, Dp;           // Dp = D rounded up to kBK
+    int64_t offset;          // global index of row 0
+    int32_t screen_fmt;
+    void *h16;               // [Gpad, Dp] fp16/bf16 screening copy (Gpad = G rounded up to kBM)
+    float *gnorm;            // [Gpad] ||b||^2 (kPadNorm beyond G)
+    float *scalars;          // [4]: max ||b||^2, max ||b_lo||^2, max ||b_hi||^2 (float bits, >= 0)
+    CUtensorMap tmapA;
+    int device;
+};
+
+struct eosvr_workspace {
+    int64_t maxP;
+    int32_t D, Dp;
+    int64_t cap_rows;        // plan rows capacity
+    int64_t cand_cap;
+    void *slab;              // single device allocation
+    // carved views
+    void *q16;               // [cap_rows, Dp] packed probe plan (16-bit)
+    float *na, *wl, *wr, *margin, *epsd;   // [cap_rows]
+    int32_t *rowmap;         // [cap_rows] emitted probe row or -1
+    unsigned int *gthr;      // [maxP] float bits of the running threshold
+    unsigned long long *best;  // [maxP] packed winners
+    int32_t *rowflag;        // [maxP]
+    int32_t *flaglist;       // [maxP]
+    float *dsamp;            // [maxP, kSeedSamples]
+    eosvr::Cand *cand;       // [cand_cap]
+    eosvr::Counters *counters;
+    float *dbg;              // optional [P,G] dump of screening values (tests)
+    int64_t dbg_elems;
+    // last-call info for eosvr_match_stats
+    int64_t last_tiles;
+    int32_t last_bn;
+    int device;
+};
+
+namespace eosvr {
+
+struct MatchPlan {
+    int64_t P;
+    int32_t rpe;       // rows per episode
+    int32_t R;         // emitted probe rows per tile
+    int32_t halo;      // 0/1 halo column on each side
+    int32_t BN;        // UMMA N (multiple of 16)
+    int64_t NT;        // probe tiles
+};
+
+MatchPlan make_plan(int64_t P, int32_t rpe);
+
+int launch_gallery_prep(eosvr_gallery *g, cudaStream_t st);
+int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int64_t P,
+                 int32_t rpe, float lam1, float lam2, bool exact_only, uint64_t *out_packed,
+                 float *out_score, int64_t *out_idx, cudaStream_t st);
+int launch_merge(const uint64_t *gathered, int32_t nshards, int64_t P, uint64_t *out_packed,
+                 float *out_score, int64_t *out_idx, cudaStream_t st);
+int launch_gather_rows(const eosvr_gallery *g, const int64_t *idx, int64_t P, float *out, cudaStream_t st);
+int launch_splice(const float *probes, const float *wrows, int64_t E, int32_t n, int32_t S, int32_t D,
+                  int32_t orig_mode, float *out, cudaStream_t st);
+int launch_proto_score(const float *sup, const float *sup_y, const float *query, int64_t E, int32_t R,
+                       int32_t Q, int32_t D, int32_t max_proto, float *dist, float *prob, int64_t *pred,
+                       int32_t *nproto, cudaStream_t st);
+int launch_segment_features(const float *frames, int64_t N, int32_t seg_len, int32_t D, int32_t l2,
+                            float *out, cudaStream_t st);
+int encode_tmap_2d(CUtensorMap *m, const void *base, int fmt, uint64_t rows, uint64_t cols,
+                   uint32_t box_rows, uint32_t box_cols);
+
+}  // namespace eosvr

@@ -1,0 +1,842 @@
+// eosvr_match.cu -- segment matching (replaces network_test.py:208-212 of the reference):
+//   cdist(probe, gallery, 'euclidean') [fp64] -> float32 -> [lam1,lam2,lam1] taps along the
+//   probe axis (zero padded per episode) -> arg-min per probe row, lowest index on ties.
+//
+// Two cooperating parts, neither of which ever writes the [P,G] matrix:
+//   1. SCREENING (k_match_screen): a persistent, warp-specialised tcgen05 kernel.  Gallery
+//      rows ride the UMMA M axis (one TMEM lane = one gallery row), probe segments ride N, so
+//      every epilogue thread owns one gallery row and sees consecutive probe segments in
+//      consecutive registers: the temporal 3-tap is register-local.  The epilogue forms
+//      d = sqrt(|a|^2 + |b|^2 - 2 a.b), the taps, and compares against a per-probe running
+//      threshold (min so far + rigorous error margin); the few elements below it are
+//      appended to a candidate list.
+//   2. EXACT RE-RANK (k_rerank): every candidate is re-evaluated on CUDA cores exactly as
+//      the reference does (float64 direct differences, float32 cast, float32 FMA chain) and
+//      merged with a packed 64-bit atomicMin whose low word is the gallery index, which
+//      gives the lowest-index tie rule for free.
+// The error margin guarantees the true winner (and every exact tie) is among the candidates,
+// so indices and scores are bit-equal to the reference, not merely close.
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "eosvr_internal.h"
+#include "eosvr_ptx.cuh"
+
+namespace eosvr {
+
+using namespace ptx;
+
+constexpr float kBig = 1.0e30f;
+constexpr float kSlopMul = 1.0f + 1.0f / 65536.0f;   // covers fp32 rounding of the screening taps / sqrt.approx
+
+__device__ __forceinline__ unsigned long long pack_score_idx(float t, uint32_t gidx)
+{
+    uint32_t b = __float_as_uint(t);
+    b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);          // order-preserving float -> uint
+    return (static_cast<unsigned long long>(b) << 32) | gidx;
+}
+__device__ __forceinline__ float unpack_score(unsigned long long v)
+{
+    uint32_t b = static_cast<uint32_t>(v >> 32);
+    b = (b & 0x80000000u) ? (b & 0x7FFFFFFFu) : ~b;
+    return __uint_as_float(b);
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// -------------------------------------------------------------------------------------------
+// Gallery cache build (off the timed path): 16-bit screening copy, squared norms, bound scalars.
+// One warp per gallery row.
+// -------------------------------------------------------------------------------------------
+template <typename T16>
+__device__ __forceinline__ T16 to16(float x);
+template <>
+__device__ __forceinline__ __half to16<__half>(float x) { return __float2half_rn(x); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 to16<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+__device__ __forceinline__ float from16(__half x) { return __half2float(x); }
+__device__ __forceinline__ float from16(__nv_bfloat16 x) { return __bfloat162float(x); }
+
+__device__ __forceinline__ void atomic_max_posf(float *addr, float v)
+{
+    atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
+}
+
+template <typename T16>
+__global__ void k_gallery_prep(const float *__restrict__ feats, int64_t G, int64_t Gpad, int D, int Dp,
+                               T16 *__restrict__ h16, float *__restrict__ gnorm, float *__restrict__ scalars)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= Gpad) return;
+    T16 *dst = h16 + row * Dp;
+    if (row >= G) {
+        for (int k = lane; k < Dp; k += 32) dst[k] = to16<T16>(0.f);
+        if (lane == 0) gnorm[row] = kPadNorm;
+        return;
+    }
+    const float *src = feats + row * D;
+    double s = 0.0, sh = 0.0, sl = 0.0;
+    for (int k = lane; k < Dp; k += 32) {
+        float x = k < D ? src[k] : 0.f;
+        T16 h = to16<T16>(x);
+        dst[k] = h;
+        double xd = x, hd = from16(h);
+        s += xd * xd;
+        sh += hd * hd;
+        sl += (xd - hd) * (xd - hd);
+    }
+    s = warp_sum(s); sh = warp_sum(sh); sl = warp_sum(sl);
+    if (lane == 0) {
+        gnorm[row] = static_cast<float>(s);
+        atomic_max_posf(scalars + 0, __double2float_ru(s));
+        atomic_max_posf(scalars + 1, __double2float_ru(sl));
+        atomic_max_posf(scalars + 2, __double2float_ru(sh));
+    }
+}
+
+int launch_gallery_prep(eosvr_gallery *g, cudaStream_t st)
+{
+    const int64_t Gpad = (g->G + kBM - 1) / kBM * kBM;
+    EOSVR_CUDA(cudaMemsetAsync(g->scalars, 0, 4 * sizeof(float), st));
+    const int threads = 256;
+    const int64_t blocks = (Gpad * 32 + threads - 1) / threads;
+    if (g->screen_fmt == EOSVR_SCREEN_F16)
+        k_gallery_prep<__half><<<static_cast<unsigned>(blocks), threads, 0, st>>>(
+            g->feats, g->G, Gpad, g->D, g->Dp, static_cast<__half *>(g->h16), g->gnorm, g->scalars);
+    else
+        k_gallery_prep<__nv_bfloat16><<<static_cast<unsigned>(blocks), threads, 0, st>>>(
+            g->feats, g->G, Gpad, g->D, g->Dp, static_cast<__nv_bfloat16 *>(g->h16), g->gnorm, g->scalars);
+    EOSVR_CUDA(cudaGetLastError());
+    return EOSVR_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// Probe plan.  Probe rows are laid out as NT tiles of BN columns; tile t emits probe rows
+// [t*R, (t+1)*R).  When an episode fits a tile (rpe <= 256) R is a whole number of episodes and
+// no halo is needed; otherwise each tile carries one halo column on each side so the taps of its
+// first/last emitted row see their neighbours.
+// -------------------------------------------------------------------------------------------
+MatchPlan make_plan(int64_t P, int32_t rpe)
+{
+    MatchPlan pl;
+    pl.P = P;
+    pl.rpe = rpe;
+    if (rpe <= kMaxBN) {
+        int64_t k = kMaxBN / rpe;
+        pl.R = static_cast<int32_t>(k * rpe);
+        pl.halo = 0;
+    } else {
+        pl.R = kMaxBN - 2;
+        pl.halo = 1;
+    }
+    if (pl.R > P) pl.R = static_cast<int32_t>(P);
+    pl.BN = (pl.R + 2 * pl.halo + 15) / 16 * 16;
+    pl.NT = (P + pl.R - 1) / pl.R;
+    return pl;
+}
+
+struct PlanDev {
+    int64_t P;
+    int32_t rpe, R, halo, BN;
+    int64_t NT;
+};
+
+__device__ __forceinline__ int64_t plan_row_of(const PlanDev &pl, int64_t col, bool &valid, bool &emit)
+{
+    const int64_t t = col / pl.BN;
+    const int c = static_cast<int>(col % pl.BN);
+    const int jj = c - pl.halo;
+    const int64_t p = t * pl.R + jj;
+    valid = (c < pl.R + 2 * pl.halo) && p >= 0 && p < pl.P;
+    emit = valid && jj >= 0 && jj < pl.R;
+    return p;
+}
+
+// One warp per plan column: convert the probe row to the 16-bit screening format, compute the
+// squared norm and the per-column error bound E2 (see DESIGN.md "Error bound").
+template <typename T16>
+__global__ void k_probe_prep(const float *__restrict__ probes, PlanDev pl, int D, int Dp,
+                             const float *__restrict__ gscal, T16 *__restrict__ q16,
+                             float *__restrict__ na, float *__restrict__ epsd, int32_t *__restrict__ rowmap,
+                             Counters *ctr)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t col = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (col >= pl.NT * pl.BN) return;
+    bool valid, emit;
+    const int64_t p = plan_row_of(pl, col, valid, emit);
+    T16 *dst = q16 + col * Dp;
+    if (!valid) {
+        for (int k = lane; k < Dp; k += 32) dst[k] = to16<T16>(0.f);
+        if (lane == 0) { na[col] = kPadNorm; epsd[col] = 0.f; rowmap[col] = -1; }
+        return;
+    }
+    const float *src = probes + p * D;
+    double s = 0.0, sh = 0.0, sl = 0.0;
+    for (int k = lane; k < Dp; k += 32) {
+        float x = k < D ? src[k] : 0.f;
+        T16 h = to16<T16>(x);
+        dst[k] = h;
+        double xd = x, hd = from16(h);
+        s += xd * xd;
+        sh += hd * hd;
+        sl += (xd - hd) * (xd - hd);
+    }
+    s = warp_sum(s); sh = warp_sum(sh); sl = warp_sum(sl);
+    if (lane == 0) {
+        const double B2 = gscal[0], Bl2 = gscal[1], Bh2 = gscal[2];
+        const double ulp = 1.0 / 4194304.0;   // 2^-22
+        // |x~ - x| <= 2(|a_lo||b| + |a_hi||b_lo|) + tensor-core accumulation + fp32 rounding
+        double e2 = 2.0 * (sqrt(sl * B2) + sqrt(sh * Bl2))
+                  + 2.0 * ulp * (Dp / 16 + 1) * sqrt(sh * Bh2)
+                  + 2.0 * ulp * (s + B2);
+        e2 *= 1.01;
+        if (e2 < 1e-30) e2 = 1e-30;
+        na[col] = static_cast<float>(s);
+        epsd[col] = __double2float_ru(sqrt(e2) / 16.0);           // E2 / (2 sqrt(64 E2))
+        rowmap[col] = emit ? static_cast<int32_t>(p) : -1;
+        atomicMax(&ctr->xfloor_bits, __float_as_uint(__double2float_ru(65.0 * e2)));
+    }
+}
+
+// Distances of every probe row to kSeedSamples strided gallery rows (fp32 inputs, fp32 math):
+// upper bounds that seed the running thresholds.
+__global__ void k_seed_dist(const float *__restrict__ probes, int64_t P, int D,
+                            const float *__restrict__ gal, int64_t G, float *__restrict__ dsamp)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (w >= P * kSeedSamples) return;
+    const int64_t p = w / kSeedSamples;
+    const int s = static_cast<int>(w % kSeedSamples);
+    const int64_t g = (G * s) / kSeedSamples;
+    const float *a = probes + p * D, *b = gal + g * D;
+    double acc = 0.0;
+    for (int k = lane; k < D; k += 32) { double df = static_cast<double>(a[k]) - static_cast<double>(b[k]); acc += df * df; }
+    acc = warp_sum(acc);
+    if (lane == 0) dsamp[w] = static_cast<float>(sqrt(acc));
+}
+
+// Thread per plan column: tap weights and threshold margin; thread per probe row: seed threshold.
+__global__ void k_column_plan(PlanDev pl, float w, const float *__restrict__ epsd,
+                              float *__restrict__ wl, float *__restrict__ wr, float *__restrict__ margin,
+                              const float *__restrict__ dsamp, unsigned int *__restrict__ gthr)
+{
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t ncol = pl.NT * pl.BN;
+    if (i < ncol) {
+        bool valid, emit;
+        const int64_t p = plan_row_of(pl, i, valid, emit);
+        const int c = static_cast<int>(i % pl.BN);
+        float l = 0.f, r = 0.f, el = 0.f, er = 0.f;
+        if (valid) {
+            if (c > 0 && p > 0 && (p % pl.rpe) != 0) { l = w; el = epsd[i - 1]; }
+            if (c + 1 < pl.BN && p + 1 < pl.P && ((p + 1) % pl.rpe) != 0) {
+                bool v2, e2;
+                plan_row_of(pl, i + 1, v2, e2);
+                if (v2) { r = w; er = epsd[i + 1]; }
+            }
+        }
+        wl[i] = l; wr[i] = r;
+        margin[i] = valid ? 2.02f * (epsd[i] + l * el + r * er) + 1e-7f : 0.f;
+    }
+    if (i < pl.P) {
+        const int64_t p = i;
+        const int r = static_cast<int>(p % pl.rpe);
+        const bool hl = r > 0, hr = (r + 1 < pl.rpe) && (p + 1 < pl.P);
+        float best = kBig;
+        for (int s = 0; s < kSeedSamples; ++s) {
+            float t = dsamp[p * kSeedSamples + s];
+            if (hl) t = fmaf(w, dsamp[(p - 1) * kSeedSamples + s], t);
+            if (hr) t = fmaf(w, dsamp[(p + 1) * kSeedSamples + s], t);
+            best = fminf(best, t);
+        }
+        // margin of p's own column
+        const int64_t col = (p / pl.R) * pl.BN + pl.halo + (p % pl.R);
+        float e = epsd[col];
+        float el = hl ? epsd[col - 1] : 0.f, er = hr ? epsd[col + 1] : 0.f;
+        float m = 2.02f * (e + w * (el + er)) + 1e-7f;
+        gthr[p] = __float_as_uint(fmaf(best, kSlopMul, m));
+    }
+}
+
+__global__ void k_reset(Counters *ctr, unsigned long long *best, int32_t *rowflag, int64_t P, int flag_all)
+{
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        ctr->cand_count = 0; ctr->n_exact = 0; ctr->n_unsafe = 0;
+        ctr->overflow = flag_all ? 1u : 0u; ctr->n_flag_rows = 0; ctr->xfloor_bits = 0; ctr->pad = 0;
+    }
+    if (i < P) { best[i] = ~0ull; rowflag[i] = flag_all; }
+}
+
+// -------------------------------------------------------------------------------------------
+// Screening kernel
+// -------------------------------------------------------------------------------------------
+struct ScreenParams {
+    const float *gnorm;
+    int64_t G;
+    int32_t KB;             // K blocks of 64 elements
+    int32_t BN;
+    int64_t NT, GT;
+    int32_t TPU;            // gallery tiles per work unit
+    int64_t cps;            // work-unit chunks per L2 slab
+    int64_t n_chunks;       // total gallery chunks
+    int64_t n_units;
+    const float *na, *wl, *wr, *margin;
+    const int32_t *rowmap;
+    unsigned int *gthr;
+    Cand *cand;
+    int64_t cand_cap;
+    Counters *ctr;
+    int32_t *rowflag;
+    uint32_t idesc;
+    float *dbg;             // optional [P,G] dump of the screening values
+};
+
+struct __align__(16) ScreenSmemTail {
+    float na[kMaxBN];
+    float wl[kMaxBN];
+    float wr[kMaxBN];
+    float mg[kMaxBN];
+    unsigned int thr[kMaxBN];
+    int32_t row[kMaxBN];
+    uint64_t full[kStages];
+    uint64_t empty[kStages];
+    uint64_t tfull[kAccStages];
+    uint64_t tempty[kAccStages];
+    uint32_t tmem_base;
+};
+
+constexpr int kABytes = kBM * kBK * 2;          // 16 KiB
+constexpr int kBBytes = kMaxBN * kBK * 2;       // 32 KiB
+constexpr size_t kScreenSmem = 1024 + static_cast<size_t>(kStages) * (kABytes + kBBytes) + sizeof(ScreenSmemTail);
+
+struct UnitIter {
+    int64_t u, jt, gt0, gt1;
+};
+
+__device__ __forceinline__ bool decode_unit(const ScreenParams &p, int64_t u, UnitIter &it)
+{
+    const int64_t ups = p.NT * p.cps;
+    const int64_t slab = u / ups, r = u % ups;
+    it.u = u;
+    it.jt = r / p.cps;
+    const int64_t chunk = slab * p.cps + (r % p.cps);
+    if (chunk >= p.n_chunks) return false;
+    it.gt0 = chunk * p.TPU;
+    it.gt1 = min(it.gt0 + p.TPU, p.GT);
+    return it.gt0 < it.gt1;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const ScreenParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + kStages * kABytes;
+    ScreenSmemTail *tl = reinterpret_cast<ScreenSmemTail *>(smem + kStages * (kABytes + kBBytes));
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&tl->full[s], 1); mbar_init(&tl->empty[s], 1); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tl->tfull[s], 1); mbar_init(&tl->tempty[s], 32 * kEpiWarps); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(&tl->tmem_base, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tl->tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t tx = kABytes + static_cast<uint32_t>(p.BN) * kBK * 2;
+            for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+                UnitIter it;
+                if (!decode_unit(p, u, it)) continue;
+                for (int64_t gt = it.gt0; gt < it.gt1; ++gt) {
+                    for (int kb = 0; kb < p.KB; ++kb) {
+                        mbar_wait(&tl->empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&tl->full[stage], tx);
+                        tma_load_2d(sA + stage * kABytes, &tmA, &tl->full[stage], kb * kBK,
+                                    static_cast<int32_t>(gt * kBM));
+                        tma_load_2d(sB + stage * kBBytes, &tmB, &tl->full[stage], kb * kBK,
+                                    static_cast<int32_t>(it.jt * p.BN));
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t accphase = 0;
+            for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+                UnitIter it;
+                if (!decode_unit(p, u, it)) continue;
+                for (int64_t gt = it.gt0; gt < it.gt1; ++gt) {
+                    mbar_wait(&tl->tempty[acc], accphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * kMaxBN;
+                    for (int kb = 0; kb < p.KB; ++kb) {
+                        mbar_wait(&tl->full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a0 = smem_u32(sA + stage * kABytes);
+                        const uint32_t b0 = smem_u32(sB + stage * kBBytes);
+#pragma unroll
+                        for (int k = 0; k < kBK / 16; ++k)
+                            mma_f16_ss(d_tmem, umma_desc_sw128(a0, k * 32), umma_desc_sw128(b0, k * 32),
+                                       p.idesc, (kb | k) != 0 ? 1u : 0u);
+                        mma_commit(&tl->empty[stage]);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                    mma_commit(&tl->tfull[acc]);
+                    if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: 8 warps, warp%4 selects the TMEM lane quadrant, (warp-4)/4 the column half =====
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int te = threadIdx.x - 128;
+        const int BN = p.BN;
+        const int nchunks = BN / kChunk;
+        const int hc = (nchunks + 1) >> 1;
+        const int cbeg = half == 0 ? 0 : hc;
+        const int cend = half == 0 ? hc : nchunks;
+        const float xfloor = __uint_as_float(p.ctr->xfloor_bits);
+        const float dfloor = sqrtf(xfloor) * 1.000001f;
+        int acc = 0; uint32_t accphase = 0;
+        for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+            UnitIter it;
+            if (!decode_unit(p, u, it)) continue;
+            // per-unit column arrays -> smem
+            named_bar_sync(1, 32 * kEpiWarps);
+            if (te < BN) {
+                const int64_t c = it.jt * BN + te;
+                tl->na[te] = p.na[c];
+                tl->wl[te] = p.wl[c];
+                tl->wr[te] = p.wr[c];
+                tl->mg[te] = p.margin[c];
+                const int32_t rm = p.rowmap[c];
+                tl->row[te] = rm;
+                tl->thr[te] = rm >= 0 ? *reinterpret_cast<volatile unsigned int *>(p.gthr + rm)
+                                      : __float_as_uint(-1.0f);
+            }
+            named_bar_sync(1, 32 * kEpiWarps);
+
+            for (int64_t gt = it.gt0; gt < it.gt1; ++gt) {
+                mbar_wait(&tl->tfull[acc], accphase);
+                tc_fence_after();
+                const int64_t g = gt * kBM + q * 32 + lane;
+                const float nb = p.gnorm[g];
+                const uint32_t trow = tmem_base + static_cast<uint32_t>(acc) * kMaxBN + (static_cast<uint32_t>(q * 32) << 16);
+
+                float dprev = kBig;
+                if (cbeg > 0) {
+                    uint32_t v;
+                    tmem_ld_x1(trow + cbeg * kChunk - 1, v);
+                    tmem_ld_wait();
+                    const float x = fmaf(-2.f, __uint_as_float(v), nb) + tl->na[cbeg * kChunk - 1];
+                    dprev = sqrt_approx(fmaxf(x, 0.f));
+                }
+                for (int ch = cbeg; ch < cend; ++ch) {
+                    const int c0 = ch * kChunk;
+                    uint32_t v[kChunk];
+                    tmem_ld_x16(trow + c0, v);
+                    uint32_t vn = 0;
+                    const bool hasn = (c0 + kChunk) < BN;
+                    if (hasn) tmem_ld_x1(trow + c0 + kChunk, vn);
+                    tmem_ld_wait();
+
+                    float d[kChunk];
+                    float minx = kBig;
+                    const float4 *na4 = reinterpret_cast<const float4 *>(tl->na + c0);
+#pragma unroll
+                    for (int j4 = 0; j4 < kChunk / 4; ++j4) {
+                        const float4 a = na4[j4];
+                        const float aa[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = j4 * 4 + jj;
+                            const float x = fmaf(-2.f, __uint_as_float(v[j]), nb) + aa[jj];
+                            minx = fminf(minx, x);
+                            d[j] = sqrt_approx(fmaxf(x, 0.f));
+                        }
+                    }
+                    float dn = kBig;
+                    if (hasn) {
+                        const float x = fmaf(-2.f, __uint_as_float(vn), nb) + tl->na[c0 + kChunk];
+                        dn = sqrt_approx(fmaxf(x, 0.f));
+                    }
+                    const float dprev_in = dprev;
+                    dprev = d[kChunk - 1];
+
+                    bool any = false;
+                    float t[kChunk];
+                    const float4 *wl4 = reinterpret_cast<const float4 *>(tl->wl + c0);
+                    const float4 *wr4 = reinterpret_cast<const float4 *>(tl->wr + c0);
+                    const float4 *th4 = reinterpret_cast<const float4 *>(tl->thr + c0);
+#pragma unroll
+                    for (int j4 = 0; j4 < kChunk / 4; ++j4) {
+                        const float4 l = wl4[j4], r = wr4[j4], th = th4[j4];
+                        const float ll[4] = {l.x, l.y, l.z, l.w};
+                        const float rr[4] = {r.x, r.y, r.z, r.w};
+                        const float tt[4] = {th.x, th.y, th.z, th.w};
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = j4 * 4 + jj;
+                            const float dl = j ? d[j - 1] : dprev_in;
+                            const float dr = (j < kChunk - 1) ? d[j + 1] : dn;
+                            t[j] = fmaf(ll[jj], dl, fmaf(rr[jj], dr, d[j]));
+                            any |= (t[j] <= tt[jj]);
+                        }
+                    }
+                    const bool need = any || (minx < xfloor) || (fminf(dprev_in, dn) < dfloor);
+                    if (__any_sync(0xffffffffu, need)) {
+                        // ---- rare path: append candidates, tighten thresholds ----
+                        if (need && g < p.G) {
+#pragma unroll
+                            for (int j = 0; j < kChunk; ++j) {
+                                const int c = c0 + j;
+                                const int32_t rm = tl->row[c];
+                                if (rm < 0) continue;
+                                const float dl = j ? d[j - 1] : dprev_in;
+                                const float dr = (j < kChunk - 1) ? d[j + 1] : dn;
+                                const float m3 = fminf(d[j], fminf(tl->wl[c] > 0.f ? dl : kBig,
+                                                                   tl->wr[c] > 0.f ? dr : kBig));
+                                const bool uns = m3 < dfloor;
+                                const float thr = __uint_as_float(*reinterpret_cast<volatile unsigned int *>(&tl->thr[c]));
+                                if (uns || t[j] <= thr) {
+                                    const unsigned long long pos = atomicAdd(&p.ctr->cand_count, 1ull);
+                                    if (pos < static_cast<unsigned long long>(p.cand_cap)) {
+                                        Cand cd;
+                                        cd.p = rm; cd.g = static_cast<int32_t>(g);
+                                        cd.tbits = __float_as_uint(t[j]); cd.unsafe = uns ? 1u : 0u;
+                                        p.cand[pos] = cd;
+                                    } else {
+                                        p.rowflag[rm] = 1;
+                                        atomicAdd(&p.ctr->overflow, 1u);
+                                    }
+                                    if (!uns) {
+                                        const unsigned int nb2 = __float_as_uint(fmaf(t[j], kSlopMul, tl->mg[c]));
+                                        atomicMin(&tl->thr[c], nb2);
+                                        atomicMin(p.gthr + rm, nb2);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (p.dbg != nullptr && g < p.G) {
+#pragma unroll
+                        for (int j = 0; j < kChunk; ++j) {
+                            const int32_t rm = tl->row[c0 + j];
+                            if (rm >= 0) p.dbg[static_cast<int64_t>(rm) * p.G + g] = t[j];
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tl->tempty[acc]);
+                if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// -------------------------------------------------------------------------------------------
+// Exact evaluation (the reference's arithmetic): network_test.py:208 (scipy cdist, float64 direct
+// differences), :109 (float32 cast), models.py:42-56 taps as the float32 FMA chain
+//   acc = lam1*d[p-1];  acc = fma(lam2, d[p], acc);  acc = fma(lam1, d[p+1], acc)
+// with zero padding at episode ends.  Warp-cooperative; all lanes return the value.
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ float exact_t(const float *__restrict__ probes, int64_t P, int D, int rpe,
+                                         int64_t p, const float *__restrict__ b, float lam1, float lam2, int lane)
+{
+    const int r = static_cast<int>(p % rpe);
+    const bool hl = r > 0, hr = (r + 1 < rpe) && (p + 1 < P);
+    const float *a1 = probes + p * D;
+    const float *a0 = hl ? a1 - D : a1;
+    const float *a2 = hr ? a1 + D : a1;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int k = lane; k < D; k += 32) {
+        const double bv = b[k];
+        const double e0 = static_cast<double>(a0[k]) - bv;
+        const double e1 = static_cast<double>(a1[k]) - bv;
+        const double e2 = static_cast<double>(a2[k]) - bv;
+        s0 += e0 * e0; s1 += e1 * e1; s2 += e2 * e2;
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    const float d0 = hl ? static_cast<float>(sqrt(s0)) : 0.f;
+    const float d1 = static_cast<float>(sqrt(s1));
+    const float d2 = hr ? static_cast<float>(sqrt(s2)) : 0.f;
+    float acc = __fmul_rn(lam1, d0);
+    acc = __fmaf_rn(lam2, d1, acc);
+    acc = __fmaf_rn(lam1, d2, acc);
+    return acc;
+}
+
+struct RerankParams {
+    const float *probes;
+    const float *gal;
+    int64_t P, G, offset;
+    int32_t D, rpe;
+    float lam1, lam2;
+    const Cand *cand;
+    int64_t cand_cap;
+    Counters *ctr;
+    const unsigned int *gthr;
+    unsigned long long *best;
+    int32_t *rowflag;
+    int32_t *flaglist;
+};
+
+__global__ void k_rerank(const RerankParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long cnt = p.ctr->cand_count;
+    const int64_t n = cnt < static_cast<unsigned long long>(p.cand_cap) ? static_cast<int64_t>(cnt) : p.cand_cap;
+    unsigned long long done = 0, uns = 0;
+    for (; w < n; w += nw) {
+        const Cand c = p.cand[w];
+        if (!c.unsafe && __uint_as_float(c.tbits) > __uint_as_float(p.gthr[c.p])) continue;
+        const float t = exact_t(p.probes, p.P, p.D, p.rpe, c.p, p.gal + static_cast<int64_t>(c.g) * p.D,
+                                p.lam1, p.lam2, lane);
+        if (lane == 0) {
+            atomicMin(p.best + c.p, pack_score_idx(t, static_cast<uint32_t>(p.offset + c.g)));
+            ++done; uns += c.unsafe;
+        }
+    }
+    if (lane == 0 && done) { atomicAdd(&p.ctr->n_exact, done); atomicAdd(&p.ctr->n_unsafe, uns); }
+}
+
+// Rows whose candidates overflowed the list (or all rows, for eosvr_match_exact) are resolved by
+// exhaustive exact evaluation.  Early exit when nothing overflowed.
+__global__ void k_compact_flags(const RerankParams p)
+{
+    if (p.ctr->overflow == 0) return;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.P;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        if (p.rowflag[i]) {
+            const unsigned int pos = atomicAdd(&p.ctr->n_flag_rows, 1u);
+            p.flaglist[pos] = static_cast<int32_t>(i);
+        }
+    }
+}
+
+constexpr int kStrip = 64;   // gallery rows per warp work item in the exhaustive kernel
+
+__global__ void k_exact_fallback(const RerankParams p)
+{
+    if (p.ctr->overflow == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nrows = p.ctr->n_flag_rows;
+    const int64_t nstrips = (p.G + kStrip - 1) / kStrip;
+    for (; w < nrows * nstrips; w += nw) {
+        const int64_t row = p.flaglist[w / nstrips];
+        const int64_t g0 = (w % nstrips) * kStrip, g1 = min(g0 + kStrip, p.G);
+        unsigned long long loc = ~0ull;
+        for (int64_t g = g0; g < g1; ++g) {
+            const float t = exact_t(p.probes, p.P, p.D, p.rpe, row, p.gal + g * p.D, p.lam1, p.lam2, lane);
+            const unsigned long long v = pack_score_idx(t, static_cast<uint32_t>(p.offset + g));
+            loc = v < loc ? v : loc;
+        }
+        if (lane == 0) atomicMin(p.best + row, loc);
+    }
+}
+
+__global__ void k_finalize(const unsigned long long *__restrict__ best, int64_t P,
+                           uint64_t *out_packed, float *out_score, int64_t *out_idx)
+{
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const unsigned long long v = best[i];
+    if (out_packed) out_packed[i] = v;
+    if (out_score) out_score[i] = (v == ~0ull) ? __int_as_float(0x7fc00000) : unpack_score(v);
+    if (out_idx) out_idx[i] = (v == ~0ull) ? -1 : static_cast<int64_t>(v & 0xFFFFFFFFull);
+}
+
+__global__ void k_merge_top1(const unsigned long long *__restrict__ gathered, int nshards, int64_t P,
+                             uint64_t *out_packed, float *out_score, int64_t *out_idx)
+{
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    unsigned long long v = ~0ull;
+    for (int s = 0; s < nshards; ++s) {
+        const unsigned long long x = gathered[static_cast<int64_t>(s) * P + i];
+        v = x < v ? x : v;
+    }
+    if (out_packed) out_packed[i] = v;
+    if (out_score) out_score[i] = (v == ~0ull) ? __int_as_float(0x7fc00000) : unpack_score(v);
+    if (out_idx) out_idx[i] = (v == ~0ull) ? -1 : static_cast<int64_t>(v & 0xFFFFFFFFull);
+}
+
+int launch_merge(const uint64_t *gathered, int32_t nshards, int64_t P, uint64_t *out_packed,
+                 float *out_score, int64_t *out_idx, cudaStream_t st)
+{
+    if (P == 0) return EOSVR_OK;
+    const int threads = 256;
+    k_merge_top1<<<static_cast<unsigned>((P + threads - 1) / threads), threads, 0, st>>>(
+        reinterpret_cast<const unsigned long long *>(gathered), nshards, P, out_packed, out_score, out_idx);
+    EOSVR_CUDA(cudaGetLastError());
+    return EOSVR_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// Host orchestration of one eosvr_match call (all asynchronous on `st`).
+// -------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+
+int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int64_t P,
+                 int32_t rpe, float lam1, float lam2, bool exact_only, uint64_t *out_packed,
+                 float *out_score, int64_t *out_idx, cudaStream_t st)
+{
+    if (P == 0) return EOSVR_OK;
+    if (g_num_sms == 0) {
+        int dev = 0;
+        EOSVR_CUDA(cudaGetDevice(&dev));
+        EOSVR_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const MatchPlan pl = make_plan(P, rpe);
+    const int64_t ncol = pl.NT * pl.BN;
+    if (ncol > ws->cap_rows) {
+        set_error("workspace too small: plan needs %lld rows, capacity %lld", (long long)ncol, (long long)ws->cap_rows);
+        return EOSVR_EINVAL;
+    }
+    PlanDev pd{pl.P, pl.rpe, pl.R, pl.halo, pl.BN, pl.NT};
+    const int threads = 256;
+
+    k_reset<<<static_cast<unsigned>((P + threads - 1) / threads), threads, 0, st>>>(
+        ws->counters, ws->best, ws->rowflag, P, exact_only ? 1 : 0);
+    EOSVR_CUDA(cudaGetLastError());
+
+    RerankParams rp;
+    rp.probes = probes; rp.gal = g->feats; rp.P = P; rp.G = g->G; rp.offset = g->offset;
+    rp.D = g->D; rp.rpe = rpe; rp.lam1 = lam1; rp.lam2 = lam2;
+    rp.cand = ws->cand; rp.cand_cap = ws->cand_cap; rp.ctr = ws->counters; rp.gthr = ws->gthr;
+    rp.best = ws->best; rp.rowflag = ws->rowflag; rp.flaglist = ws->flaglist;
+
+    ws->last_tiles = 0;
+    ws->last_bn = pl.BN;
+    if (!exact_only) {
+        const unsigned pblocks = static_cast<unsigned>((ncol * 32 + threads - 1) / threads);
+        if (g->screen_fmt == EOSVR_SCREEN_F16)
+            k_probe_prep<__half><<<pblocks, threads, 0, st>>>(probes, pd, g->D, g->Dp, g->scalars,
+                static_cast<__half *>(ws->q16), ws->na, ws->epsd, ws->rowmap, ws->counters);
+        else
+            k_probe_prep<__nv_bfloat16><<<pblocks, threads, 0, st>>>(probes, pd, g->D, g->Dp, g->scalars,
+                static_cast<__nv_bfloat16 *>(ws->q16), ws->na, ws->epsd, ws->rowmap, ws->counters);
+        EOSVR_CUDA(cudaGetLastError());
+        k_seed_dist<<<static_cast<unsigned>((P * kSeedSamples * 32 + threads - 1) / threads), threads, 0, st>>>(
+            probes, P, g->D, g->feats, g->G, ws->dsamp);
+        EOSVR_CUDA(cudaGetLastError());
+        const int64_t nthr = ncol > P ? ncol : P;
+        k_column_plan<<<static_cast<unsigned>((nthr + threads - 1) / threads), threads, 0, st>>>(
+            pd, lam1 / lam2, ws->epsd, ws->wl, ws->wr, ws->margin, ws->dsamp, ws->gthr);
+        EOSVR_CUDA(cudaGetLastError());
+
+        CUtensorMap tmB;
+        int rc = encode_tmap_2d(&tmB, ws->q16, g->screen_fmt, static_cast<uint64_t>(ncol),
+                                static_cast<uint64_t>(g->Dp), static_cast<uint32_t>(pl.BN), kBK);
+        if (rc) return rc;
+
+        ScreenParams sp;
+        sp.gnorm = g->gnorm; sp.G = g->G; sp.KB = g->Dp / kBK; sp.BN = pl.BN; sp.NT = pl.NT;
+        sp.GT = (g->G + kBM - 1) / kBM;
+        const int64_t total_tiles = sp.NT * sp.GT;
+        int64_t tpu = total_tiles / (static_cast<int64_t>(g_num_sms) * 6);
+        if (tpu < 1) tpu = 1;
+        if (tpu > 32) tpu = 32;
+        sp.TPU = static_cast<int32_t>(tpu);
+        sp.n_chunks = (sp.GT + tpu - 1) / tpu;
+        int64_t slab_tiles = (static_cast<int64_t>(48) << 20) / (static_cast<int64_t>(kBM) * g->Dp * 2);
+        int64_t cps = slab_tiles / tpu;
+        if (cps < 1) cps = 1;
+        if (cps > sp.n_chunks) cps = sp.n_chunks;
+        sp.cps = cps;
+        const int64_t n_slabs = (sp.n_chunks + cps - 1) / cps;
+        sp.n_units = n_slabs * sp.NT * cps;
+        sp.na = ws->na; sp.wl = ws->wl; sp.wr = ws->wr; sp.margin = ws->margin; sp.rowmap = ws->rowmap;
+        sp.gthr = ws->gthr; sp.cand = ws->cand; sp.cand_cap = ws->cand_cap; sp.ctr = ws->counters;
+        sp.rowflag = ws->rowflag;
+        sp.idesc = umma_idesc_f16(g->screen_fmt == EOSVR_SCREEN_F16 ? 0 : 1, kBM, pl.BN);
+        sp.dbg = (ws->dbg && ws->dbg_elems >= P * g->G) ? ws->dbg : nullptr;
+        ws->last_tiles = total_tiles;
+
+        static bool attr_set = false;
+        if (!attr_set) {
+            EOSVR_CUDA(cudaFuncSetAttribute(k_match_screen, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(kScreenSmem)));
+            attr_set = true;
+        }
+        const unsigned grid = static_cast<unsigned>(sp.n_units < g_num_sms ? sp.n_units : g_num_sms);
+        k_match_screen<<<grid, kThreads, kScreenSmem, st>>>(g->tmapA, tmB, sp);
+        EOSVR_CUDA(cudaGetLastError());
+
+        k_rerank<<<g_num_sms * 4, 256, 0, st>>>(rp);
+        EOSVR_CUDA(cudaGetLastError());
+    }
+    k_compact_flags<<<64, 256, 0, st>>>(rp);
+    EOSVR_CUDA(cudaGetLastError());
+    k_exact_fallback<<<g_num_sms * 8, 256, 0, st>>>(rp);
+    EOSVR_CUDA(cudaGetLastError());
+    k_finalize<<<static_cast<unsigned>((P + threads - 1) / threads), threads, 0, st>>>(
+        ws->best, P, out_packed, out_score, out_idx);
+    EOSVR_CUDA(cudaGetLastError());
+    return EOSVR_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// Winner rows (multi-GPU exchange helper and input of the splice kernel).
+// -------------------------------------------------------------------------------------------
+__global__ void k_gather_rows(const float *__restrict__ gal, int64_t G, int64_t offset, int D,
+                              const int64_t *__restrict__ idx, float *__restrict__ out)
+{
+    const int64_t p = blockIdx.x;
+    const int64_t g = idx[p] - offset;
+    const bool own = g >= 0 && g < G;
+    const float *src = gal + (own ? g : 0) * D;
+    float *dst = out + p * D;
+    if ((D & 3) == 0) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(src);
+        float4 *d4 = reinterpret_cast<float4 *>(dst);
+        for (int k = threadIdx.x; k < D / 4; k += blockDim.x) d4[k] = own ? s4[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        for (int k = threadIdx.x; k < D; k += blockDim.x) dst[k] = own ? src[k] : 0.f;
+    }
+}
+
+int launch_gather_rows(const eosvr_gallery *g, const int64_t *idx, int64_t P, float *out, cudaStream_t st)
+{
+    if (P == 0) return EOSVR_OK;
+    k_gather_rows<<<static_cast<unsigned>(P), 128, 0, st>>>(g->feats, g->G, g->offset, g->D, idx, out);
+    EOSVR_CUDA(cudaGetLastError());
+    return EOSVR_OK;
+}
+
+}  // namespace eosvr

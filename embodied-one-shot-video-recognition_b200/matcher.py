@@ -1,0 +1,281 @@
+"""PyTorch host layer over the C ABI: gallery cache, segment matching, augmented-clip assembly,
+episode scoring, and the batched episode pipeline.
+
+PyTorch is plumbing here (device memory, streams); every computation below is a call into
+libeosvr.so with raw device pointers.  Reference lines cited are relative to the reference
+checkout (network_test.py / classifier.py).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from eosvr_b200 import _lib
+from eosvr_b200._lib import (METRIC_EUCLID_TEMPORAL, ORIG_REF_QUIRK, SCREEN_F16, check, lib)
+
+LAMDA1, LAMDA2 = 0.1, 1.0     # utils.py:43
+
+
+def _stream_ptr(stream=None):
+    s = torch.cuda.current_stream() if stream is None else stream
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must live on a CUDA device (there is no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+class GalleryFeatureCache:
+    """Gallery segment features resident in HBM -- replaces the per-run arrays of
+    network_test.py:184-189 (``gallery_seg_features``).
+
+    feats: [G, D] float32 CUDA tensor (kept alive by this object; the exact re-rank reads it).
+    global_offset: index of row 0 in the un-sharded gallery (multi-GPU sharding by segment).
+    """
+
+    def __init__(self, feats: torch.Tensor, global_offset: int = 0, screen_fmt: int = SCREEN_F16, stream=None):
+        feats = _dev_f32(feats, "feats")
+        if feats.dim() != 2:
+            raise ValueError("feats must be [G, D]")
+        self.feats = feats
+        self.G, self.D = int(feats.shape[0]), int(feats.shape[1])
+        self.global_offset = int(global_offset)
+        self.screen_fmt = int(screen_fmt)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(feats.device):
+            check(lib().eosvr_gallery_create(_ptr(feats), self.G, self.D, 0, self.global_offset, self.screen_fmt,
+                                             _stream_ptr(stream), ctypes.byref(self._h)), "eosvr_gallery_create")
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def device(self):
+        return self.feats.device
+
+    def close(self):
+        if self._h:
+            lib().eosvr_gallery_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MatchWorkspace:
+    """Scratch of the matcher for up to max_probe_rows probe segments per call."""
+
+    def __init__(self, max_probe_rows: int, D: int, cand_capacity: int = 0, device=None):
+        self.max_probe_rows, self.D = int(max_probe_rows), int(D)
+        self._h = ctypes.c_void_p()
+        self._dbg = None
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = dev
+        with torch.cuda.device(dev):
+            check(lib().eosvr_workspace_create(self.max_probe_rows, self.D, int(cand_capacity), ctypes.byref(self._h)),
+                  "eosvr_workspace_create")
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_debug_dump(self, P: int, G: int):
+        """Test hook: keep the screening values t~[P,G] of subsequent match calls."""
+        self._dbg = torch.full((P, G), float("nan"), dtype=torch.float32, device=self.device)
+        check(lib().eosvr_workspace_set_debug(self._h, _ptr(self._dbg), P * G))
+        return self._dbg
+
+    def clear_debug_dump(self):
+        check(lib().eosvr_workspace_set_debug(self._h, ctypes.c_void_p(0), 0))
+        self._dbg = None
+
+    def stats(self, stream=None) -> dict:
+        out = (ctypes.c_int64 * 8)()
+        check(lib().eosvr_match_stats(self._h, _stream_ptr(stream), out), "eosvr_match_stats")
+        keys = ["candidates", "exact_evals", "fallback_rows", "cand_capacity", "tiles", "mma_n", "unsafe", "overflow"]
+        return dict(zip(keys, [int(v) for v in out]))
+
+    def close(self):
+        if self._h:
+            lib().eosvr_workspace_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _match(fn_name, gallery, ws, probes, rows_per_episode, lam1, lam2, want_packed, stream):
+    probes = _dev_f32(probes, "probes")
+    if probes.dim() != 2 or probes.shape[1] != gallery.D:
+        raise ValueError(f"probes must be [P, {gallery.D}]")
+    P = int(probes.shape[0])
+    packed = torch.empty(P, dtype=torch.int64, device=probes.device)     # uint64 payload
+    score = torch.empty(P, dtype=torch.float32, device=probes.device)
+    idx = torch.empty(P, dtype=torch.int64, device=probes.device)
+    with torch.cuda.device(probes.device):
+        check(getattr(lib(), fn_name)(gallery.handle, ws.handle, _ptr(probes), P, int(rows_per_episode),
+                                      METRIC_EUCLID_TEMPORAL, float(lam1), float(lam2), _ptr(packed), _ptr(score),
+                                      _ptr(idx), _stream_ptr(stream)), fn_name)
+    return (idx, score, packed) if want_packed else (idx, score)
+
+
+def match_segments(gallery: GalleryFeatureCache, ws: MatchWorkspace, probes: torch.Tensor, rows_per_episode: int,
+                   lam1: float = LAMDA1, lam2: float = LAMDA2, want_packed: bool = False, stream=None):
+    """network_test.py:208-212 for a batch of episodes: euclidean cdist -> float32 -> temporal taps
+    -> arg-min.  probes [P, D]; returns (idx int64[P] global gallery indices, score float32[P]
+    smoothed distance of the winner[, packed int64[P] shard-merge words])."""
+    return _match("eosvr_match", gallery, ws, probes, rows_per_episode, lam1, lam2, want_packed, stream)
+
+
+def match_segments_exact(gallery, ws, probes, rows_per_episode, lam1=LAMDA1, lam2=LAMDA2, want_packed=False,
+                         stream=None):
+    """Same contract through the exhaustive float64 CUDA-core kernel (validation / fallback)."""
+    return _match("eosvr_match_exact", gallery, ws, probes, rows_per_episode, lam1, lam2, want_packed, stream)
+
+
+def merge_top1(gathered_packed: torch.Tensor, stream=None):
+    """[nshards, P] packed winners (e.g. after all_gather) -> (idx, score, packed) of the global winner."""
+    g = gathered_packed.contiguous()
+    if g.dtype != torch.int64 or g.dim() != 2 or not g.is_cuda:
+        raise ValueError("gathered_packed must be a CUDA int64 [nshards, P] tensor")
+    n, P = int(g.shape[0]), int(g.shape[1])
+    packed = torch.empty(P, dtype=torch.int64, device=g.device)
+    score = torch.empty(P, dtype=torch.float32, device=g.device)
+    idx = torch.empty(P, dtype=torch.int64, device=g.device)
+    with torch.cuda.device(g.device):
+        check(lib().eosvr_merge_top1(_ptr(g), n, P, _ptr(packed), _ptr(score), _ptr(idx), _stream_ptr(stream)),
+              "eosvr_merge_top1")
+    return idx, score, packed
+
+
+def gather_winner_rows(gallery: GalleryFeatureCache, idx: torch.Tensor, stream=None) -> torch.Tensor:
+    """Rows of the winners this shard owns (zeros elsewhere): [P, D] float32."""
+    idx = idx.contiguous()
+    P = int(idx.shape[0])
+    out = torch.empty(P, gallery.D, dtype=torch.float32, device=idx.device)
+    with torch.cuda.device(idx.device):
+        check(lib().eosvr_gather_rows(gallery.handle, _ptr(idx), P, _ptr(out), _stream_ptr(stream)), "eosvr_gather_rows")
+    return out
+
+
+def splice_augmented(probes: torch.Tensor, winner_rows: torch.Tensor, n: int, S: int,
+                     orig_mode: int = ORIG_REF_QUIRK, stream=None) -> torch.Tensor:
+    """network_test.py:220-250 in feature space.  probes [E*n*S, D] (or [E, n, S, D]); winner_rows
+    [E*n*S, D]; returns the augmented support set [E, n*(1+S), D]."""
+    D = int(probes.shape[-1])
+    probes = _dev_f32(probes, "probes").reshape(-1, D)
+    winner_rows = _dev_f32(winner_rows, "winner_rows").reshape(-1, D)
+    if probes.shape[0] % (n * S) or probes.shape != winner_rows.shape:
+        raise ValueError("probes / winner_rows must be [E*n*S, D]")
+    E = probes.shape[0] // (n * S)
+    out = torch.empty(E, n * (1 + S), D, dtype=torch.float32, device=probes.device)
+    with torch.cuda.device(probes.device):
+        check(lib().eosvr_splice(_ptr(probes), _ptr(winner_rows), E, n, S, D, int(orig_mode), _ptr(out),
+                                 _stream_ptr(stream)), "eosvr_splice")
+    return out
+
+
+def proto_score(support: torch.Tensor, support_y: torch.Tensor, query: torch.Tensor, max_proto: int = 0, stream=None):
+    """classifier.py:9-90 for E episodes.  support [E,R,D], support_y [E,R] float32, query [E,Q,D].
+    Returns dict(pred int64[E,Q] prototype position, dist float32[E,Q,max_proto] (logits = -dist),
+    prob float32[E,Q,max_proto], nproto int32[E])."""
+    support, support_y, query = _dev_f32(support, "support"), _dev_f32(support_y, "support_y"), _dev_f32(query, "query")
+    if support.dim() != 3 or query.dim() != 3 or support_y.shape != support.shape[:2]:
+        raise ValueError("support [E,R,D], support_y [E,R], query [E,Q,D] expected")
+    E, R, D = (int(x) for x in support.shape)
+    Q = int(query.shape[1])
+    mp = int(max_proto) if max_proto else min(R, 64)
+    dev = support.device
+    dist = torch.empty(E, Q, mp, dtype=torch.float32, device=dev)
+    prob = torch.empty(E, Q, mp, dtype=torch.float32, device=dev)
+    pred = torch.empty(E, Q, dtype=torch.int64, device=dev)
+    nproto = torch.empty(E, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().eosvr_proto_score(_ptr(support), _ptr(support_y), _ptr(query), E, R, Q, D, mp, _ptr(dist),
+                                      _ptr(prob), _ptr(pred), _ptr(nproto), _stream_ptr(stream)), "eosvr_proto_score")
+    return dict(pred=pred, dist=dist, prob=prob, nproto=nproto)
+
+
+def segment_features(frames: torch.Tensor, seg_len: int, l2: bool = True, stream=None) -> torch.Tensor:
+    """network_test.py:187-189 / :203-205 (+ per-frame L2 of :79-80): [N*seg_len, D] -> [N, D]."""
+    frames = _dev_f32(frames, "frames")
+    if frames.dim() != 2 or frames.shape[0] % seg_len:
+        raise ValueError("frames must be [N*seg_len, D]")
+    N, D = frames.shape[0] // seg_len, int(frames.shape[1])
+    out = torch.empty(N, D, dtype=torch.float32, device=frames.device)
+    with torch.cuda.device(frames.device):
+        check(lib().eosvr_segment_features(_ptr(frames), N, int(seg_len), D, int(bool(l2)), _ptr(out),
+                                           _stream_ptr(stream)), "eosvr_segment_features")
+    return out
+
+
+class EpisodePipeline:
+    """The loop body of ``test_network_aug_segment`` (network_test.py:195-259) for a batch of episodes on
+    cached segment embeddings: match -> winner rows -> augmented support set -> ProtoNet scoring.
+
+    With ``group`` (a torch.distributed process group) the gallery is sharded by segment: every rank
+    matches the same probes against its shard, one all_gather of the packed winners + an element-wise
+    min gives the global winners, and one sum all_reduce delivers the winner rows.
+    """
+
+    def __init__(self, gallery: GalleryFeatureCache, n_way: int, k_shot: int, num_segs: int,
+                 max_episodes: int, lam1: float = LAMDA1, lam2: float = LAMDA2, orig_mode: int = ORIG_REF_QUIRK,
+                 group=None, cand_capacity: int = 0):
+        self.gallery = gallery
+        self.n, self.S, self.n_way = n_way * k_shot, num_segs, n_way
+        self.rpe = self.n * self.S
+        self.lam1, self.lam2, self.orig_mode = lam1, lam2, orig_mode
+        self.group = group
+        self.ws = MatchWorkspace(max_episodes * self.rpe, gallery.D, cand_capacity, device=gallery.device)
+
+    def run(self, probes: torch.Tensor, support_y: torch.Tensor, query: torch.Tensor, stream=None) -> dict:
+        """probes [E, n, S, D] (device), support_y [E, n] float32, query [E, Q, D].
+        Returns dict(pred [E,Q], idx [E,n,S], score [E,n,S], dist, prob)."""
+        E = int(probes.shape[0])
+        D = self.gallery.D
+        flat = probes.reshape(E * self.rpe, D)
+        idx, score, packed = match_segments(self.gallery, self.ws, flat, self.rpe, self.lam1, self.lam2, True, stream)
+        if self.group is not None:
+            import torch.distributed as dist
+            ws = dist.get_world_size(self.group)
+            gathered = torch.empty(ws, packed.shape[0], dtype=torch.int64, device=packed.device)
+            dist.all_gather_into_tensor(gathered, packed, group=self.group)
+            idx, score, packed = merge_top1(gathered, stream)
+            rows = gather_winner_rows(self.gallery, idx, stream)
+            dist.all_reduce(rows, group=self.group)          # one non-zero contributor per row: exact
+        else:
+            rows = gather_winner_rows(self.gallery, idx, stream)
+        aug = splice_augmented(flat, rows, self.n, self.S, self.orig_mode, stream)
+        labels = support_y.to(torch.float32).repeat_interleave(1 + self.S, dim=1).contiguous()
+        res = proto_score(aug, labels, query, self.n_way, stream)
+        res.update(idx=idx.view(E, self.n, self.S), score=score.view(E, self.n, self.S), support_feature=aug,
+                   support_y=labels)
+        return res
+
+    def run_host(self, probes_host: torch.Tensor, support_y_host: torch.Tensor, query_host: torch.Tensor) -> dict:
+        """End-to-end call with HOST tensors (pinned for speed): H2D copies, the pipeline, and the D2H read
+        of predictions and winner indices."""
+        dev = self.gallery.device
+        p = probes_host.to(dev, non_blocking=True)
+        y = support_y_host.to(dev, non_blocking=True)
+        q = query_host.to(dev, non_blocking=True)
+        r = self.run(p, y, q)
+        return dict(pred=r["pred"].cpu(), idx=r["idx"].cpu())

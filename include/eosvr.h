@@ -1,0 +1,161 @@
+/*
+ * eosvr.h -- C ABI of the B200-native test-time episodic hot path
+ *            (video-segment augmentation + one-shot episode scoring).
+ *
+ * The reference (lovelyqian/Embodied-One-Shot-Video-Recognition) is pure Python and has
+ * no FFI; this boundary is new.  Each entry point replaces the arithmetic of the
+ * reference lines cited beside it (paths relative to the reference checkout).  The
+ * reference-side binding is a ctypes stub; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative EOSVR_E* code; the message of
+ *     the last failure on the calling thread is eosvr_last_error();
+ *   - all d_* pointers are DEVICE pointers owned by the caller (e.g. tensor.data_ptr());
+ *     the library allocates device memory only inside the opaque handles;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); no call
+ *     synchronises the host except where stated; outputs are valid once the stream has
+ *     reached the end of the call's work;
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef EOSVR_H_
+#define EOSVR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EOSVR_VERSION 100
+
+/* error codes */
+#define EOSVR_OK          0
+#define EOSVR_EINVAL     -1   /* bad argument (shape, alignment, enum) */
+#define EOSVR_ECUDA      -2   /* CUDA runtime / driver error           */
+#define EOSVR_ENOMEM     -3   /* device allocation failed              */
+#define EOSVR_EUNSUPPORTED -4 /* device is not sm_100                  */
+
+/* feature storage types */
+#define EOSVR_F32  0          /* float32 rows (the reference's dtype, network_test.py:187-189) */
+
+/* 16-bit format of the tensor-core screening copy */
+#define EOSVR_SCREEN_F16   0  /* default: fp16, 11-bit significand -> tight error bound */
+#define EOSVR_SCREEN_BF16  1  /* bf16; exact when the features are bf16-representable  */
+
+/* metric / selection rule of the segment matching */
+#define EOSVR_METRIC_EUCLID_TEMPORAL 0 /* cdist euclidean + [lam1,lam2,lam1] taps + arg-min (network_test.py:208-212) */
+
+/* "original clip feature" row of the augmented support set */
+#define EOSVR_ORIG_REF_QUIRK 0 /* flat segment row i, as written at network_test.py:229 */
+#define EOSVR_ORIG_CLIP_MEAN 1 /* mean of clip i's segment rows, the commented intent :227-228 */
+
+typedef struct eosvr_gallery   eosvr_gallery_t;    /* gallery feature cache (replaces the arrays of network_test.py:184-189) */
+typedef struct eosvr_workspace eosvr_workspace_t;  /* per-stream scratch of the matcher */
+
+int         eosvr_version(void);
+const char *eosvr_last_error(void);
+/* 0 if a usable sm_100 device is current, EOSVR_EUNSUPPORTED / EOSVR_ECUDA otherwise. */
+int         eosvr_device_check(void);
+
+/* ---- gallery feature cache -------------------------------------------------------
+ * Wraps the gallery segment features gallery_seg_features[G,D] (network_test.py:187-189)
+ * resident in HBM.  d_feats stays owned by the caller and must outlive the handle (the
+ * exact re-rank reads it).  Builds, on `stream`, the 16-bit screening copy [G, Dpad]
+ * (K-major, 128-byte swizzle friendly), the squared-norm side array and the error-bound
+ * scalars.  global_offset is the index of row 0 in the un-sharded gallery (multi-GPU
+ * sharding by segment); returned indices are global. */
+int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtype,
+                         int64_t global_offset, int32_t screen_fmt, void *stream,
+                         eosvr_gallery_t **out);
+int eosvr_gallery_destroy(eosvr_gallery_t *g);
+int eosvr_gallery_rows(const eosvr_gallery_t *g, int64_t *G, int32_t *D, int64_t *global_offset);
+
+/* ---- workspace --------------------------------------------------------------------
+ * Scratch for up to max_probe_rows probe segments of dimension D per call.
+ * cand_capacity = number of (probe, gallery) near-minimum candidates the screening pass
+ * may hand to the exact re-rank per call (0 = default: 64 per probe row, >= 1 Mi). */
+int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capacity,
+                           eosvr_workspace_t **out);
+int eosvr_workspace_destroy(eosvr_workspace_t *ws);
+
+/* ---- segment matching -------------------------------------------------------------
+ * Replaces, for a batch of episodes, network_test.py:208-212:
+ *     distance = cdist(support_seg_features, gallery_seg_features, 'euclidean')   # fp64
+ *     distance = temporal_convolution_flating_layer(distance)                     # fp32 taps
+ *     gallery_pool_ids = np.argsort(distance, axis=1)[:, :1]
+ * d_probes [P,D] float32 = the support segment features of P/rows_per_episode episodes
+ * (rows_per_episode = n_way*k_shot*num_segs consecutive rows are smoothed together with
+ * zero padding at both ends, exactly as the reference pads one episode).
+ * The [P,G] matrix is never written to memory.
+ * Outputs (any may be NULL except d_out_packed):
+ *   d_out_packed[P] uint64 : (order-preserving bits of the float32 smoothed distance) << 32
+ *                            | global gallery index -- the shard-merge format;
+ *   d_out_score[P]  float32: smoothed distance of the winner (bit-equal to the reference's);
+ *   d_out_idx[P]    int64  : global index of the winning gallery segment, lowest index on
+ *                            exact ties. */
+int eosvr_match(const eosvr_gallery_t *g, eosvr_workspace_t *ws, const float *d_probes,
+                int64_t P, int32_t rows_per_episode, int32_t metric, float lam1, float lam2,
+                uint64_t *d_out_packed, float *d_out_score, int64_t *d_out_idx, void *stream);
+
+/* Same contract, evaluated entirely with the exact float64 CUDA-core kernel (no tensor
+ * cores, no screening).  Used by the matcher for rows whose candidate list overflowed and
+ * exposed for validation at small sizes. */
+int eosvr_match_exact(const eosvr_gallery_t *g, eosvr_workspace_t *ws, const float *d_probes,
+                      int64_t P, int32_t rows_per_episode, int32_t metric, float lam1, float lam2,
+                      uint64_t *d_out_packed, float *d_out_score, int64_t *d_out_idx, void *stream);
+
+/* Counters of the last eosvr_match on this workspace (synchronises `stream`):
+ * out[0] candidates appended, out[1] candidates evaluated exactly, out[2] rows sent to the
+ * exact fallback, out[3] candidate capacity, out[4] screening tiles, out[5] N of the MMA,
+ * out[6] unsafe (cancellation-guard) candidates, out[7] reserved. */
+int eosvr_match_stats(eosvr_workspace_t *ws, void *stream, int64_t out[8]);
+
+/* ---- multi-GPU shard merge (new) --------------------------------
+ * d_gathered [nshards, P] = the d_out_packed arrays of all gallery shards (e.g. after one
+ * ncclAllGather).  Element-wise minimum = global winner with the lowest-global-index tie
+ * rule. */
+int eosvr_merge_top1(const uint64_t *d_gathered, int32_t nshards, int64_t P,
+                     uint64_t *d_out_packed, float *d_out_score, int64_t *d_out_idx, void *stream);
+
+/* Rows of the winners: d_out_rows[p,:] = gallery[idx[p] - global_offset,:] when this shard
+ * owns idx[p], else zeros (so a sum-reduce over shards delivers every winner row exactly). */
+int eosvr_gather_rows(const eosvr_gallery_t *g, const int64_t *d_idx, int64_t P,
+                      float *d_out_rows, void *stream);
+
+/* ---- augmented-clip assembly -------------------------------------------------------
+ * Replaces network_test.py:220-250 (video_segment_augmentation :119-129 + backbone
+ * re-encode) in feature space:  for episode e, clip i: row 0 = "original" (orig_mode),
+ * rows 1+s = float32 mean over the clip's S segment rows with row s replaced by the
+ * winner row.  d_probes [E*n, S, D]; d_winner_rows [E*n*S, D]; d_out [E, n*(1+S), D].
+ * Summation order = numpy's (sequential rows, one true division): bit-equal results. */
+int eosvr_splice(const float *d_probes, const float *d_winner_rows, int64_t E, int32_t n,
+                 int32_t S, int32_t D, int32_t orig_mode, float *d_out, void *stream);
+
+/* ---- ProtoNet episode scoring ------------------------------------------------------
+ * Replaces Classifier('protonet').predict, classifier.py:9-90, for E episodes:
+ * d_support [E, R, D], d_support_y [E, R] float32 labels, d_query [E, Q, D].
+ * Prototypes in first-appearance label order (float32 sequential mean), float64 distance
+ * cast to float32, softmax(-d), first arg-max.  max_proto bounds the classes per episode.
+ * Outputs (nullable): d_dist [E,Q,max_proto] float32 distances (logits = -d; unused slots
+ * = +inf), d_prob [E,Q,max_proto], d_pred [E,Q] int64 prototype POSITION (classifier.py:85),
+ * d_nproto [E] int32. */
+int eosvr_proto_score(const float *d_support, const float *d_support_y, const float *d_query,
+                      int64_t E, int32_t R, int32_t Q, int32_t D, int32_t max_proto,
+                      float *d_dist, float *d_prob, int64_t *d_pred, int32_t *d_nproto,
+                      void *stream);
+
+/* ---- gallery / probe cache builder -------------------------------------------------
+ * Replaces np.resize + np.mean of network_test.py:188-189 / :204-205 (+ per-frame
+ * F.normalize of :79-80 when l2 != 0): d_frames [N*seg_len, D] -> d_out [N, D]. */
+int eosvr_segment_features(const float *d_frames, int64_t N, int32_t seg_len, int32_t D,
+                           int32_t l2, float *d_out, void *stream);
+
+/* ---- test hook (not part of the reference-facing surface) ---------------------------
+ * Dump the screening values t~[P,G] (float32, un-emitted entries untouched) of subsequent
+ * eosvr_match calls into a caller-owned device buffer of `elems` floats; NULL disables. */
+int eosvr_workspace_set_debug(eosvr_workspace_t *ws, float *d_dump, int64_t elems);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EOSVR_H_ */
