@@ -38,6 +38,10 @@ SIGNATURES = {
     "eosvr_workspace_create": (_c.c_int, [_i64, _i32, _i64, _c.POINTER(_vp)]),
     "eosvr_workspace_destroy": (_c.c_int, [_vp]),
     "eosvr_workspace_set_debug": (_c.c_int, [_vp, _vp, _i64]),
+    "eosvr_workspace_set_timing": (_c.c_int, [_vp, _i32]),
+    "eosvr_workspace_screen_ms": (_c.c_int, [_vp, _c.POINTER(_c.c_double), _c.POINTER(_i64)]),
+    "eosvr_launch_count": (_c.c_uint64, []),
+    "eosvr_plan": (_c.c_int, [_i64, _i32, _c.POINTER(_i64)]),
     "eosvr_match": (_c.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _vp]),
     "eosvr_match_exact": (_c.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _vp]),
     "eosvr_match_stats": (_c.c_int, [_vp, _vp, _c.POINTER(_i64)]),

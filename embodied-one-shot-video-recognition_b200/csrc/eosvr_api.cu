@@ -9,6 +9,7 @@
 namespace eosvr {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char *fmt, ...)
 {
@@ -180,6 +181,10 @@ int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capac
 int eosvr_workspace_destroy(eosvr_workspace_t *ws)
 {
     if (!ws) return EOSVR_OK;
+    for (int i = 0; i < kTimingRing; ++i) {
+        if (ws->ev0[i]) cudaEventDestroy(ws->ev0[i]);
+        if (ws->ev1[i]) cudaEventDestroy(ws->ev1[i]);
+    }
     if (ws->slab) cudaFree(ws->slab);
     delete ws;
     return EOSVR_OK;
@@ -191,6 +196,45 @@ int eosvr_workspace_set_debug(eosvr_workspace_t *ws, float *d_dump, int64_t elem
 {
     if (!ws) { set_error("set_debug: NULL workspace"); return EOSVR_EINVAL; }
     ws->dbg = d_dump; ws->dbg_elems = d_dump ? elems : 0;
+    return EOSVR_OK;
+}
+
+int eosvr_workspace_set_timing(eosvr_workspace_t *ws, int32_t on)
+{
+    if (!ws) { set_error("set_timing: NULL workspace"); return EOSVR_EINVAL; }
+    if (on && !ws->ev0[0]) {
+        for (int i = 0; i < kTimingRing; ++i) {
+            EOSVR_CUDA(cudaEventCreate(&ws->ev0[i]));
+            EOSVR_CUDA(cudaEventCreate(&ws->ev1[i]));
+        }
+    }
+    ws->timing_on = on ? 1 : 0;
+    ws->timing_calls = 0;
+    return EOSVR_OK;
+}
+
+int eosvr_workspace_screen_ms(eosvr_workspace_t *ws, double *sum_ms, int64_t *calls)
+{
+    if (!ws || !sum_ms || !calls) { set_error("screen_ms: NULL argument"); return EOSVR_EINVAL; }
+    const int64_t n = ws->timing_calls < kTimingRing ? ws->timing_calls : kTimingRing;
+    double tot = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        float ms = 0.f;
+        EOSVR_CUDA(cudaEventSynchronize(ws->ev1[i]));
+        EOSVR_CUDA(cudaEventElapsedTime(&ms, ws->ev0[i], ws->ev1[i]));
+        tot += ms;
+    }
+    *sum_ms = tot; *calls = n;
+    return EOSVR_OK;
+}
+
+uint64_t eosvr_launch_count(void) { return g_launches; }
+
+int eosvr_plan(int64_t P, int32_t rows_per_episode, int64_t out[4])
+{
+    if (P < 1 || rows_per_episode < 1 || !out) { set_error("plan: bad arguments"); return EOSVR_EINVAL; }
+    const MatchPlan pl = make_plan(P, rows_per_episode);
+    out[0] = pl.R; out[1] = pl.halo; out[2] = pl.BN; out[3] = pl.NT;
     return EOSVR_OK;
 }
 

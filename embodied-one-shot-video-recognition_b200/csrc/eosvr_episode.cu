@@ -51,6 +51,7 @@ int launch_splice(const float *probes, const float *wrows, int64_t E, int32_t n,
     dim3 grid(static_cast<unsigned>(E * n), static_cast<unsigned>(1 + S));
     k_splice<<<grid, 128, 0, st>>>(probes, wrows, n, S, D, orig_mode, out);
     EOSVR_CUDA(cudaGetLastError());
+    EOSVR_COUNT_LAUNCH(1);
     return EOSVR_OK;
 }
 
@@ -160,6 +161,7 @@ int launch_proto_score(const float *sup, const float *sup_y, const float *query,
     k_proto_score<<<static_cast<unsigned>(E), kProtoThreads, 0, st>>>(sup, sup_y, query, R, Q, D, max_proto,
                                                                      dist, prob, pred, nproto);
     EOSVR_CUDA(cudaGetLastError());
+    EOSVR_COUNT_LAUNCH(1);
     return EOSVR_OK;
 }
 
@@ -203,6 +205,7 @@ int launch_segment_features(const float *frames, int64_t N, int32_t seg_len, int
     k_segment_features<<<static_cast<unsigned>((N * 32 + threads - 1) / threads), threads, 0, st>>>(
         frames, N, seg_len, D, l2, out);
     EOSVR_CUDA(cudaGetLastError());
+    EOSVR_COUNT_LAUNCH(1);
     return EOSVR_OK;
 }
 

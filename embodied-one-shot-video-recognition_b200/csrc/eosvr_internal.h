@@ -21,6 +21,10 @@ constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kChunk = 16;        // TMEM columns per tcgen05.ld
 constexpr int kSeedSamples = 16;  // gallery rows sampled to seed the per-probe thresholds
 constexpr float kPadNorm = 1.0e30f;
+constexpr int kTimingRing = 256;  // event pairs kept for eosvr_workspace_screen_ms
+
+extern unsigned long long g_launches;   // kernels launched by this library (host-side count)
+#define EOSVR_COUNT_LAUNCH(n) (::eosvr::g_launches += (n))
 
 void set_error(const char *fmt, ...);
 
@@ -90,6 +94,10 @@ struct eosvr_workspace {
     int64_t last_tiles;
     int32_t last_bn;
     int device;
+    // optional CUDA-event timing of the screening kernel (bench.py roofline)
+    int timing_on;
+    int64_t timing_calls;
+    cudaEvent_t ev0[eosvr::kTimingRing], ev1[eosvr::kTimingRing];
 };
 
 namespace eosvr {

@@ -704,6 +704,7 @@ int launch_merge(const uint64_t *gathered, int32_t nshards, int64_t P, uint64_t 
     k_merge_top1<<<static_cast<unsigned>((P + threads - 1) / threads), threads, 0, st>>>(
         reinterpret_cast<const unsigned long long *>(gathered), nshards, P, out_packed, out_score, out_idx);
     EOSVR_CUDA(cudaGetLastError());
+    EOSVR_COUNT_LAUNCH(1);
     return EOSVR_OK;
 }
 
@@ -788,15 +789,15 @@ int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probe
         sp.dbg = (ws->dbg && ws->dbg_elems >= P * g->G) ? ws->dbg : nullptr;
         ws->last_tiles = total_tiles;
 
-        static bool attr_set = false;
-        if (!attr_set) {
-            EOSVR_CUDA(cudaFuncSetAttribute(k_match_screen, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(kScreenSmem)));
-            attr_set = true;
-        }
+        EOSVR_CUDA(cudaFuncSetAttribute(k_match_screen, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(kScreenSmem)));
         const unsigned grid = static_cast<unsigned>(sp.n_units < g_num_sms ? sp.n_units : g_num_sms);
+        const bool timed = ws->timing_on && ws->timing_calls < kTimingRing;
+        if (timed) EOSVR_CUDA(cudaEventRecord(ws->ev0[ws->timing_calls], st));
         k_match_screen<<<grid, kThreads, kScreenSmem, st>>>(g->tmapA, tmB, sp);
         EOSVR_CUDA(cudaGetLastError());
+        if (timed) { EOSVR_CUDA(cudaEventRecord(ws->ev1[ws->timing_calls], st)); ++ws->timing_calls; }
+        EOSVR_COUNT_LAUNCH(5);   // probe_prep, seed_dist, column_plan, match_screen, rerank
 
         k_rerank<<<g_num_sms * 4, 256, 0, st>>>(rp);
         EOSVR_CUDA(cudaGetLastError());
@@ -808,6 +809,7 @@ int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probe
     k_finalize<<<static_cast<unsigned>((P + threads - 1) / threads), threads, 0, st>>>(
         ws->best, P, out_packed, out_score, out_idx);
     EOSVR_CUDA(cudaGetLastError());
+    EOSVR_COUNT_LAUNCH(4);       // reset, compact_flags, exact_fallback, finalize
     return EOSVR_OK;
 }
 
@@ -836,6 +838,7 @@ int launch_gather_rows(const eosvr_gallery *g, const int64_t *idx, int64_t P, fl
     if (P == 0) return EOSVR_OK;
     k_gather_rows<<<static_cast<unsigned>(P), 128, 0, st>>>(g->feats, g->G, g->offset, g->D, idx, out);
     EOSVR_CUDA(cudaGetLastError());
+    EOSVR_COUNT_LAUNCH(1);
     return EOSVR_OK;
 }
 

@@ -104,6 +104,16 @@ class MatchWorkspace:
         check(lib().eosvr_workspace_set_debug(self._h, ctypes.c_void_p(0), 0))
         self._dbg = None
 
+    def set_timing(self, on: bool = True):
+        """Bracket the screening kernel of following match calls with CUDA events (<= 256 calls)."""
+        check(lib().eosvr_workspace_set_timing(self._h, int(bool(on))), "eosvr_workspace_set_timing")
+
+    def screen_ms(self):
+        """(sum of screening-kernel durations in ms, number of calls recorded)."""
+        tot, n = ctypes.c_double(), ctypes.c_int64()
+        check(lib().eosvr_workspace_screen_ms(self._h, ctypes.byref(tot), ctypes.byref(n)), "eosvr_workspace_screen_ms")
+        return tot.value, n.value
+
     def stats(self, stream=None) -> dict:
         out = (ctypes.c_int64 * 8)()
         check(lib().eosvr_match_stats(self._h, _stream_ptr(stream), out), "eosvr_match_stats")

