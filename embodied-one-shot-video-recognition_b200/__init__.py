@@ -7,10 +7,10 @@ Import as ``eosvr_b200``.
 from eosvr_b200._lib import (EosvrError, lib, lib_path, load_library, ORIG_CLIP_MEAN,  # noqa: F401
                              ORIG_REF_QUIRK, SCREEN_BF16, SCREEN_F16)
 from eosvr_b200.matcher import (EpisodePipeline, GalleryFeatureCache, MatchWorkspace,  # noqa: F401
-                                match_segments, match_segments_exact, merge_top1, proto_score,
+                                episode_score, gather_winner_rows, match_segments, match_segments_exact, merge_top1, proto_score,
                                 segment_features, splice_augmented)
 
 __all__ = ["EosvrError", "lib", "lib_path", "load_library", "GalleryFeatureCache", "MatchWorkspace",
-           "EpisodePipeline", "match_segments", "match_segments_exact", "merge_top1", "proto_score",
+           "EpisodePipeline", "episode_score", "gather_winner_rows", "match_segments", "match_segments_exact", "merge_top1", "proto_score",
            "segment_features", "splice_augmented", "ORIG_REF_QUIRK", "ORIG_CLIP_MEAN", "SCREEN_F16",
            "SCREEN_BF16"]

@@ -49,6 +49,8 @@ SIGNATURES = {
     "eosvr_gather_rows": (_c.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "eosvr_splice": (_c.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "eosvr_proto_score": (_c.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "eosvr_episode_score": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32,
+                                       _vp, _vp, _vp, _vp, _vp]),
     "eosvr_segment_features": (_c.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp]),
 }
 

@@ -39,12 +39,12 @@ static PFN_encodeTiled get_encode()
 
 // 2-D row-major [rows, cols] 16-bit tensor, box = box_rows x box_cols, 128-byte swizzle.
 int encode_tmap_2d(CUtensorMap *m, const void *base, int fmt, uint64_t rows, uint64_t cols,
-                   uint32_t box_rows, uint32_t box_cols)
+                   uint32_t box_rows, uint32_t box_cols, uint64_t row_stride)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return EOSVR_ECUDA; }
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstr[1] = {cols * 2};
+    cuuint64_t gstr[1] = {cols * 2 * row_stride};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, fmt == EOSVR_SCREEN_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
@@ -110,7 +110,16 @@ int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtyp
         return EOSVR_ENOMEM;
     }
     rc = launch_gallery_prep(g, static_cast<cudaStream_t>(stream));
-    if (!rc) rc = encode_tmap_2d(&g->tmapA, g->h16, screen_fmt, static_cast<uint64_t>(Gpad), static_cast<uint64_t>(g->Dp), kBM, kBK);
+    if (!rc) rc = encode_tmap_2d(&g->tmapA, g->h16, screen_fmt, static_cast<uint64_t>(Gpad), static_cast<uint64_t>(g->Dp), kBM, kBK, 1);
+    // strided seed sample: seed_tiles tiles of rows {0, stride, 2*stride, ...}
+    const int64_t GT = Gpad / kBM;
+    int64_t st_tiles = GT / 40;
+    if (st_tiles < 1) st_tiles = 1;
+    if (st_tiles > kMaxSeedTiles) st_tiles = kMaxSeedTiles;
+    g->seed_tiles = static_cast<int32_t>(st_tiles);
+    g->seed_stride = Gpad / (st_tiles * kBM);
+    if (!rc) rc = encode_tmap_2d(&g->tmapSeed, g->h16, screen_fmt, static_cast<uint64_t>(st_tiles * kBM),
+                                 static_cast<uint64_t>(g->Dp), kBM, kBK, static_cast<uint64_t>(g->seed_stride));
     if (rc) { eosvr_gallery_destroy(g); return rc; }
     *out = g;
     return EOSVR_OK;
@@ -148,7 +157,9 @@ int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capac
     memset(ws, 0, sizeof(*ws));
     ws->maxP = max_probe_rows; ws->D = D; ws->Dp = (D + kBK - 1) / kBK * kBK;
     ws->cap_rows = max_probe_rows + max_probe_rows / 4 + 4 * kMaxBN;
-    ws->cand_cap = cand_capacity ? cand_capacity : (max_probe_rows * 64 > (1ll << 20) ? max_probe_rows * 64 : (1ll << 20));
+    ws->cand_cap = cand_capacity ? (cand_capacity + max_probe_rows - 1) / max_probe_rows : 128;   // per probe row
+    if (ws->cand_cap < 32) ws->cand_cap = 32;
+    if (ws->cand_cap > 4096) ws->cand_cap = 4096;
     cudaGetDevice(&ws->device);
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
@@ -156,8 +167,8 @@ int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capac
     const size_t o_na = carve(ws->cap_rows * 4), o_wl = carve(ws->cap_rows * 4), o_wr = carve(ws->cap_rows * 4);
     const size_t o_mg = carve(ws->cap_rows * 4), o_ep = carve(ws->cap_rows * 4), o_rm = carve(ws->cap_rows * 4);
     const size_t o_thr = carve(ws->maxP * 4), o_best = carve(ws->maxP * 8), o_rf = carve(ws->maxP * 4);
-    const size_t o_fl = carve(ws->maxP * 4), o_ds = carve(static_cast<size_t>(ws->maxP) * kSeedSamples * 4);
-    const size_t o_cd = carve(static_cast<size_t>(ws->cand_cap) * sizeof(Cand)), o_ct = carve(sizeof(Counters));
+    const size_t o_fl = carve(ws->maxP * 4), o_rc = carve(ws->maxP * 4);
+    const size_t o_cd = carve(static_cast<size_t>(ws->maxP) * ws->cand_cap * sizeof(Cand)), o_ct = carve(sizeof(Counters));
     if (cudaMalloc(&ws->slab, off) != cudaSuccess) {
         cudaGetLastError();
         set_error("workspace_create: device allocation of %zu bytes failed", off);
@@ -172,7 +183,7 @@ int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capac
     ws->epsd = reinterpret_cast<float *>(b + o_ep); ws->rowmap = reinterpret_cast<int32_t *>(b + o_rm);
     ws->gthr = reinterpret_cast<unsigned int *>(b + o_thr); ws->best = reinterpret_cast<unsigned long long *>(b + o_best);
     ws->rowflag = reinterpret_cast<int32_t *>(b + o_rf); ws->flaglist = reinterpret_cast<int32_t *>(b + o_fl);
-    ws->dsamp = reinterpret_cast<float *>(b + o_ds); ws->cand = reinterpret_cast<Cand *>(b + o_cd);
+    ws->rowcnt = reinterpret_cast<unsigned int *>(b + o_rc); ws->cand = reinterpret_cast<Cand *>(b + o_cd);
     ws->counters = reinterpret_cast<Counters *>(b + o_ct);
     *out = ws;
     return EOSVR_OK;
@@ -281,7 +292,7 @@ int eosvr_match_stats(eosvr_workspace_t *ws, void *stream, int64_t out[8])
     out[0] = static_cast<int64_t>(c.cand_count);
     out[1] = static_cast<int64_t>(c.n_exact);
     out[2] = c.n_flag_rows;
-    out[3] = ws->cand_cap;
+    out[3] = ws->cand_cap * ws->maxP;
     out[4] = ws->last_tiles;
     out[5] = ws->last_bn;
     out[6] = static_cast<int64_t>(c.n_unsafe);
@@ -319,6 +330,20 @@ int eosvr_proto_score(const float *d_support, const float *d_support_y, const fl
     if (E < 0 || D < 1 || (E > 0 && (!d_support || !d_support_y || !d_query))) { set_error("proto_score: bad arguments"); return EOSVR_EINVAL; }
     return launch_proto_score(d_support, d_support_y, d_query, E, R, Q, D, max_proto, d_dist, d_prob, d_pred, d_nproto,
                               static_cast<cudaStream_t>(stream));
+}
+
+int eosvr_episode_score(const float *d_probes, const float *d_winner_rows, const eosvr_gallery_t *g,
+                        const int64_t *d_idx, const float *d_support_y, const float *d_query, int64_t E, int32_t n,
+                        int32_t S, int32_t Q, int32_t D, int32_t orig_mode, int32_t max_proto, float *d_dist,
+                        float *d_prob, int64_t *d_pred, int32_t *d_nproto, void *stream)
+{
+    if (E < 0 || D < 1 || (E > 0 && (!d_probes || !d_support_y || !d_query))) { set_error("episode_score: bad arguments"); return EOSVR_EINVAL; }
+    if (E > 0 && !d_winner_rows && !(g && d_idx)) { set_error("episode_score: need d_winner_rows, or a gallery handle and d_idx"); return EOSVR_EINVAL; }
+    if (!d_winner_rows && g && g->D != D) { set_error("episode_score: gallery D=%d != D=%d", g->D, D); return EOSVR_EINVAL; }
+    if (orig_mode != EOSVR_ORIG_REF_QUIRK && orig_mode != EOSVR_ORIG_CLIP_MEAN) { set_error("episode_score: bad orig_mode %d", orig_mode); return EOSVR_EINVAL; }
+    return launch_episode_score(d_probes, d_winner_rows, d_winner_rows ? nullptr : g->feats, d_winner_rows ? 0 : g->G,
+                                d_winner_rows ? 0 : g->offset, d_idx, d_support_y, d_query, E, n, S, Q, D, orig_mode,
+                                max_proto, d_dist, d_prob, d_pred, d_nproto, static_cast<cudaStream_t>(stream));
 }
 
 int eosvr_segment_features(const float *d_frames, int64_t N, int32_t seg_len, int32_t D, int32_t l2, float *d_out,

@@ -165,6 +165,189 @@ int launch_proto_score(const float *sup, const float *sup_y, const float *query,
     return EOSVR_OK;
 }
 
+// -------------------------------------------------------------------------------------------
+// Fused augmented-clip assembly + ProtoNet scoring (network_test.py:220-259 + classifier.py:9-90) for a
+// batch of episodes: the augmented support features [E, n(1+S), D] are formed in registers and folded
+// straight into the class prototypes; nothing but the distances / predictions is written.
+// Bit-equal to k_splice followed by k_proto_score (same float32 evaluation order).
+// One block per episode; threads stride D.  Winner rows come either from d_wrows [E*n*S, D] (multi-GPU:
+// after the shard exchange) or directly from the local gallery through idx.
+// -------------------------------------------------------------------------------------------
+constexpr int kMaxClips = 256;
+
+template <int S_T>
+__global__ void __launch_bounds__(kProtoThreads)
+k_episode_score(const float *__restrict__ probes, const float *__restrict__ wrows, const float *__restrict__ gal,
+                int64_t G, int64_t goff, const int64_t *__restrict__ idx, const float *__restrict__ sup_y,
+                const float *__restrict__ query, int n, int S_rt, int Q, int D, int orig_mode, int max_proto,
+                float *__restrict__ dist, float *__restrict__ prob, int64_t *__restrict__ pred,
+                int32_t *__restrict__ nproto_out)
+{
+    __shared__ int16_t s_cls[kMaxClips];
+    __shared__ int16_t s_order[kMaxClips];      // clips grouped by class, original order inside a class
+    __shared__ int16_t s_start[kMaxProto + 1];
+    __shared__ float s_pid[kMaxProto];
+    __shared__ int s_np;
+    __shared__ double s_red[kProtoThreads / 32][kMaxQ];
+    __shared__ float s_d[kMaxQ][kMaxProto];
+
+    const int S = S_T > 0 ? S_T : S_rt;
+    const int64_t e = blockIdx.x;
+    const float *Pe = probes + e * n * S * D;             // the episode's n*S segment rows
+    const float *Y = sup_y + e * n;
+    const float *Qp = query + e * Q * D;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        int np = 0;
+        for (int i = 0; i < n; ++i) {                     // classifier.py:21-29 (every row of clip i carries Y[i])
+            const float y = Y[i];
+            int c = -1;
+            for (int j = 0; j < np; ++j) if (s_pid[j] == y) { c = j; break; }
+            if (c < 0) { if (np < max_proto) { c = np; s_pid[np++] = y; } else c = -1; }
+            s_cls[i] = static_cast<int16_t>(c);
+        }
+        int pos = 0;
+        for (int c = 0; c < np; ++c) {
+            s_start[c] = static_cast<int16_t>(pos);
+            for (int i = 0; i < n; ++i) if (s_cls[i] == c) s_order[pos++] = static_cast<int16_t>(i);
+        }
+        s_start[np] = static_cast<int16_t>(pos);
+        s_np = np;
+    }
+    __syncthreads();
+    const int np = s_np;
+    const float fS = static_cast<float>(S);
+
+    for (int c = 0; c < np; ++c) {
+        double part[kMaxQ];
+#pragma unroll
+        for (int q = 0; q < kMaxQ; ++q) part[q] = 0.0;
+        const int i0 = s_start[c], i1 = s_start[c + 1];
+        for (int k = tid; k < D; k += kProtoThreads) {
+            float acc = 0.f;
+            int cnt = 0;
+            for (int ii = i0; ii < i1; ++ii) {
+                const int i = s_order[ii];
+                const float *pc = Pe + static_cast<int64_t>(i) * S * D + k;
+                const int64_t wbase = (e * n + i) * S;
+                if (S_T > 0) {
+                    float pr[S_T > 0 ? S_T : 1], w[S_T > 0 ? S_T : 1];
+#pragma unroll
+                    for (int s = 0; s < S_T; ++s) pr[s] = pc[static_cast<int64_t>(s) * D];
+#pragma unroll
+                    for (int s = 0; s < S_T; ++s) {
+                        if (wrows) w[s] = wrows[(wbase + s) * D + k];
+                        else {
+                            const int64_t g = idx[wbase + s] - goff;
+                            w[s] = (g >= 0 && g < G) ? gal[g * D + k] : 0.f;
+                        }
+                    }
+                    float o;
+                    if (orig_mode == EOSVR_ORIG_REF_QUIRK) o = Pe[static_cast<int64_t>(i) * D + k];   // network_test.py:229
+                    else {
+                        o = pr[0];
+#pragma unroll
+                        for (int s = 1; s < S_T; ++s) o = __fadd_rn(o, pr[s]);
+                        o = __fdiv_rn(o, fS);
+                    }
+                    acc = cnt ? __fadd_rn(acc, o) : o; ++cnt;
+#pragma unroll
+                    for (int s = 0; s < S_T; ++s) {
+                        float a = (s == 0) ? w[0] : pr[0];
+#pragma unroll
+                        for (int s2 = 1; s2 < S_T; ++s2) a = __fadd_rn(a, (s2 == s) ? w[s2] : pr[s2]);
+                        acc = __fadd_rn(acc, __fdiv_rn(a, fS)); ++cnt;
+                    }
+                } else {
+                    float o;
+                    if (orig_mode == EOSVR_ORIG_REF_QUIRK) o = Pe[static_cast<int64_t>(i) * D + k];
+                    else {
+                        o = pc[0];
+                        for (int s = 1; s < S; ++s) o = __fadd_rn(o, pc[static_cast<int64_t>(s) * D]);
+                        o = __fdiv_rn(o, fS);
+                    }
+                    acc = cnt ? __fadd_rn(acc, o) : o; ++cnt;
+                    for (int s = 0; s < S; ++s) {
+                        float wv;
+                        if (wrows) wv = wrows[(wbase + s) * D + k];
+                        else {
+                            const int64_t g = idx[wbase + s] - goff;
+                            wv = (g >= 0 && g < G) ? gal[g * D + k] : 0.f;
+                        }
+                        float a = (s == 0) ? wv : pc[0];
+                        for (int s2 = 1; s2 < S; ++s2) a = __fadd_rn(a, (s2 == s) ? wv : pc[static_cast<int64_t>(s2) * D]);
+                        acc = __fadd_rn(acc, __fdiv_rn(a, fS)); ++cnt;
+                    }
+                }
+            }
+            const float pk = __fdiv_rn(acc, static_cast<float>(cnt));
+#pragma unroll
+            for (int q = 0; q < kMaxQ; ++q) {
+                if (q < Q) {
+                    const double df = static_cast<double>(Qp[static_cast<int64_t>(q) * D + k]) - static_cast<double>(pk);
+                    part[q] += df * df;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kMaxQ; ++q) {
+            double v = part[q];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_red[warp][q] = v;
+        }
+        __syncthreads();
+        if (tid < Q) {
+            double v = 0.0;
+            for (int w = 0; w < kProtoThreads / 32; ++w) v += s_red[w][tid];
+            s_d[tid][c] = static_cast<float>(sqrt(v));
+        }
+        __syncthreads();
+    }
+
+    if (tid < Q) {
+        const int q = tid;
+        float mx = -s_d[q][0]; int best = 0;
+        for (int c = 1; c < np; ++c) { if (-s_d[q][c] > mx) mx = -s_d[q][c]; if (s_d[q][c] < s_d[q][best]) best = c; }
+        float sum = 0.f;
+        for (int c = 0; c < np; ++c) sum += expf(-s_d[q][c] - mx);
+        for (int c = 0; c < max_proto; ++c) {
+            const int64_t o = (e * Q + q) * max_proto + c;
+            if (dist) dist[o] = c < np ? s_d[q][c] : INFINITY;
+            if (prob) prob[o] = c < np ? expf(-s_d[q][c] - mx) / sum : 0.f;
+        }
+        if (pred) pred[e * Q + q] = best;
+    }
+    if (tid == 0 && nproto_out) nproto_out[e] = np;
+}
+
+int launch_episode_score(const float *probes, const float *wrows, const float *gal, int64_t G, int64_t goff,
+                         const int64_t *idx, const float *sup_y, const float *query, int64_t E, int32_t n,
+                         int32_t S, int32_t Q, int32_t D, int32_t orig_mode, int32_t max_proto, float *dist,
+                         float *prob, int64_t *pred, int32_t *nproto, cudaStream_t st)
+{
+    if (E == 0) return EOSVR_OK;
+    if (n < 1 || n > kMaxClips || S < 1 || Q < 1 || Q > kMaxQ || max_proto < 1 || max_proto > kMaxProto) {
+        set_error("episode_score: need 1<=n<=%d, S>=1, 1<=Q<=%d, 1<=max_proto<=%d", kMaxClips, kMaxQ, kMaxProto);
+        return EOSVR_EINVAL;
+    }
+    const unsigned grid = static_cast<unsigned>(E);
+#define EOSVR_EP_LAUNCH(ST)                                                                                    \
+    k_episode_score<ST><<<grid, kProtoThreads, 0, st>>>(probes, wrows, gal, G, goff, idx, sup_y, query, n, S, Q, D, \
+                                                        orig_mode, max_proto, dist, prob, pred, nproto)
+    switch (S) {
+        case 2: EOSVR_EP_LAUNCH(2); break;
+        case 4: EOSVR_EP_LAUNCH(4); break;
+        case 8: EOSVR_EP_LAUNCH(8); break;
+        case 16: EOSVR_EP_LAUNCH(16); break;
+        default: EOSVR_EP_LAUNCH(0); break;
+    }
+#undef EOSVR_EP_LAUNCH
+    EOSVR_CUDA(cudaGetLastError());
+    EOSVR_COUNT_LAUNCH(1);
+    return EOSVR_OK;
+}
+
 // One warp per output segment row.
 __global__ void k_segment_features(const float *__restrict__ frames, int64_t N, int seg_len, int D, int l2,
                                    float *__restrict__ out)

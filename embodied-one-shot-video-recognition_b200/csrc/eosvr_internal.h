@@ -19,7 +19,7 @@ constexpr int kTmemCols = 512;
 constexpr int kEpiWarps = 8;      // warps 4..11
 constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kChunk = 16;        // TMEM columns per tcgen05.ld
-constexpr int kSeedSamples = 16;  // gallery rows sampled to seed the per-probe thresholds
+constexpr int kMaxSeedTiles = 4;  // strided gallery tiles screened first to seed the per-probe thresholds
 constexpr float kPadNorm = 1.0e30f;
 constexpr int kTimingRing = 256;  // event pairs kept for eosvr_workspace_screen_ms
 
@@ -38,13 +38,13 @@ void set_error(const char *fmt, ...);
         }                                                                                    \
     } while (0)
 
-// near-minimum candidate handed from the tensor-core screening pass to the exact re-rank
+// near-minimum candidate handed from the tensor-core screening pass to the exact re-rank;
+// candidates are kept in per-probe-row lists of fixed capacity
 struct Cand {
-    int32_t p;        // probe row
     int32_t g;        // gallery row, local to the shard
-    uint32_t tbits;   // screening value (float bits)
-    uint32_t unsafe;  // 1 = inside the cancellation guard (always re-ranked)
+    uint32_t tbits;   // screening value (float bits); kCandUnsafe = inside the cancellation guard
 };
+constexpr uint32_t kCandUnsafe = 0xFFFFFFFFu;
 
 struct Counters {
     unsigned long long cand_count;   // appended (may exceed capacity)
@@ -61,6 +61,9 @@ struct Counters {
 struct eosvr_gallery {
     const float *feats;      // [G,D] float32, caller-owned
     int64_t G;
+    int32_t seed_tiles;      // gallery tiles of the strided seed pass
+    int64_t seed_stride;     // row stride of the seed pass
+    CUtensorMap tmapSeed;
     int32_t D, Dp;           // Dp = D rounded up to kBK
     int64_t offset;          // global index of row 0
     int32_t screen_fmt;
@@ -75,7 +78,7 @@ struct eosvr_workspace {
     int64_t maxP;
     int32_t D, Dp;
     int64_t cap_rows;        // plan rows capacity
-    int64_t cand_cap;
+    int64_t cand_cap;        // candidates per probe row
     void *slab;              // single device allocation
     // carved views
     void *q16;               // [cap_rows, Dp] packed probe plan (16-bit)
@@ -85,8 +88,8 @@ struct eosvr_workspace {
     unsigned long long *best;  // [maxP] packed winners
     int32_t *rowflag;        // [maxP]
     int32_t *flaglist;       // [maxP]
-    float *dsamp;            // [maxP, kSeedSamples]
-    eosvr::Cand *cand;       // [cand_cap]
+    unsigned int *rowcnt;    // [maxP] candidates appended per probe row
+    eosvr::Cand *cand;       // [maxP, cand_cap]
     eosvr::Counters *counters;
     float *dbg;              // optional [P,G] dump of screening values (tests)
     int64_t dbg_elems;
@@ -122,12 +125,16 @@ int launch_merge(const uint64_t *gathered, int32_t nshards, int64_t P, uint64_t 
 int launch_gather_rows(const eosvr_gallery *g, const int64_t *idx, int64_t P, float *out, cudaStream_t st);
 int launch_splice(const float *probes, const float *wrows, int64_t E, int32_t n, int32_t S, int32_t D,
                   int32_t orig_mode, float *out, cudaStream_t st);
+int launch_episode_score(const float *probes, const float *wrows, const float *gal, int64_t G, int64_t goff,
+                         const int64_t *idx, const float *sup_y, const float *query, int64_t E, int32_t n,
+                         int32_t S, int32_t Q, int32_t D, int32_t orig_mode, int32_t max_proto, float *dist,
+                         float *prob, int64_t *pred, int32_t *nproto, cudaStream_t st);
 int launch_proto_score(const float *sup, const float *sup_y, const float *query, int64_t E, int32_t R,
                        int32_t Q, int32_t D, int32_t max_proto, float *dist, float *prob, int64_t *pred,
                        int32_t *nproto, cudaStream_t st);
 int launch_segment_features(const float *frames, int64_t N, int32_t seg_len, int32_t D, int32_t l2,
                             float *out, cudaStream_t st);
 int encode_tmap_2d(CUtensorMap *m, const void *base, int fmt, uint64_t rows, uint64_t cols,
-                   uint32_t box_rows, uint32_t box_cols);
+                   uint32_t box_rows, uint32_t box_cols, uint64_t row_stride = 1);
 
 }  // namespace eosvr

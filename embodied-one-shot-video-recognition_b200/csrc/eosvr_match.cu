@@ -206,75 +206,38 @@ __global__ void k_probe_prep(const float *__restrict__ probes, PlanDev pl, int D
     }
 }
 
-// Distances of every probe row to kSeedSamples strided gallery rows (fp32 inputs, fp32 math):
-// upper bounds that seed the running thresholds.
-__global__ void k_seed_dist(const float *__restrict__ probes, int64_t P, int D,
-                            const float *__restrict__ gal, int64_t G, float *__restrict__ dsamp)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    if (w >= P * kSeedSamples) return;
-    const int64_t p = w / kSeedSamples;
-    const int s = static_cast<int>(w % kSeedSamples);
-    const int64_t g = (G * s) / kSeedSamples;
-    const float *a = probes + p * D, *b = gal + g * D;
-    double acc = 0.0;
-    for (int k = lane; k < D; k += 32) { double df = static_cast<double>(a[k]) - static_cast<double>(b[k]); acc += df * df; }
-    acc = warp_sum(acc);
-    if (lane == 0) dsamp[w] = static_cast<float>(sqrt(acc));
-}
-
-// Thread per plan column: tap weights and threshold margin; thread per probe row: seed threshold.
+// Thread per plan column: tap weights and threshold margin.
 __global__ void k_column_plan(PlanDev pl, float w, const float *__restrict__ epsd,
-                              float *__restrict__ wl, float *__restrict__ wr, float *__restrict__ margin,
-                              const float *__restrict__ dsamp, unsigned int *__restrict__ gthr)
+                              float *__restrict__ wl, float *__restrict__ wr, float *__restrict__ margin)
 {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t ncol = pl.NT * pl.BN;
-    if (i < ncol) {
-        bool valid, emit;
-        const int64_t p = plan_row_of(pl, i, valid, emit);
-        const int c = static_cast<int>(i % pl.BN);
-        float l = 0.f, r = 0.f, el = 0.f, er = 0.f;
-        if (valid) {
-            if (c > 0 && p > 0 && (p % pl.rpe) != 0) { l = w; el = epsd[i - 1]; }
-            if (c + 1 < pl.BN && p + 1 < pl.P && ((p + 1) % pl.rpe) != 0) {
-                bool v2, e2;
-                plan_row_of(pl, i + 1, v2, e2);
-                if (v2) { r = w; er = epsd[i + 1]; }
-            }
+    if (i >= ncol) return;
+    bool valid, emit;
+    const int64_t p = plan_row_of(pl, i, valid, emit);
+    const int c = static_cast<int>(i % pl.BN);
+    float l = 0.f, r = 0.f, el = 0.f, er = 0.f;
+    if (valid) {
+        if (c > 0 && p > 0 && (p % pl.rpe) != 0) { l = w; el = epsd[i - 1]; }
+        if (c + 1 < pl.BN && p + 1 < pl.P && ((p + 1) % pl.rpe) != 0) {
+            bool v2, e2;
+            plan_row_of(pl, i + 1, v2, e2);
+            if (v2) { r = w; er = epsd[i + 1]; }
         }
-        wl[i] = l; wr[i] = r;
-        margin[i] = valid ? 2.02f * (epsd[i] + l * el + r * er) + 1e-7f : 0.f;
     }
-    if (i < pl.P) {
-        const int64_t p = i;
-        const int r = static_cast<int>(p % pl.rpe);
-        const bool hl = r > 0, hr = (r + 1 < pl.rpe) && (p + 1 < pl.P);
-        float best = kBig;
-        for (int s = 0; s < kSeedSamples; ++s) {
-            float t = dsamp[p * kSeedSamples + s];
-            if (hl) t = fmaf(w, dsamp[(p - 1) * kSeedSamples + s], t);
-            if (hr) t = fmaf(w, dsamp[(p + 1) * kSeedSamples + s], t);
-            best = fminf(best, t);
-        }
-        // margin of p's own column
-        const int64_t col = (p / pl.R) * pl.BN + pl.halo + (p % pl.R);
-        float e = epsd[col];
-        float el = hl ? epsd[col - 1] : 0.f, er = hr ? epsd[col + 1] : 0.f;
-        float m = 2.02f * (e + w * (el + er)) + 1e-7f;
-        gthr[p] = __float_as_uint(fmaf(best, kSlopMul, m));
-    }
+    wl[i] = l; wr[i] = r;
+    margin[i] = valid ? 2.02f * (epsd[i] + l * el + r * er) + 1e-7f : 0.f;
 }
 
-__global__ void k_reset(Counters *ctr, unsigned long long *best, int32_t *rowflag, int64_t P, int flag_all)
+__global__ void k_reset(Counters *ctr, unsigned long long *best, int32_t *rowflag, unsigned int *rowcnt,
+                        unsigned int *gthr, int64_t P, int flag_all)
 {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i == 0) {
         ctr->cand_count = 0; ctr->n_exact = 0; ctr->n_unsafe = 0;
         ctr->overflow = flag_all ? 1u : 0u; ctr->n_flag_rows = 0; ctr->xfloor_bits = 0; ctr->pad = 0;
     }
-    if (i < P) { best[i] = ~0ull; rowflag[i] = flag_all; }
+    if (i < P) { best[i] = ~0ull; rowflag[i] = flag_all; rowcnt[i] = 0; gthr[i] = 0x7f800000u; }
 }
 
 // -------------------------------------------------------------------------------------------
@@ -287,14 +250,16 @@ struct ScreenParams {
     int32_t BN;
     int64_t NT, GT;
     int32_t TPU;            // gallery tiles per work unit
-    int64_t cps;            // work-unit chunks per L2 slab
-    int64_t n_chunks;       // total gallery chunks
-    int64_t n_units;
+    int64_t n_chunks;       // gallery chunks (of TPU tiles)
+    int64_t n_units;        // n_chunks * NT, chunk-major: concurrent CTAs share a gallery chunk
+    int64_t g_stride;       // gallery row stride (1; > 1 in the seed pass)
+    int32_t seed_mode;      // 1: only tighten the thresholds, append nothing
     const float *na, *wl, *wr, *margin;
     const int32_t *rowmap;
     unsigned int *gthr;
     Cand *cand;
-    int64_t cand_cap;
+    unsigned int *rowcnt;
+    int32_t cand_cap;       // per probe row
     Counters *ctr;
     int32_t *rowflag;
     uint32_t idesc;
@@ -323,14 +288,14 @@ struct UnitIter {
     int64_t u, jt, gt0, gt1;
 };
 
+// Work units are chunk-major: unit u = chunk * NT + probe_tile.  CTAs running at the same time work on
+// the same few gallery chunks (L2-hot, read from HBM once) and on different probe tiles, so a probe
+// row is rarely screened by two CTAs at once and its running threshold stays tight.
 __device__ __forceinline__ bool decode_unit(const ScreenParams &p, int64_t u, UnitIter &it)
 {
-    const int64_t ups = p.NT * p.cps;
-    const int64_t slab = u / ups, r = u % ups;
+    const int64_t chunk = u / p.NT;
     it.u = u;
-    it.jt = r / p.cps;
-    const int64_t chunk = slab * p.cps + (r % p.cps);
-    if (chunk >= p.n_chunks) return false;
+    it.jt = u % p.NT;
     it.gt0 = chunk * p.TPU;
     it.gt1 = min(it.gt0 + p.TPU, p.GT);
     return it.gt0 < it.gt1;
@@ -444,9 +409,14 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             named_bar_sync(1, 32 * kEpiWarps);
 
             for (int64_t gt = it.gt0; gt < it.gt1; ++gt) {
+                // pick up thresholds tightened by other CTAs since the last tile (benign race)
+                if (te < BN) {
+                    const int32_t rm = tl->row[te];
+                    if (rm >= 0) atomicMin(&tl->thr[te], *reinterpret_cast<volatile unsigned int *>(p.gthr + rm));
+                }
                 mbar_wait(&tl->tfull[acc], accphase);
                 tc_fence_after();
-                const int64_t g = gt * kBM + q * 32 + lane;
+                const int64_t g = (gt * kBM + q * 32 + lane) * p.g_stride;
                 const float nb = p.gnorm[g];
                 const uint32_t trow = tmem_base + static_cast<uint32_t>(acc) * kMaxBN + (static_cast<uint32_t>(q * 32) << 16);
 
@@ -512,40 +482,58 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     const bool need = any || (minx < xfloor) || (fminf(dprev_in, dn) < dfloor);
                     if (__any_sync(0xffffffffu, need)) {
-                        // ---- rare path: append candidates, tighten thresholds ----
-                        if (need && g < p.G) {
+                        // ---- rare path (whole warp): tighten the threshold with the warp minimum first,
+                        //      then append what is still below it, one atomicAdd per warp and column ----
+                        const bool rowok = g < p.G;
 #pragma unroll
-                            for (int j = 0; j < kChunk; ++j) {
-                                const int c = c0 + j;
-                                const int32_t rm = tl->row[c];
-                                if (rm < 0) continue;
-                                const float dl = j ? d[j - 1] : dprev_in;
-                                const float dr = (j < kChunk - 1) ? d[j + 1] : dn;
-                                const float m3 = fminf(d[j], fminf(tl->wl[c] > 0.f ? dl : kBig,
-                                                                   tl->wr[c] > 0.f ? dr : kBig));
-                                const bool uns = m3 < dfloor;
-                                const float thr = __uint_as_float(*reinterpret_cast<volatile unsigned int *>(&tl->thr[c]));
-                                if (uns || t[j] <= thr) {
-                                    const unsigned long long pos = atomicAdd(&p.ctr->cand_count, 1ull);
-                                    if (pos < static_cast<unsigned long long>(p.cand_cap)) {
+                        for (int j = 0; j < kChunk; ++j) {
+                            const int c = c0 + j;
+                            const int32_t rm = tl->row[c];
+                            if (rm < 0) continue;                          // warp-uniform
+                            const float dl = j ? d[j - 1] : dprev_in;
+                            const float dr = (j < kChunk - 1) ? d[j + 1] : dn;
+                            const float m3 = fminf(d[j], fminf(tl->wl[c] > 0.f ? dl : kBig,
+                                                               tl->wr[c] > 0.f ? dr : kBig));
+                            const bool uns = rowok && (m3 < dfloor);
+                            float thr = __uint_as_float(*reinterpret_cast<volatile unsigned int *>(&tl->thr[c]));
+                            bool pass = rowok && !uns && (t[j] <= thr);
+                            if (__ballot_sync(0xffffffffu, pass)) {
+                                float mn = pass ? t[j] : kBig;
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                                const float nt = fmaf(mn, kSlopMul, tl->mg[c]);
+                                if (nt < thr) {
+                                    if (lane == 0) {
+                                        atomicMin(&tl->thr[c], __float_as_uint(nt));
+                                        atomicMin(p.gthr + rm, __float_as_uint(nt));
+                                    }
+                                    thr = nt;
+                                }
+                                pass = pass && (t[j] <= thr);
+                            }
+                            if (p.seed_mode) continue;
+                            const bool app = pass || uns;
+                            const unsigned ma = __ballot_sync(0xffffffffu, app);
+                            if (ma) {
+                                unsigned base = 0;
+                                if (lane == 0) base = atomicAdd(p.rowcnt + rm, static_cast<unsigned>(__popc(ma)));
+                                base = __shfl_sync(0xffffffffu, base, 0);
+                                if (app) {
+                                    const unsigned pos = base + __popc(ma & ((1u << lane) - 1u));
+                                    if (pos < static_cast<unsigned>(p.cand_cap)) {
                                         Cand cd;
-                                        cd.p = rm; cd.g = static_cast<int32_t>(g);
-                                        cd.tbits = __float_as_uint(t[j]); cd.unsafe = uns ? 1u : 0u;
-                                        p.cand[pos] = cd;
+                                        cd.g = static_cast<int32_t>(g);
+                                        cd.tbits = uns ? kCandUnsafe : __float_as_uint(t[j]);
+                                        p.cand[static_cast<int64_t>(rm) * p.cand_cap + pos] = cd;
                                     } else {
                                         p.rowflag[rm] = 1;
-                                        atomicAdd(&p.ctr->overflow, 1u);
-                                    }
-                                    if (!uns) {
-                                        const unsigned int nb2 = __float_as_uint(fmaf(t[j], kSlopMul, tl->mg[c]));
-                                        atomicMin(&tl->thr[c], nb2);
-                                        atomicMin(p.gthr + rm, nb2);
+                                        p.ctr->overflow = 1u;
                                     }
                                 }
                             }
                         }
                     }
-                    if (p.dbg != nullptr && g < p.G) {
+                    if (p.dbg != nullptr && g < p.G && !p.seed_mode) {
 #pragma unroll
                         for (int j = 0; j < kChunk; ++j) {
                             const int32_t rm = tl->row[c0 + j];
@@ -604,7 +592,8 @@ struct RerankParams {
     int32_t D, rpe;
     float lam1, lam2;
     const Cand *cand;
-    int64_t cand_cap;
+    const unsigned int *rowcnt;
+    int32_t cand_cap;
     Counters *ctr;
     const unsigned int *gthr;
     unsigned long long *best;
@@ -612,25 +601,46 @@ struct RerankParams {
     int32_t *flaglist;
 };
 
+// One warp per probe row: keep the candidates still below the row's FINAL threshold, evaluate them
+// exactly, and keep the smallest packed (score, index).  The three probe rows stay in L1 across the
+// row's candidates.
 __global__ void k_rerank(const RerankParams p)
 {
     const int lane = threadIdx.x & 31;
     const int64_t nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-    int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const unsigned long long cnt = p.ctr->cand_count;
-    const int64_t n = cnt < static_cast<unsigned long long>(p.cand_cap) ? static_cast<int64_t>(cnt) : p.cand_cap;
-    unsigned long long done = 0, uns = 0;
-    for (; w < n; w += nw) {
-        const Cand c = p.cand[w];
-        if (!c.unsafe && __uint_as_float(c.tbits) > __uint_as_float(p.gthr[c.p])) continue;
-        const float t = exact_t(p.probes, p.P, p.D, p.rpe, c.p, p.gal + static_cast<int64_t>(c.g) * p.D,
-                                p.lam1, p.lam2, lane);
-        if (lane == 0) {
-            atomicMin(p.best + c.p, pack_score_idx(t, static_cast<uint32_t>(p.offset + c.g)));
-            ++done; uns += c.unsafe;
+    unsigned long long appended = 0, done = 0, uns = 0;
+    for (int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < p.P; row += nw) {
+        const unsigned cnt = p.rowcnt[row];
+        const int n = cnt < static_cast<unsigned>(p.cand_cap) ? static_cast<int>(cnt) : p.cand_cap;
+        appended += cnt;
+        const float thr = __uint_as_float(p.gthr[row]);
+        const Cand *list = p.cand + row * p.cand_cap;
+        unsigned long long loc = ~0ull;
+        for (int b0 = 0; b0 < n; b0 += 32) {
+            Cand c;
+            c.g = 0; c.tbits = 0x7f800000u;
+            if (b0 + lane < n) c = list[b0 + lane];
+            const bool keep = (b0 + lane < n) && (c.tbits == kCandUnsafe || __uint_as_float(c.tbits) <= thr);
+            unsigned m = __ballot_sync(0xffffffffu, keep);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int32_t g = __shfl_sync(0xffffffffu, c.g, src);
+                const uint32_t tb = __shfl_sync(0xffffffffu, c.tbits, src);
+                const float t = exact_t(p.probes, p.P, p.D, p.rpe, row, p.gal + static_cast<int64_t>(g) * p.D,
+                                        p.lam1, p.lam2, lane);
+                const unsigned long long v = pack_score_idx(t, static_cast<uint32_t>(p.offset + g));
+                loc = v < loc ? v : loc;
+                ++done; uns += (tb == kCandUnsafe);
+            }
         }
+        if (lane == 0 && loc != ~0ull) atomicMin(p.best + row, loc);
     }
-    if (lane == 0 && done) { atomicAdd(&p.ctr->n_exact, done); atomicAdd(&p.ctr->n_unsafe, uns); }
+    if (lane == 0) {
+        if (appended) atomicAdd(&p.ctr->cand_count, appended);
+        if (done) atomicAdd(&p.ctr->n_exact, done);
+        if (uns) atomicAdd(&p.ctr->n_unsafe, uns);
+    }
 }
 
 // Rows whose candidates overflowed the list (or all rows, for eosvr_match_exact) are resolved by
@@ -713,6 +723,37 @@ int launch_merge(const uint64_t *gathered, int32_t nshards, int64_t P, uint64_t 
 // -------------------------------------------------------------------------------------------
 static int g_num_sms = 0;
 
+static int launch_screen(const eosvr_gallery *g, eosvr_workspace *ws, const MatchPlan &pl, const CUtensorMap &tmA,
+                         const CUtensorMap &tmB, int64_t gallery_tiles, int64_t g_stride, int seed_mode, int64_t P,
+                         bool timed, cudaStream_t st)
+{
+    ScreenParams sp;
+    sp.gnorm = g->gnorm; sp.G = g->G; sp.KB = g->Dp / kBK; sp.BN = pl.BN; sp.NT = pl.NT;
+    sp.GT = gallery_tiles;
+    const int64_t total_tiles = sp.NT * sp.GT;
+    int64_t tpu = total_tiles / (static_cast<int64_t>(g_num_sms) * 6);
+    if (tpu < 1) tpu = 1;
+    if (tpu > 16) tpu = 16;
+    if (tpu > sp.GT) tpu = sp.GT;
+    sp.TPU = static_cast<int32_t>(tpu);
+    sp.n_chunks = (sp.GT + tpu - 1) / tpu;
+    sp.n_units = sp.n_chunks * sp.NT;
+    sp.g_stride = g_stride; sp.seed_mode = seed_mode;
+    sp.na = ws->na; sp.wl = ws->wl; sp.wr = ws->wr; sp.margin = ws->margin; sp.rowmap = ws->rowmap;
+    sp.gthr = ws->gthr; sp.cand = ws->cand; sp.rowcnt = ws->rowcnt; sp.cand_cap = static_cast<int32_t>(ws->cand_cap);
+    sp.ctr = ws->counters; sp.rowflag = ws->rowflag;
+    sp.idesc = umma_idesc_f16(g->screen_fmt == EOSVR_SCREEN_F16 ? 0 : 1, kBM, pl.BN);
+    sp.dbg = (!seed_mode && ws->dbg && ws->dbg_elems >= P * g->G) ? ws->dbg : nullptr;
+    const unsigned grid = static_cast<unsigned>(sp.n_units < g_num_sms ? sp.n_units : g_num_sms);
+    const bool rec = timed && ws->timing_on && ws->timing_calls < kTimingRing;
+    if (rec) EOSVR_CUDA(cudaEventRecord(ws->ev0[ws->timing_calls], st));
+    k_match_screen<<<grid, kThreads, kScreenSmem, st>>>(tmA, tmB, sp);
+    EOSVR_CUDA(cudaGetLastError());
+    if (rec) { EOSVR_CUDA(cudaEventRecord(ws->ev1[ws->timing_calls], st)); ++ws->timing_calls; }
+    EOSVR_COUNT_LAUNCH(1);
+    return EOSVR_OK;
+}
+
 int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int64_t P,
                  int32_t rpe, float lam1, float lam2, bool exact_only, uint64_t *out_packed,
                  float *out_score, int64_t *out_idx, cudaStream_t st)
@@ -733,13 +774,15 @@ int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probe
     const int threads = 256;
 
     k_reset<<<static_cast<unsigned>((P + threads - 1) / threads), threads, 0, st>>>(
-        ws->counters, ws->best, ws->rowflag, P, exact_only ? 1 : 0);
+        ws->counters, ws->best, ws->rowflag, ws->rowcnt, ws->gthr, P, exact_only ? 1 : 0);
     EOSVR_CUDA(cudaGetLastError());
+    EOSVR_COUNT_LAUNCH(1);
 
     RerankParams rp;
     rp.probes = probes; rp.gal = g->feats; rp.P = P; rp.G = g->G; rp.offset = g->offset;
     rp.D = g->D; rp.rpe = rpe; rp.lam1 = lam1; rp.lam2 = lam2;
-    rp.cand = ws->cand; rp.cand_cap = ws->cand_cap; rp.ctr = ws->counters; rp.gthr = ws->gthr;
+    rp.cand = ws->cand; rp.rowcnt = ws->rowcnt; rp.cand_cap = static_cast<int32_t>(ws->cand_cap);
+    rp.ctr = ws->counters; rp.gthr = ws->gthr;
     rp.best = ws->best; rp.rowflag = ws->rowflag; rp.flaglist = ws->flaglist;
 
     ws->last_tiles = 0;
@@ -753,54 +796,31 @@ int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probe
             k_probe_prep<__nv_bfloat16><<<pblocks, threads, 0, st>>>(probes, pd, g->D, g->Dp, g->scalars,
                 static_cast<__nv_bfloat16 *>(ws->q16), ws->na, ws->epsd, ws->rowmap, ws->counters);
         EOSVR_CUDA(cudaGetLastError());
-        k_seed_dist<<<static_cast<unsigned>((P * kSeedSamples * 32 + threads - 1) / threads), threads, 0, st>>>(
-            probes, P, g->D, g->feats, g->G, ws->dsamp);
+        k_column_plan<<<static_cast<unsigned>((ncol + threads - 1) / threads), threads, 0, st>>>(
+            pd, lam1 / lam2, ws->epsd, ws->wl, ws->wr, ws->margin);
         EOSVR_CUDA(cudaGetLastError());
-        const int64_t nthr = ncol > P ? ncol : P;
-        k_column_plan<<<static_cast<unsigned>((nthr + threads - 1) / threads), threads, 0, st>>>(
-            pd, lam1 / lam2, ws->epsd, ws->wl, ws->wr, ws->margin, ws->dsamp, ws->gthr);
-        EOSVR_CUDA(cudaGetLastError());
+        EOSVR_COUNT_LAUNCH(2);
 
         CUtensorMap tmB;
         int rc = encode_tmap_2d(&tmB, ws->q16, g->screen_fmt, static_cast<uint64_t>(ncol),
                                 static_cast<uint64_t>(g->Dp), static_cast<uint32_t>(pl.BN), kBK);
         if (rc) return rc;
-
-        ScreenParams sp;
-        sp.gnorm = g->gnorm; sp.G = g->G; sp.KB = g->Dp / kBK; sp.BN = pl.BN; sp.NT = pl.NT;
-        sp.GT = (g->G + kBM - 1) / kBM;
-        const int64_t total_tiles = sp.NT * sp.GT;
-        int64_t tpu = total_tiles / (static_cast<int64_t>(g_num_sms) * 6);
-        if (tpu < 1) tpu = 1;
-        if (tpu > 32) tpu = 32;
-        sp.TPU = static_cast<int32_t>(tpu);
-        sp.n_chunks = (sp.GT + tpu - 1) / tpu;
-        int64_t slab_tiles = (static_cast<int64_t>(48) << 20) / (static_cast<int64_t>(kBM) * g->Dp * 2);
-        int64_t cps = slab_tiles / tpu;
-        if (cps < 1) cps = 1;
-        if (cps > sp.n_chunks) cps = sp.n_chunks;
-        sp.cps = cps;
-        const int64_t n_slabs = (sp.n_chunks + cps - 1) / cps;
-        sp.n_units = n_slabs * sp.NT * cps;
-        sp.na = ws->na; sp.wl = ws->wl; sp.wr = ws->wr; sp.margin = ws->margin; sp.rowmap = ws->rowmap;
-        sp.gthr = ws->gthr; sp.cand = ws->cand; sp.cand_cap = ws->cand_cap; sp.ctr = ws->counters;
-        sp.rowflag = ws->rowflag;
-        sp.idesc = umma_idesc_f16(g->screen_fmt == EOSVR_SCREEN_F16 ? 0 : 1, kBM, pl.BN);
-        sp.dbg = (ws->dbg && ws->dbg_elems >= P * g->G) ? ws->dbg : nullptr;
-        ws->last_tiles = total_tiles;
-
         EOSVR_CUDA(cudaFuncSetAttribute(k_match_screen, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(kScreenSmem)));
-        const unsigned grid = static_cast<unsigned>(sp.n_units < g_num_sms ? sp.n_units : g_num_sms);
-        const bool timed = ws->timing_on && ws->timing_calls < kTimingRing;
-        if (timed) EOSVR_CUDA(cudaEventRecord(ws->ev0[ws->timing_calls], st));
-        k_match_screen<<<grid, kThreads, kScreenSmem, st>>>(g->tmapA, tmB, sp);
-        EOSVR_CUDA(cudaGetLastError());
-        if (timed) { EOSVR_CUDA(cudaEventRecord(ws->ev1[ws->timing_calls], st)); ++ws->timing_calls; }
-        EOSVR_COUNT_LAUNCH(5);   // probe_prep, seed_dist, column_plan, match_screen, rerank
+        const int64_t GT = (g->G + kBM - 1) / kBM;
+        // seed pass over a strided sample of the gallery: tightens every probe row's threshold before the
+        // full pass so that concurrent CTAs do not flood the candidate lists
+        if (g->seed_tiles > 0 && GT > g->seed_tiles) {
+            rc = launch_screen(g, ws, pl, g->tmapSeed, tmB, g->seed_tiles, g->seed_stride, 1, P, false, st);
+            if (rc) return rc;
+        }
+        rc = launch_screen(g, ws, pl, g->tmapA, tmB, GT, 1, 0, P, true, st);
+        if (rc) return rc;
+        ws->last_tiles = pl.NT * GT;
 
-        k_rerank<<<g_num_sms * 4, 256, 0, st>>>(rp);
+        k_rerank<<<g_num_sms * 8, 256, 0, st>>>(rp);
         EOSVR_CUDA(cudaGetLastError());
+        EOSVR_COUNT_LAUNCH(1);
     }
     k_compact_flags<<<64, 256, 0, st>>>(rp);
     EOSVR_CUDA(cudaGetLastError());
@@ -809,7 +829,7 @@ int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probe
     k_finalize<<<static_cast<unsigned>((P + threads - 1) / threads), threads, 0, st>>>(
         ws->best, P, out_packed, out_score, out_idx);
     EOSVR_CUDA(cudaGetLastError());
-    EOSVR_COUNT_LAUNCH(4);       // reset, compact_flags, exact_fallback, finalize
+    EOSVR_COUNT_LAUNCH(3);
     return EOSVR_OK;
 }
 

@@ -224,6 +224,45 @@ def proto_score(support: torch.Tensor, support_y: torch.Tensor, query: torch.Ten
     return dict(pred=pred, dist=dist, prob=prob, nproto=nproto)
 
 
+def episode_score(probes: torch.Tensor, support_y: torch.Tensor, query: torch.Tensor, n: int, S: int,
+                  winner_rows: torch.Tensor | None = None, gallery: GalleryFeatureCache | None = None,
+                  idx: torch.Tensor | None = None, orig_mode: int = ORIG_REF_QUIRK, max_proto: int = 0, stream=None):
+    """Fused splice_augmented + proto_score (network_test.py:220-259 + classifier.py:9-90) without writing the
+    augmented support set.  probes [E*n*S, D]; support_y [E, n] (one label per clip); query [E, Q, D]; winner
+    rows either given ([E*n*S, D]) or read from `gallery` through the global indices `idx` [E*n*S]."""
+    D = int(probes.shape[-1])
+    probes = _dev_f32(probes, "probes").reshape(-1, D)
+    support_y, query = _dev_f32(support_y, "support_y"), _dev_f32(query, "query")
+    if probes.shape[0] % (n * S):
+        raise ValueError("probes must be [E*n*S, D]")
+    E = probes.shape[0] // (n * S)
+    if tuple(support_y.shape) != (E, n) or query.dim() != 3 or query.shape[0] != E:
+        raise ValueError("support_y [E,n] and query [E,Q,D] expected")
+    Q = int(query.shape[1])
+    if winner_rows is not None:
+        winner_rows = _dev_f32(winner_rows, "winner_rows").reshape(-1, D)
+        if winner_rows.shape != probes.shape:
+            raise ValueError("winner_rows must be [E*n*S, D]")
+    elif gallery is None or idx is None:
+        raise ValueError("need winner_rows, or gallery and idx")
+    else:
+        idx = idx.contiguous().view(-1)
+        if idx.dtype != torch.int64 or idx.numel() != probes.shape[0]:
+            raise ValueError("idx must be int64 [E*n*S]")
+    mp = int(max_proto) if max_proto else min(n, 64)
+    dev = probes.device
+    dist = torch.empty(E, Q, mp, dtype=torch.float32, device=dev)
+    prob = torch.empty(E, Q, mp, dtype=torch.float32, device=dev)
+    pred = torch.empty(E, Q, dtype=torch.int64, device=dev)
+    nproto = torch.empty(E, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().eosvr_episode_score(_ptr(probes), _ptr(winner_rows), gallery.handle if gallery is not None else None,
+                                        _ptr(idx), _ptr(support_y), _ptr(query), E, int(n), int(S), Q, D, int(orig_mode),
+                                        mp, _ptr(dist), _ptr(prob), _ptr(pred), _ptr(nproto), _stream_ptr(stream)),
+              "eosvr_episode_score")
+    return dict(pred=pred, dist=dist, prob=prob, nproto=nproto)
+
+
 def segment_features(frames: torch.Tensor, seg_len: int, l2: bool = True, stream=None) -> torch.Tensor:
     """network_test.py:187-189 / :203-205 (+ per-frame L2 of :79-80): [N*seg_len, D] -> [N, D]."""
     frames = _dev_f32(frames, "frames")
@@ -256,13 +295,16 @@ class EpisodePipeline:
         self.group = group
         self.ws = MatchWorkspace(max_episodes * self.rpe, gallery.D, cand_capacity, device=gallery.device)
 
-    def run(self, probes: torch.Tensor, support_y: torch.Tensor, query: torch.Tensor, stream=None) -> dict:
+    def run(self, probes: torch.Tensor, support_y: torch.Tensor, query: torch.Tensor, stream=None,
+            return_support: bool = False) -> dict:
         """probes [E, n, S, D] (device), support_y [E, n] float32, query [E, Q, D].
-        Returns dict(pred [E,Q], idx [E,n,S], score [E,n,S], dist, prob)."""
+        Returns dict(pred [E,Q], idx [E,n,S], score [E,n,S], dist, prob).  return_support=True goes through the
+        un-fused splice + proto_score calls and also returns the augmented support set."""
         E = int(probes.shape[0])
         D = self.gallery.D
         flat = probes.reshape(E * self.rpe, D)
         idx, score, packed = match_segments(self.gallery, self.ws, flat, self.rpe, self.lam1, self.lam2, True, stream)
+        rows = None
         if self.group is not None:
             import torch.distributed as dist
             ws = dist.get_world_size(self.group)
@@ -271,13 +313,18 @@ class EpisodePipeline:
             idx, score, packed = merge_top1(gathered, stream)
             rows = gather_winner_rows(self.gallery, idx, stream)
             dist.all_reduce(rows, group=self.group)          # one non-zero contributor per row: exact
+        y = support_y.to(torch.float32)
+        if return_support:
+            if rows is None:
+                rows = gather_winner_rows(self.gallery, idx, stream)
+            aug = splice_augmented(flat, rows, self.n, self.S, self.orig_mode, stream)
+            labels = y.repeat_interleave(1 + self.S, dim=1).contiguous()
+            res = proto_score(aug, labels, query, self.n_way, stream)
+            res.update(support_feature=aug, support_y=labels)
         else:
-            rows = gather_winner_rows(self.gallery, idx, stream)
-        aug = splice_augmented(flat, rows, self.n, self.S, self.orig_mode, stream)
-        labels = support_y.to(torch.float32).repeat_interleave(1 + self.S, dim=1).contiguous()
-        res = proto_score(aug, labels, query, self.n_way, stream)
-        res.update(idx=idx.view(E, self.n, self.S), score=score.view(E, self.n, self.S), support_feature=aug,
-                   support_y=labels)
+            res = episode_score(flat, y, query, self.n, self.S, winner_rows=rows, gallery=self.gallery, idx=idx,
+                                orig_mode=self.orig_mode, max_proto=self.n_way, stream=stream)
+        res.update(idx=idx.view(E, self.n, self.S), score=score.view(E, self.n, self.S))
         return res
 
     def run_host(self, probes_host: torch.Tensor, support_y_host: torch.Tensor, query_host: torch.Tensor) -> dict:

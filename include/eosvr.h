@@ -144,6 +144,20 @@ int eosvr_proto_score(const float *d_support, const float *d_support_y, const fl
                       float *d_dist, float *d_prob, int64_t *d_pred, int32_t *d_nproto,
                       void *stream);
 
+/* ---- fused augmented-clip assembly + ProtoNet scoring -------------------------------
+ * eosvr_splice followed by eosvr_proto_score for E episodes of n support clips x S segments,
+ * without writing the augmented support set (network_test.py:220-259, classifier.py:9-90):
+ * every clip contributes its "original" row and its S spliced rows, all labelled
+ * d_support_y[e, i] (network_test.py:225,:232,:248).  Winner rows come from d_winner_rows
+ * [E*n*S, D] when given (multi-GPU, after the shard exchange), else straight from gallery g
+ * through the global indices d_idx [E*n*S] (rows g does not own read as zero).
+ * Bit-equal to the two-call path.  Outputs as in eosvr_proto_score. */
+int eosvr_episode_score(const float *d_probes, const float *d_winner_rows, const eosvr_gallery_t *g,
+                        const int64_t *d_idx, const float *d_support_y, const float *d_query,
+                        int64_t E, int32_t n, int32_t S, int32_t Q, int32_t D, int32_t orig_mode,
+                        int32_t max_proto, float *d_dist, float *d_prob, int64_t *d_pred,
+                        int32_t *d_nproto, void *stream);
+
 /* ---- gallery / probe cache builder -------------------------------------------------
  * Replaces np.resize + np.mean of network_test.py:188-189 / :204-205 (+ per-frame
  * F.normalize of :79-80 when l2 != 0): d_frames [N*seg_len, D] -> d_out [N, D]. */

@@ -124,6 +124,24 @@ def test_match_ties_and_cancellation():
     assert oid[3] == 7 and r["stats"]["unsafe"] > 0
 
 
+def test_overflow_goes_to_exact_fallback():
+    """More exact ties than a probe row's candidate list can hold: the row is resolved by the exhaustive exact
+    kernel and still returns the lowest index."""
+    ep = synth.episode_batch(15, 1, 5, 1, 4, 64)
+    gal = synth.gallery(65, 900, 64, centroid_seed=15)
+    A = ep["probe"].reshape(-1, 64)
+    base, _ = O.c_match(A, gal, 20)
+    gal = gal.copy()
+    gal[300:700] = gal[base[2]]                     # 400 exact duplicates of probe row 2's winner
+    oid, oval = O.c_match(A, gal, 20)
+    cache = ev.GalleryFeatureCache(_cuda(gal))
+    ws = ev.MatchWorkspace(20, 64, cand_capacity=20 * 32)
+    idx, score = ev.match_segments(cache, ws, _cuda(A), 20)
+    st = ws.stats()
+    assert st["fallback_rows"] >= 1 and st["overflow"] >= 1, st
+    assert np.array_equal(idx.cpu().numpy(), oid) and np.array_equal(score.cpu().numpy(), oval)
+
+
 def test_screening_error_within_margin():
     """The tensor-core screening values must lie within the rigorous error margin used for the candidate
     test; checked on every element of a small case through the debug dump."""
@@ -190,7 +208,7 @@ def test_golden_augseg(golden_dir, tag):
     probes = np.stack(eps)
     query = np.stack([fx[f"e{e}_query"] for e in range(E)])
     y = np.tile(np.arange(n_way, dtype=np.float32), (E, 1))
-    r = pipe.run(_cuda(probes), _cuda(y), _cuda(query))
+    r = pipe.run(_cuda(probes), _cuda(y), _cuda(query), return_support=True)
     torch.cuda.synchronize()
     sub = slice(None, None, 16)
     for e in range(E):
@@ -241,7 +259,10 @@ def test_episode_pipeline_vs_oracle(mode):
     gal = synth.gallery(seed + 50, G, D, centroid_seed=seed)
     cache = ev.GalleryFeatureCache(_cuda(gal))
     pipe = ev.EpisodePipeline(cache, n_way, 1, S, E, orig_mode=mode)
-    r = pipe.run(_cuda(ep["probe"]), _cuda(ep["support_y"]), _cuda(ep["query"]))
+    r = pipe.run(_cuda(ep["probe"]), _cuda(ep["support_y"]), _cuda(ep["query"]), return_support=True)
+    f = pipe.run(_cuda(ep["probe"]), _cuda(ep["support_y"]), _cuda(ep["query"]))
+    for k in ("pred", "dist", "prob", "idx", "score"):
+        assert torch.equal(r[k], f[k]), f"fused path differs in {k}"
     for e in range(E):
         o = O.lib_episode(ep["probe"][e], ep["support_y"][e], ep["query"][e], gal, orig_mode=mode)
         assert np.array_equal(r["idx"][e].cpu().numpy(), o["ids"])
@@ -260,7 +281,10 @@ def test_kshot5_and_multi_query():
     cache = ev.GalleryFeatureCache(_cuda(gal))
     pipe = ev.EpisodePipeline(cache, n_way, k, S, E)
     q3 = np.concatenate([ep["query"], ep["query"] * np.float32(0.5), ep["probe"][:, :3].mean(axis=2)], axis=1)
-    r = pipe.run(_cuda(ep["probe"]), _cuda(ep["support_y"]), _cuda(q3))
+    r = pipe.run(_cuda(ep["probe"]), _cuda(ep["support_y"]), _cuda(q3), return_support=True)
+    f = pipe.run(_cuda(ep["probe"]), _cuda(ep["support_y"]), _cuda(q3))
+    for k in ("pred", "dist", "prob", "idx", "score"):
+        assert torch.equal(r[k], f[k]), f"fused path differs in {k}"
     for e in range(E):
         o = O.lib_episode(ep["probe"][e], ep["support_y"][e], q3[e], gal)
         assert np.array_equal(r["idx"][e].cpu().numpy(), o["ids"])

@@ -110,7 +110,7 @@ def case_episode():
     for mode in (ev.ORIG_REF_QUIRK, ev.ORIG_CLIP_MEAN):
         pipe = ev.EpisodePipeline(cache, n_way, 1, S, E, orig_mode=mode)
         r = pipe.run(torch.from_numpy(ep["probe"]).cuda(), torch.from_numpy(ep["support_y"]).cuda(),
-                     torch.from_numpy(ep["query"]).cuda())
+                     torch.from_numpy(ep["query"]).cuda(), return_support=True)
         torch.cuda.synchronize()
         for e in range(E):
             o = O.lib_episode(ep["probe"][e], ep["support_y"][e], ep["query"][e], gal, orig_mode=mode)
