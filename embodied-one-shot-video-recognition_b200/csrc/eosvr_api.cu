@@ -100,7 +100,7 @@ int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtyp
     g->G = G; g->D = D; g->Dp = (D + kBK - 1) / kBK * kBK;
     g->offset = global_offset; g->screen_fmt = screen_fmt;
     cudaGetDevice(&g->device);
-    const int64_t Gpad = (G + kBM - 1) / kBM * kBM;
+    const int64_t Gpad = (G + kPairM - 1) / kPairM * kPairM;
     if (cudaMalloc(&g->h16, static_cast<size_t>(Gpad) * g->Dp * 2) != cudaSuccess ||
         cudaMalloc(&g->gnorm, static_cast<size_t>(Gpad) * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&g->scalars, 4 * sizeof(float)) != cudaSuccess) {
@@ -112,13 +112,15 @@ int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtyp
     rc = launch_gallery_prep(g, static_cast<cudaStream_t>(stream));
     if (!rc) rc = encode_tmap_2d(&g->tmapA, g->h16, screen_fmt, static_cast<uint64_t>(Gpad), static_cast<uint64_t>(g->Dp), kBM, kBK, 1);
     // strided seed sample: seed_tiles tiles of rows {0, stride, 2*stride, ...}
-    const int64_t GT = Gpad / kBM;
-    int64_t st_tiles = GT / 40;
+    // (an ODD stride so that periodic class layouts of the gallery cannot alias with the sample)
+    const int64_t GT = Gpad / kPairM;
+    int64_t st_tiles = GT / 24;
     if (st_tiles < 1) st_tiles = 1;
     if (st_tiles > kMaxSeedTiles) st_tiles = kMaxSeedTiles;
     g->seed_tiles = static_cast<int32_t>(st_tiles);
-    g->seed_stride = Gpad / (st_tiles * kBM);
-    if (!rc) rc = encode_tmap_2d(&g->tmapSeed, g->h16, screen_fmt, static_cast<uint64_t>(st_tiles * kBM),
+    g->seed_stride = Gpad / (st_tiles * kPairM);
+    if (g->seed_stride > 1 && (g->seed_stride & 1) == 0) g->seed_stride -= 1;
+    if (!rc) rc = encode_tmap_2d(&g->tmapSeed, g->h16, screen_fmt, static_cast<uint64_t>(st_tiles * kPairM),
                                  static_cast<uint64_t>(g->Dp), kBM, kBK, static_cast<uint64_t>(g->seed_stride));
     if (rc) { eosvr_gallery_destroy(g); return rc; }
     *out = g;

@@ -10,16 +10,17 @@
 namespace eosvr {
 
 // ---- tiling constants of the screening kernel ----------------------------------------
-constexpr int kBM = 128;          // gallery rows per tile  (UMMA M, one TMEM lane per row)
+constexpr int kBM = 128;          // gallery rows per CTA and tile (one TMEM lane per row)
+constexpr int kPairM = 256;       // gallery rows per CTA pair and tile (UMMA M with cta_group::2)
 constexpr int kBK = 64;           // K elements per pipeline stage (128-byte rows, SWIZZLE_128B)
 constexpr int kMaxBN = 256;       // probe columns per tile (UMMA N), multiple of 16
-constexpr int kStages = 4;        // TMA -> MMA smem ring
+constexpr int kStages = 6;        // TMA -> MMA smem ring (16 KiB A + 16 KiB B-half per stage and CTA)
 constexpr int kAccStages = 2;     // TMEM accumulator double buffer (2 x 256 columns)
 constexpr int kTmemCols = 512;
 constexpr int kEpiWarps = 8;      // warps 4..11
 constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kChunk = 16;        // TMEM columns per tcgen05.ld
-constexpr int kMaxSeedTiles = 4;  // strided gallery tiles screened first to seed the per-probe thresholds
+constexpr int kMaxSeedTiles = 2;  // strided gallery tiles screened first to seed the per-probe thresholds
 constexpr float kPadNorm = 1.0e30f;
 constexpr int kTimingRing = 256;  // event pairs kept for eosvr_workspace_screen_ms
 

@@ -103,7 +103,7 @@ __global__ void k_gallery_prep(const float *__restrict__ feats, int64_t G, int64
 
 int launch_gallery_prep(eosvr_gallery *g, cudaStream_t st)
 {
-    const int64_t Gpad = (g->G + kBM - 1) / kBM * kBM;
+    const int64_t Gpad = (g->G + kPairM - 1) / kPairM * kPairM;
     EOSVR_CUDA(cudaMemsetAsync(g->scalars, 0, 4 * sizeof(float), st));
     const int threads = 256;
     const int64_t blocks = (Gpad * 32 + threads - 1) / threads;
@@ -280,8 +280,8 @@ struct __align__(16) ScreenSmemTail {
     uint32_t tmem_base;
 };
 
-constexpr int kABytes = kBM * kBK * 2;          // 16 KiB
-constexpr int kBBytes = kMaxBN * kBK * 2;       // 32 KiB
+constexpr int kABytes = kBM * kBK * 2;              // 16 KiB: this CTA's 128 gallery rows
+constexpr int kBBytes = (kMaxBN / 2) * kBK * 2;     // 16 KiB: this CTA's half of the probe tile
 constexpr size_t kScreenSmem = 1024 + static_cast<size_t>(kStages) * (kABytes + kBBytes) + sizeof(ScreenSmemTail);
 
 struct UnitIter {
@@ -301,7 +301,7 @@ __device__ __forceinline__ bool decode_unit(const ScreenParams &p, int64_t u, Un
     return it.gt0 < it.gt1;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ScreenParams p)
 {
@@ -313,47 +313,53 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();            // 0 = leader (issues the MMAs), 1 = peer
+    const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
-        for (int s = 0; s < kStages; ++s) { mbar_init(&tl->full[s], 1); mbar_init(&tl->empty[s], 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tl->tfull[s], 1); mbar_init(&tl->tempty[s], 32 * kEpiWarps); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&tl->full[s], 2); mbar_init(&tl->empty[s], 1); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tl->tfull[s], 1); mbar_init(&tl->tempty[s], 2 * kEpiWarps); }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc(&tl->tmem_base, kTmemCols);
+    if (warp == 2) tmem_alloc_2sm(&tl->tmem_base, kTmemCols);
     tc_fence_before();
-    __syncthreads();
+    cluster_sync();
     tc_fence_after();
     const uint32_t tmem_base = tl->tmem_base;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer (both CTAs): own 128 gallery rows + own half of the probe tile; the bytes of
+        //       both CTAs complete on the LEADER's full barrier =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            const uint32_t tx = kABytes + static_cast<uint32_t>(p.BN) * kBK * 2;
-            for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+            const int32_t bhalf = p.BN >> 1;
+            const uint32_t tx_pair = 2u * (kABytes + static_cast<uint32_t>(bhalf) * kBK * 2);
+            for (int64_t u = pair; u < p.n_units; u += npairs) {
                 UnitIter it;
                 if (!decode_unit(p, u, it)) continue;
                 for (int64_t gt = it.gt0; gt < it.gt1; ++gt) {
                     for (int kb = 0; kb < p.KB; ++kb) {
                         mbar_wait(&tl->empty[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&tl->full[stage], tx);
-                        tma_load_2d(sA + stage * kABytes, &tmA, &tl->full[stage], kb * kBK,
-                                    static_cast<int32_t>(gt * kBM));
-                        tma_load_2d(sB + stage * kBBytes, &tmB, &tl->full[stage], kb * kBK,
-                                    static_cast<int32_t>(it.jt * p.BN));
+                        const uint32_t lbar = mapa(smem_u32(&tl->full[stage]), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(&tl->full[stage], tx_pair);
+                        else mbar_arrive_cluster(lbar);
+                        tma_load_2d_2sm(sA + stage * kABytes, &tmA, lbar, kb * kBK,
+                                        static_cast<int32_t>(gt * kPairM + rank * kBM));
+                        tma_load_2d_2sm(sB + stage * kBBytes, &tmB, lbar, kb * kBK,
+                                        static_cast<int32_t>(it.jt * p.BN + rank * bhalf));
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        // ===== MMA issuer: one thread of the leader CTA drives the tensor cores of both SMs =====
+        if (lane == 0 && rank == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t accphase = 0;
-            for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+            for (int64_t u = pair; u < p.n_units; u += npairs) {
                 UnitIter it;
                 if (!decode_unit(p, u, it)) continue;
                 for (int64_t gt = it.gt0; gt < it.gt1; ++gt) {
@@ -367,12 +373,12 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t b0 = smem_u32(sB + stage * kBBytes);
 #pragma unroll
                         for (int k = 0; k < kBK / 16; ++k)
-                            mma_f16_ss(d_tmem, umma_desc_sw128(a0, k * 32), umma_desc_sw128(b0, k * 32),
-                                       p.idesc, (kb | k) != 0 ? 1u : 0u);
-                        mma_commit(&tl->empty[stage]);
+                            mma_f16_ss_2sm(d_tmem, umma_desc_sw128(a0, k * 32), umma_desc_sw128(b0, k * 32),
+                                           p.idesc, (kb | k) != 0 ? 1u : 0u);
+                        mma_commit_2sm(&tl->empty[stage], 3);       // frees the stage in both CTAs
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
-                    mma_commit(&tl->tfull[acc]);
+                    mma_commit_2sm(&tl->tfull[acc], 3);             // accumulators ready in both CTAs
                     if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
                 }
             }
@@ -390,7 +396,9 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float xfloor = __uint_as_float(p.ctr->xfloor_bits);
         const float dfloor = sqrtf(xfloor) * 1.000001f;
         int acc = 0; uint32_t accphase = 0;
-        for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const uint32_t tempty_leader0 = mapa(smem_u32(&tl->tempty[0]), 0);
+        const uint32_t tempty_leader1 = mapa(smem_u32(&tl->tempty[1]), 0);
+        for (int64_t u = pair; u < p.n_units; u += npairs) {
             UnitIter it;
             if (!decode_unit(p, u, it)) continue;
             // per-unit column arrays -> smem
@@ -416,7 +424,7 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 mbar_wait(&tl->tfull[acc], accphase);
                 tc_fence_after();
-                const int64_t g = (gt * kBM + q * 32 + lane) * p.g_stride;
+                const int64_t g = (gt * kPairM + rank * kBM + q * 32 + lane) * p.g_stride;
                 const float nb = p.gnorm[g];
                 const uint32_t trow = tmem_base + static_cast<uint32_t>(acc) * kMaxBN + (static_cast<uint32_t>(q * 32) << 16);
 
@@ -542,15 +550,16 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&tl->tempty[acc]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
                 if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
             }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+    cluster_sync();          // neither CTA may exit (or free TMEM) while its peer can still reach it
+    if (warp == 2) tmem_dealloc_2sm(tmem_base, kTmemCols);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -731,7 +740,7 @@ static int launch_screen(const eosvr_gallery *g, eosvr_workspace *ws, const Matc
     sp.gnorm = g->gnorm; sp.G = g->G; sp.KB = g->Dp / kBK; sp.BN = pl.BN; sp.NT = pl.NT;
     sp.GT = gallery_tiles;
     const int64_t total_tiles = sp.NT * sp.GT;
-    int64_t tpu = total_tiles / (static_cast<int64_t>(g_num_sms) * 6);
+    int64_t tpu = total_tiles / (static_cast<int64_t>(g_num_sms / 2) * 6);
     if (tpu < 1) tpu = 1;
     if (tpu > 16) tpu = 16;
     if (tpu > sp.GT) tpu = sp.GT;
@@ -742,9 +751,10 @@ static int launch_screen(const eosvr_gallery *g, eosvr_workspace *ws, const Matc
     sp.na = ws->na; sp.wl = ws->wl; sp.wr = ws->wr; sp.margin = ws->margin; sp.rowmap = ws->rowmap;
     sp.gthr = ws->gthr; sp.cand = ws->cand; sp.rowcnt = ws->rowcnt; sp.cand_cap = static_cast<int32_t>(ws->cand_cap);
     sp.ctr = ws->counters; sp.rowflag = ws->rowflag;
-    sp.idesc = umma_idesc_f16(g->screen_fmt == EOSVR_SCREEN_F16 ? 0 : 1, kBM, pl.BN);
+    sp.idesc = umma_idesc_f16(g->screen_fmt == EOSVR_SCREEN_F16 ? 0 : 1, kPairM, pl.BN);
     sp.dbg = (!seed_mode && ws->dbg && ws->dbg_elems >= P * g->G) ? ws->dbg : nullptr;
-    const unsigned grid = static_cast<unsigned>(sp.n_units < g_num_sms ? sp.n_units : g_num_sms);
+    const int64_t max_pairs = g_num_sms / 2;
+    const unsigned grid = 2u * static_cast<unsigned>(sp.n_units < max_pairs ? sp.n_units : max_pairs);
     const bool rec = timed && ws->timing_on && ws->timing_calls < kTimingRing;
     if (rec) EOSVR_CUDA(cudaEventRecord(ws->ev0[ws->timing_calls], st));
     k_match_screen<<<grid, kThreads, kScreenSmem, st>>>(tmA, tmB, sp);
@@ -803,11 +813,11 @@ int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probe
 
         CUtensorMap tmB;
         int rc = encode_tmap_2d(&tmB, ws->q16, g->screen_fmt, static_cast<uint64_t>(ncol),
-                                static_cast<uint64_t>(g->Dp), static_cast<uint32_t>(pl.BN), kBK);
+                                static_cast<uint64_t>(g->Dp), static_cast<uint32_t>(pl.BN / 2), kBK);
         if (rc) return rc;
         EOSVR_CUDA(cudaFuncSetAttribute(k_match_screen, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(kScreenSmem)));
-        const int64_t GT = (g->G + kBM - 1) / kBM;
+        const int64_t GT = (g->G + kPairM - 1) / kPairM;   // 256-row tiles of the CTA pair
         // seed pass over a strided sample of the gallery: tightens every probe row's threshold before the
         // full pass so that concurrent CTAs do not flood the candidate lists
         if (g->seed_tiles > 0 && GT > g->seed_tiles) {
