@@ -171,6 +171,8 @@ int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capac
     const size_t o_thr = carve(ws->maxP * 4), o_best = carve(ws->maxP * 8), o_rf = carve(ws->maxP * 4);
     const size_t o_fl = carve(ws->maxP * 4), o_rc = carve(ws->maxP * 4);
     const size_t o_cd = carve(static_cast<size_t>(ws->maxP) * ws->cand_cap * sizeof(Cand)), o_ct = carve(sizeof(Counters));
+    ws->ovf_cap = ws->maxP * 16 > (1ll << 16) ? ws->maxP * 16 : (1ll << 16);
+    const size_t o_ov = carve(static_cast<size_t>(ws->ovf_cap) * sizeof(OvfCand));
     if (cudaMalloc(&ws->slab, off) != cudaSuccess) {
         cudaGetLastError();
         set_error("workspace_create: device allocation of %zu bytes failed", off);
@@ -187,6 +189,7 @@ int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capac
     ws->rowflag = reinterpret_cast<int32_t *>(b + o_rf); ws->flaglist = reinterpret_cast<int32_t *>(b + o_fl);
     ws->rowcnt = reinterpret_cast<unsigned int *>(b + o_rc); ws->cand = reinterpret_cast<Cand *>(b + o_cd);
     ws->counters = reinterpret_cast<Counters *>(b + o_ct);
+    ws->ovf = reinterpret_cast<OvfCand *>(b + o_ov);
     *out = ws;
     return EOSVR_OK;
 }
@@ -298,7 +301,7 @@ int eosvr_match_stats(eosvr_workspace_t *ws, void *stream, int64_t out[8])
     out[4] = ws->last_tiles;
     out[5] = ws->last_bn;
     out[6] = static_cast<int64_t>(c.n_unsafe);
-    out[7] = c.overflow;
+    out[7] = c.ovf_count;
     return EOSVR_OK;
 }
 

@@ -46,6 +46,11 @@ struct Cand {
     uint32_t tbits;   // screening value (float bits); kCandUnsafe = inside the cancellation guard
 };
 constexpr uint32_t kCandUnsafe = 0xFFFFFFFFu;
+// spill-over entry for candidates that did not fit their row's list (shared buffer)
+struct OvfCand {
+    int32_t p, g;
+    uint32_t tbits, pad;
+};
 
 struct Counters {
     unsigned long long cand_count;   // appended (may exceed capacity)
@@ -54,7 +59,7 @@ struct Counters {
     unsigned int overflow;           // appends dropped
     unsigned int n_flag_rows;        // rows sent to the exact fallback
     unsigned int xfloor_bits;        // max over columns of the cancellation guard (x domain)
-    unsigned int pad;
+    unsigned int ovf_count;          // entries appended to the shared spill-over buffer
 };
 
 }  // namespace eosvr
@@ -91,6 +96,8 @@ struct eosvr_workspace {
     int32_t *flaglist;       // [maxP]
     unsigned int *rowcnt;    // [maxP] candidates appended per probe row
     eosvr::Cand *cand;       // [maxP, cand_cap]
+    eosvr::OvfCand *ovf;     // [ovf_cap] shared spill-over of full row lists
+    int64_t ovf_cap;
     eosvr::Counters *counters;
     float *dbg;              // optional [P,G] dump of screening values (tests)
     int64_t dbg_elems;

@@ -235,7 +235,7 @@ __global__ void k_reset(Counters *ctr, unsigned long long *best, int32_t *rowfla
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i == 0) {
         ctr->cand_count = 0; ctr->n_exact = 0; ctr->n_unsafe = 0;
-        ctr->overflow = flag_all ? 1u : 0u; ctr->n_flag_rows = 0; ctr->xfloor_bits = 0; ctr->pad = 0;
+        ctr->overflow = flag_all ? 1u : 0u; ctr->n_flag_rows = 0; ctr->xfloor_bits = 0; ctr->ovf_count = 0;
     }
     if (i < P) { best[i] = ~0ull; rowflag[i] = flag_all; rowcnt[i] = 0; gthr[i] = 0x7f800000u; }
 }
@@ -260,6 +260,8 @@ struct ScreenParams {
     Cand *cand;
     unsigned int *rowcnt;
     int32_t cand_cap;       // per probe row
+    OvfCand *ovf;           // shared spill-over buffer
+    int32_t ovf_cap;
     Counters *ctr;
     int32_t *rowflag;
     uint32_t idesc;
@@ -319,7 +321,7 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
-        for (int s = 0; s < kStages; ++s) { mbar_init(&tl->full[s], 2); mbar_init(&tl->empty[s], 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&tl->full[s], 1); mbar_init(&tl->empty[s], 1); }
         for (int s = 0; s < kAccStages; ++s) { mbar_init(&tl->tfull[s], 1); mbar_init(&tl->tempty[s], 2 * kEpiWarps); }
         fence_mbar_init();
     }
@@ -343,8 +345,10 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int kb = 0; kb < p.KB; ++kb) {
                         mbar_wait(&tl->empty[stage], phase ^ 1);
                         const uint32_t lbar = mapa(smem_u32(&tl->full[stage]), 0);
+                        // only the leader arrives (expecting the bytes of BOTH CTAs); the peer just issues its
+                        // loads -- it cannot run ahead of the phase because its stage is freed by the leader's
+                        // MMA commit
                         if (rank == 0) mbar_arrive_expect_tx(&tl->full[stage], tx_pair);
-                        else mbar_arrive_cluster(lbar);
                         tma_load_2d_2sm(sA + stage * kABytes, &tmA, lbar, kb * kBK,
                                         static_cast<int32_t>(gt * kPairM + rank * kBM));
                         tma_load_2d_2sm(sB + stage * kBBytes, &tmB, lbar, kb * kBK,
@@ -534,8 +538,18 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                         cd.tbits = uns ? kCandUnsafe : __float_as_uint(t[j]);
                                         p.cand[static_cast<int64_t>(rm) * p.cand_cap + pos] = cd;
                                     } else {
-                                        p.rowflag[rm] = 1;
-                                        p.ctr->overflow = 1u;
+                                        // row list full: spill to the shared buffer; only if that is full
+                                        // too is the row handed to the exhaustive exact kernel
+                                        const unsigned op = atomicAdd(&p.ctr->ovf_count, 1u);
+                                        if (op < static_cast<unsigned>(p.ovf_cap)) {
+                                            OvfCand oc;
+                                            oc.p = rm; oc.g = static_cast<int32_t>(g);
+                                            oc.tbits = uns ? kCandUnsafe : __float_as_uint(t[j]); oc.pad = 0;
+                                            p.ovf[op] = oc;
+                                        } else {
+                                            p.rowflag[rm] = 1;
+                                            p.ctr->overflow = 1u;
+                                        }
                                     }
                                 }
                             }
@@ -608,7 +622,28 @@ struct RerankParams {
     unsigned long long *best;
     int32_t *rowflag;
     int32_t *flaglist;
+    const OvfCand *ovf;
+    int32_t ovf_cap;
 };
+
+// Spill-over candidates (row lists that filled up): one warp per entry.  Exits at once when empty.
+__global__ void k_rerank_ovf(const RerankParams p)
+{
+    const unsigned cnt = p.ctr->ovf_count;
+    if (cnt == 0) return;
+    const int64_t n = cnt < static_cast<unsigned>(p.ovf_cap) ? cnt : p.ovf_cap;
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    unsigned long long done = 0;
+    for (int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < n; w += nw) {
+        const OvfCand c = p.ovf[w];
+        if (c.tbits != kCandUnsafe && __uint_as_float(c.tbits) > __uint_as_float(p.gthr[c.p])) continue;
+        const float t = exact_t(p.probes, p.P, p.D, p.rpe, c.p, p.gal + static_cast<int64_t>(c.g) * p.D,
+                                p.lam1, p.lam2, lane);
+        if (lane == 0) { atomicMin(p.best + c.p, pack_score_idx(t, static_cast<uint32_t>(p.offset + c.g))); ++done; }
+    }
+    if (lane == 0 && done) atomicAdd(&p.ctr->n_exact, done);
+}
 
 // One warp per probe row: keep the candidates still below the row's FINAL threshold, evaluate them
 // exactly, and keep the smallest packed (score, index).  The three probe rows stay in L1 across the
@@ -652,6 +687,140 @@ __global__ void k_rerank(const RerankParams p)
     }
 }
 
+// Block-per-row re-rank for D <= 128*EPT: the three probe rows the taps need are converted to float64
+// ONCE and kept in registers (EPT elements per thread and row); every surviving candidate then costs one
+// pass over its gallery row.  (fp32->fp64 conversions run at 16/clk/SM, so converting the probe rows per
+// candidate, as the warp-per-row kernel does, is what bounds it.)
+constexpr int kRrThreads = 128;
+constexpr int kRrBatch = 2;
+
+template <int EPT>
+__global__ void __launch_bounds__(kRrThreads)
+k_rerank_rows(const RerankParams p)
+{
+    static_assert(EPT % 4 == 0, "EPT must be a multiple of 4 (float4 loads)");
+    __shared__ int32_t s_g[kRrThreads];
+    __shared__ int s_warpcnt[kRrThreads / 32];
+    __shared__ double s_part[kRrThreads / 32][kRrBatch * 3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = p.D;
+    unsigned long long appended = 0, done = 0, unsafe_n = 0;
+
+    for (int64_t row = blockIdx.x; row < p.P; row += gridDim.x) {
+        const unsigned cnt = p.rowcnt[row];
+        const int n = cnt < static_cast<unsigned>(p.cand_cap) ? static_cast<int>(cnt) : p.cand_cap;
+        if (tid == 0) appended += cnt;
+        if (n == 0) continue;                                           // block-uniform
+        const int r = static_cast<int>(row % p.rpe);
+        const bool hl = r > 0, hr = (r + 1 < p.rpe) && (row + 1 < p.P);
+        const float *a1p = p.probes + row * D;
+        const float *a0p = hl ? a1p - D : a1p;
+        const float *a2p = hr ? a1p + D : a1p;
+        double a0[EPT], a1[EPT], a2[EPT];
+#pragma unroll
+        for (int i = 0; i < EPT / 4; ++i) {
+            const int k = 4 * (tid + kRrThreads * i);
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
+            if (k < D) {
+                v0 = *reinterpret_cast<const float4 *>(a0p + k);
+                v1 = *reinterpret_cast<const float4 *>(a1p + k);
+                v2 = *reinterpret_cast<const float4 *>(a2p + k);
+            }
+            a0[4 * i] = v0.x; a0[4 * i + 1] = v0.y; a0[4 * i + 2] = v0.z; a0[4 * i + 3] = v0.w;
+            a1[4 * i] = v1.x; a1[4 * i + 1] = v1.y; a1[4 * i + 2] = v1.z; a1[4 * i + 3] = v1.w;
+            a2[4 * i] = v2.x; a2[4 * i + 1] = v2.y; a2[4 * i + 2] = v2.z; a2[4 * i + 3] = v2.w;
+        }
+        const float thr = __uint_as_float(p.gthr[row]);
+        const Cand *list = p.cand + row * p.cand_cap;
+        unsigned long long loc = ~0ull;
+
+        for (int b0 = 0; b0 < n; b0 += kRrThreads) {
+            // ---- keep what is still below the row's final threshold; compact into s_g ----
+            Cand c;
+            c.g = 0; c.tbits = 0x7f800000u;
+            const bool in = b0 + tid < n;
+            if (in) c = list[b0 + tid];
+            const bool keep = in && (c.tbits == kCandUnsafe || __uint_as_float(c.tbits) <= thr);
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) s_warpcnt[warp] = __popc(m);
+            __syncthreads();
+            int base = 0, ns = 0;
+#pragma unroll
+            for (int w = 0; w < kRrThreads / 32; ++w) { if (w < warp) base += s_warpcnt[w]; ns += s_warpcnt[w]; }
+            if (keep) {
+                s_g[base + __popc(m & ((1u << lane) - 1u))] = c.g;
+                if (c.tbits == kCandUnsafe) ++unsafe_n;
+            }
+            __syncthreads();
+            // ---- exact evaluation, kRrBatch candidates per pass ----
+            for (int j0 = 0; j0 < ns; j0 += kRrBatch) {
+                double s[kRrBatch][3];
+                const float *gp[kRrBatch];
+#pragma unroll
+                for (int b = 0; b < kRrBatch; ++b) {
+                    s[b][0] = s[b][1] = s[b][2] = 0.0;
+                    const int jj = j0 + b < ns ? j0 + b : j0;
+                    gp[b] = p.gal + static_cast<int64_t>(s_g[jj]) * D;
+                }
+#pragma unroll
+                for (int i = 0; i < EPT / 4; ++i) {
+                    const int k = 4 * (tid + kRrThreads * i);
+                    if (k < D) {
+#pragma unroll
+                        for (int b = 0; b < kRrBatch; ++b) {
+                            const float4 bv = *reinterpret_cast<const float4 *>(gp[b] + k);
+                            const double bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const double e0 = a0[4 * i + e] - bb[e];
+                                const double e1 = a1[4 * i + e] - bb[e];
+                                const double e2 = a2[4 * i + e] - bb[e];
+                                s[b][0] += e0 * e0; s[b][1] += e1 * e1; s[b][2] += e2 * e2;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < kRrBatch; ++b)
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const double v = warp_sum(s[b][q]);
+                        if (lane == 0) s_part[warp][b * 3 + q] = v;
+                    }
+                __syncthreads();
+                if (tid == 0) {
+#pragma unroll
+                    for (int b = 0; b < kRrBatch; ++b) {
+                        if (j0 + b >= ns) break;
+                        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll
+                        for (int w = 0; w < kRrThreads / 32; ++w) {
+                            t0 += s_part[w][b * 3]; t1 += s_part[w][b * 3 + 1]; t2 += s_part[w][b * 3 + 2];
+                        }
+                        const float d0 = hl ? static_cast<float>(sqrt(t0)) : 0.f;
+                        const float d1 = static_cast<float>(sqrt(t1));
+                        const float d2 = hr ? static_cast<float>(sqrt(t2)) : 0.f;
+                        float acc = __fmul_rn(p.lam1, d0);
+                        acc = __fmaf_rn(p.lam2, d1, acc);
+                        acc = __fmaf_rn(p.lam1, d2, acc);
+                        const unsigned long long v = pack_score_idx(acc, static_cast<uint32_t>(p.offset + s_g[j0 + b]));
+                        loc = v < loc ? v : loc;
+                        ++done;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (tid == 0 && loc != ~0ull) atomicMin(p.best + row, loc);
+    }
+    if (tid == 0) {
+        if (appended) atomicAdd(&p.ctr->cand_count, appended);
+        if (done) atomicAdd(&p.ctr->n_exact, done);
+    }
+    unsafe_n = static_cast<unsigned long long>(warp_sum(static_cast<double>(unsafe_n)));
+    if (lane == 0 && unsafe_n) atomicAdd(&p.ctr->n_unsafe, unsafe_n);
+}
+
 // Rows whose candidates overflowed the list (or all rows, for eosvr_match_exact) are resolved by
 // exhaustive exact evaluation.  Early exit when nothing overflowed.
 __global__ void k_compact_flags(const RerankParams p)
@@ -666,7 +835,7 @@ __global__ void k_compact_flags(const RerankParams p)
     }
 }
 
-constexpr int kStrip = 64;   // gallery rows per warp work item in the exhaustive kernel
+constexpr int kStrip = 8;    // gallery rows per warp work item in the exhaustive kernel
 
 __global__ void k_exact_fallback(const RerankParams p)
 {
@@ -750,6 +919,7 @@ static int launch_screen(const eosvr_gallery *g, eosvr_workspace *ws, const Matc
     sp.g_stride = g_stride; sp.seed_mode = seed_mode;
     sp.na = ws->na; sp.wl = ws->wl; sp.wr = ws->wr; sp.margin = ws->margin; sp.rowmap = ws->rowmap;
     sp.gthr = ws->gthr; sp.cand = ws->cand; sp.rowcnt = ws->rowcnt; sp.cand_cap = static_cast<int32_t>(ws->cand_cap);
+    sp.ovf = ws->ovf; sp.ovf_cap = static_cast<int32_t>(ws->ovf_cap);
     sp.ctr = ws->counters; sp.rowflag = ws->rowflag;
     sp.idesc = umma_idesc_f16(g->screen_fmt == EOSVR_SCREEN_F16 ? 0 : 1, kPairM, pl.BN);
     sp.dbg = (!seed_mode && ws->dbg && ws->dbg_elems >= P * g->G) ? ws->dbg : nullptr;
@@ -794,6 +964,7 @@ int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probe
     rp.cand = ws->cand; rp.rowcnt = ws->rowcnt; rp.cand_cap = static_cast<int32_t>(ws->cand_cap);
     rp.ctr = ws->counters; rp.gthr = ws->gthr;
     rp.best = ws->best; rp.rowflag = ws->rowflag; rp.flaglist = ws->flaglist;
+    rp.ovf = ws->ovf; rp.ovf_cap = static_cast<int32_t>(ws->ovf_cap);
 
     ws->last_tiles = 0;
     ws->last_bn = pl.BN;
@@ -828,9 +999,15 @@ int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probe
         if (rc) return rc;
         ws->last_tiles = pl.NT * GT;
 
-        k_rerank<<<g_num_sms * 8, 256, 0, st>>>(rp);
+        const unsigned rr_grid = static_cast<unsigned>(P < static_cast<int64_t>(g_num_sms) * 16 ? P : g_num_sms * 16);
+        if ((g->D & 3) == 0 && g->D <= 512) k_rerank_rows<4><<<rr_grid, kRrThreads, 0, st>>>(rp);
+        else if ((g->D & 3) == 0 && g->D <= 1024) k_rerank_rows<8><<<rr_grid, kRrThreads, 0, st>>>(rp);
+        else if ((g->D & 3) == 0 && g->D <= 2048) k_rerank_rows<16><<<rr_grid, kRrThreads, 0, st>>>(rp);
+        else k_rerank<<<g_num_sms * 8, 256, 0, st>>>(rp);
         EOSVR_CUDA(cudaGetLastError());
-        EOSVR_COUNT_LAUNCH(1);
+        k_rerank_ovf<<<g_num_sms * 4, 256, 0, st>>>(rp);
+        EOSVR_CUDA(cudaGetLastError());
+        EOSVR_COUNT_LAUNCH(2);
     }
     k_compact_flags<<<64, 256, 0, st>>>(rp);
     EOSVR_CUDA(cudaGetLastError());

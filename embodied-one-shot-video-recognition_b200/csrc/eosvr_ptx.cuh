@@ -155,9 +155,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank)
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
     return r;
 }
+// Arrive on a barrier in another CTA of the cluster.  Default (.release.cta) semantics: the data these
+// arrivals order (TMEM reads) is fenced with tcgen05.fence, and a cluster-scope release would cost a
+// GPU-wide memory barrier per arrival.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
 {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair; completion bytes are signalled on the LEADER's mbarrier.
 __device__ __forceinline__ void tma_load_2d_2sm(void *smem_dst, const CUtensorMap *m, uint32_t leader_bar,

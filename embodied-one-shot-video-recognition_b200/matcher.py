@@ -117,7 +117,7 @@ class MatchWorkspace:
     def stats(self, stream=None) -> dict:
         out = (ctypes.c_int64 * 8)()
         check(lib().eosvr_match_stats(self._h, _stream_ptr(stream), out), "eosvr_match_stats")
-        keys = ["candidates", "exact_evals", "fallback_rows", "cand_capacity", "tiles", "mma_n", "unsafe", "overflow"]
+        keys = ["candidates", "exact_evals", "fallback_rows", "cand_capacity", "tiles", "mma_n", "unsafe", "spilled"]
         return dict(zip(keys, [int(v) for v in out]))
 
     def close(self):

@@ -107,7 +107,8 @@ int eosvr_match_exact(const eosvr_gallery_t *g, eosvr_workspace_t *ws, const flo
 /* Counters of the last eosvr_match on this workspace (synchronises `stream`):
  * out[0] candidates appended, out[1] candidates evaluated exactly, out[2] rows sent to the
  * exact fallback, out[3] candidate capacity, out[4] screening tiles, out[5] N of the MMA,
- * out[6] unsafe (cancellation-guard) candidates, out[7] reserved. */
+ * out[6] unsafe (cancellation-guard) candidates, out[7] candidates spilled from full row lists to
+ * the shared buffer. */
 int eosvr_match_stats(eosvr_workspace_t *ws, void *stream, int64_t out[8]);
 
 /* ---- multi-GPU shard merge (new) --------------------------------

@@ -124,9 +124,11 @@ def test_match_ties_and_cancellation():
     assert oid[3] == 7 and r["stats"]["unsafe"] > 0
 
 
-def test_overflow_goes_to_exact_fallback():
-    """More exact ties than a probe row's candidate list can hold: the row is resolved by the exhaustive exact
-    kernel and still returns the lowest index."""
+def test_candidate_overflow_paths():
+    """More exact ties than a probe row's candidate list can hold.  (1) 400 duplicates of one winner: the
+    extra candidates spill to the shared buffer and are re-ranked from there; (2) a gallery of 70 000
+    identical rows overflows the shared buffer too: the rows go to the exhaustive exact kernel.  Both must
+    still return the lowest index and the exact score."""
     ep = synth.episode_batch(15, 1, 5, 1, 4, 64)
     gal = synth.gallery(65, 900, 64, centroid_seed=15)
     A = ep["probe"].reshape(-1, 64)
@@ -138,8 +140,19 @@ def test_overflow_goes_to_exact_fallback():
     ws = ev.MatchWorkspace(20, 64, cand_capacity=20 * 32)
     idx, score = ev.match_segments(cache, ws, _cuda(A), 20)
     st = ws.stats()
-    assert st["fallback_rows"] >= 1 and st["overflow"] >= 1, st
+    assert st["spilled"] >= 300 and st["fallback_rows"] == 0, st
     assert np.array_equal(idx.cpu().numpy(), oid) and np.array_equal(score.cpu().numpy(), oval)
+
+    A2 = synth.segment_features(16, 20, 16)
+    gal2 = np.tile(synth.segment_features(17, 1, 16), (70000, 1))
+    gal2[69999] = synth.segment_features(18, 1, 16)[0]
+    oid2, oval2 = O.c_match(A2, gal2, 20)
+    cache2 = ev.GalleryFeatureCache(_cuda(gal2))
+    ws2 = ev.MatchWorkspace(20, 16, cand_capacity=20 * 32)
+    idx2, score2 = ev.match_segments(cache2, ws2, _cuda(A2), 20)
+    st2 = ws2.stats()
+    assert st2["fallback_rows"] >= 1, st2
+    assert np.array_equal(idx2.cpu().numpy(), oid2) and np.array_equal(score2.cpu().numpy(), oval2)
 
 
 def test_screening_error_within_margin():
