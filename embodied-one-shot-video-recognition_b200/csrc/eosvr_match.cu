@@ -19,6 +19,7 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "eosvr_internal.h"
 #include "eosvr_ptx.cuh"
@@ -252,6 +253,7 @@ struct ScreenParams {
     int32_t TPU;            // gallery tiles per work unit
     int64_t n_chunks;       // gallery chunks (of TPU tiles)
     int64_t n_units;        // n_chunks * NT, chunk-major: concurrent CTAs share a gallery chunk
+    int32_t order;          // unit order: 0 chunk-major, 1 probe-tile-major, 2 diagonal (rotated chunks)
     int64_t g_stride;       // gallery row stride (1; > 1 in the seed pass)
     int32_t seed_mode;      // 1: only tighten the thresholds, append nothing
     const float *na, *wl, *wr, *margin;
@@ -295,9 +297,16 @@ struct UnitIter {
 // row is rarely screened by two CTAs at once and its running threshold stays tight.
 __device__ __forceinline__ bool decode_unit(const ScreenParams &p, int64_t u, UnitIter &it)
 {
-    const int64_t chunk = u / p.NT;
+    int64_t chunk;
     it.u = u;
-    it.jt = u % p.NT;
+    if (p.order == 1) {
+        it.jt = u / p.n_chunks;
+        chunk = u % p.n_chunks;
+    } else {
+        chunk = u / p.NT;
+        it.jt = u % p.NT;
+        if (p.order == 2) chunk = (chunk + it.jt) % p.n_chunks;   // every (tile, chunk) still visited once
+    }
     it.gt0 = chunk * p.TPU;
     it.gt1 = min(it.gt0 + p.TPU, p.GT);
     return it.gt0 < it.gt1;
@@ -492,13 +501,30 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             any |= (t[j] <= tt[jj]);
                         }
                     }
-                    const bool need = any || (minx < xfloor) || (fminf(dprev_in, dn) < dfloor);
-                    if (__any_sync(0xffffffffu, need)) {
-                        // ---- rare path (whole warp): tighten the threshold with the warp minimum first,
-                        //      then append what is still below it, one atomicAdd per warp and column ----
+                    const bool guard = (minx < xfloor) || (fminf(dprev_in, dn) < dfloor);
+                    if (__any_sync(0xffffffffu, any || guard)) {
+                        // ---- rare path (whole warp).  Only the columns in which some lane is below its
+                        //      threshold (or, if the cancellation guard fired, all columns) are visited:
+                        //      tighten the threshold with the warp minimum first, then append what is still
+                        //      below it with one atomicAdd per warp and column ----
+                        unsigned cm = 0;
+                        {
+                            const float4 *th4b = reinterpret_cast<const float4 *>(tl->thr + c0);
+#pragma unroll
+                            for (int j4 = 0; j4 < kChunk / 4; ++j4) {
+                                const float4 th = th4b[j4];
+                                cm |= (t[j4 * 4 + 0] <= th.x ? 1u : 0u) << (j4 * 4 + 0);
+                                cm |= (t[j4 * 4 + 1] <= th.y ? 1u : 0u) << (j4 * 4 + 1);
+                                cm |= (t[j4 * 4 + 2] <= th.z ? 1u : 0u) << (j4 * 4 + 2);
+                                cm |= (t[j4 * 4 + 3] <= th.w ? 1u : 0u) << (j4 * 4 + 3);
+                            }
+                        }
+                        if (guard) cm = 0xFFFFu;
+                        cm = __reduce_or_sync(0xffffffffu, cm);
                         const bool rowok = g < p.G;
 #pragma unroll
                         for (int j = 0; j < kChunk; ++j) {
+                            if (!(cm & (1u << j))) continue;               // warp-uniform
                             const int c = c0 + j;
                             const int32_t rm = tl->row[c];
                             if (rm < 0) continue;                          // warp-uniform
@@ -624,6 +650,8 @@ struct RerankParams {
     int32_t *flaglist;
     const OvfCand *ovf;
     int32_t ovf_cap;
+    const float *margin;     // per plan column
+    int32_t planR, planBN, planHalo;
 };
 
 // Spill-over candidates (row lists that filled up): one warp per entry.  Exits at once when empty.
@@ -699,9 +727,11 @@ __global__ void __launch_bounds__(kRrThreads)
 k_rerank_rows(const RerankParams p)
 {
     static_assert(EPT % 4 == 0, "EPT must be a multiple of 4 (float4 loads)");
-    __shared__ int32_t s_g[kRrThreads];
+    __shared__ int32_t s_g[kRrThreads], s_g2[kRrThreads];
+    __shared__ float s_t[kRrThreads], s_t2[kRrThreads];
     __shared__ int s_warpcnt[kRrThreads / 32];
     __shared__ double s_part[kRrThreads / 32][kRrBatch * 3];
+    __shared__ float s_bound;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = p.D;
     unsigned long long appended = 0, done = 0, unsafe_n = 0;
@@ -731,16 +761,23 @@ k_rerank_rows(const RerankParams p)
             a2[4 * i] = v2.x; a2[4 * i + 1] = v2.y; a2[4 * i + 2] = v2.z; a2[4 * i + 3] = v2.w;
         }
         const float thr = __uint_as_float(p.gthr[row]);
+        // one-sided error bound of this row's screening values (half of the two-sided threshold margin)
+        const float eps1 = 0.5f * p.margin[(row / p.planR) * p.planBN + p.planHalo + (row % p.planR)];
+        const float inv_lam2 = 1.0f / p.lam2;
         const Cand *list = p.cand + row * p.cand_cap;
         unsigned long long loc = ~0ull;
+        if (tid == 0) s_bound = thr;            // screening-domain bound; tightened by every exact value found
+        __syncthreads();
 
         for (int b0 = 0; b0 < n; b0 += kRrThreads) {
-            // ---- keep what is still below the row's final threshold; compact into s_g ----
+            // ---- keep what can still win; compact; sort ascending by screening value ----
             Cand c;
             c.g = 0; c.tbits = 0x7f800000u;
             const bool in = b0 + tid < n;
             if (in) c = list[b0 + tid];
-            const bool keep = in && (c.tbits == kCandUnsafe || __uint_as_float(c.tbits) <= thr);
+            const bool isuns = in && c.tbits == kCandUnsafe;
+            const float tv = isuns ? -INFINITY : __uint_as_float(c.tbits);
+            const bool keep = in && (isuns || tv <= s_bound);
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             if (lane == 0) s_warpcnt[warp] = __popc(m);
             __syncthreads();
@@ -748,19 +785,33 @@ k_rerank_rows(const RerankParams p)
 #pragma unroll
             for (int w = 0; w < kRrThreads / 32; ++w) { if (w < warp) base += s_warpcnt[w]; ns += s_warpcnt[w]; }
             if (keep) {
-                s_g[base + __popc(m & ((1u << lane) - 1u))] = c.g;
-                if (c.tbits == kCandUnsafe) ++unsafe_n;
+                const int pos = base + __popc(m & ((1u << lane) - 1u));
+                s_g[pos] = c.g; s_t[pos] = tv;
+                if (isuns) ++unsafe_n;
             }
             __syncthreads();
-            // ---- exact evaluation, kRrBatch candidates per pass ----
+            if (tid < ns) {
+                const float mine = s_t[tid];
+                int rank = 0;
+                for (int j = 0; j < ns; ++j) {
+                    const float o = s_t[j];
+                    rank += (o < mine) || (o == mine && j < tid);
+                }
+                s_g2[rank] = s_g[tid]; s_t2[rank] = mine;
+            }
+            __syncthreads();
+            // ---- exact evaluation in ascending order; stop once the next screening value cannot win:
+            //      every candidate that could tie or beat the best exact value t* so far has
+            //      t~ <= t*/lam2 + eps1 ----
             for (int j0 = 0; j0 < ns; j0 += kRrBatch) {
+                if (s_t2[j0] > s_bound) break;                          // block-uniform (smem, after a sync)
                 double s[kRrBatch][3];
                 const float *gp[kRrBatch];
 #pragma unroll
                 for (int b = 0; b < kRrBatch; ++b) {
                     s[b][0] = s[b][1] = s[b][2] = 0.0;
                     const int jj = j0 + b < ns ? j0 + b : j0;
-                    gp[b] = p.gal + static_cast<int64_t>(s_g[jj]) * D;
+                    gp[b] = p.gal + static_cast<int64_t>(s_g2[jj]) * D;
                 }
 #pragma unroll
                 for (int i = 0; i < EPT / 4; ++i) {
@@ -789,6 +840,7 @@ k_rerank_rows(const RerankParams p)
                     }
                 __syncthreads();
                 if (tid == 0) {
+                    float bound = s_bound;
 #pragma unroll
                     for (int b = 0; b < kRrBatch; ++b) {
                         if (j0 + b >= ns) break;
@@ -803,15 +855,18 @@ k_rerank_rows(const RerankParams p)
                         float acc = __fmul_rn(p.lam1, d0);
                         acc = __fmaf_rn(p.lam2, d1, acc);
                         acc = __fmaf_rn(p.lam1, d2, acc);
-                        const unsigned long long v = pack_score_idx(acc, static_cast<uint32_t>(p.offset + s_g[j0 + b]));
+                        const unsigned long long v = pack_score_idx(acc, static_cast<uint32_t>(p.offset + s_g2[j0 + b]));
                         loc = v < loc ? v : loc;
+                        bound = fminf(bound, fmaf(acc * inv_lam2, 1.00002f, eps1));
                         ++done;
                     }
+                    s_bound = bound;
                 }
                 __syncthreads();
             }
         }
         if (tid == 0 && loc != ~0ull) atomicMin(p.best + row, loc);
+        __syncthreads();
     }
     if (tid == 0) {
         if (appended) atomicAdd(&p.ctr->cand_count, appended);
@@ -917,6 +972,17 @@ static int launch_screen(const eosvr_gallery *g, eosvr_workspace *ws, const Matc
     sp.n_chunks = (sp.GT + tpu - 1) / tpu;
     sp.n_units = sp.n_chunks * sp.NT;
     sp.g_stride = g_stride; sp.seed_mode = seed_mode;
+    {
+        static int order_env = -1, tpu_env = -1;
+        if (order_env < 0) { const char *e = getenv("EOSVR_ORDER"); order_env = e ? atoi(e) : 0; }
+        if (tpu_env < 0) { const char *e = getenv("EOSVR_TPU"); tpu_env = e ? atoi(e) : 0; }
+        sp.order = order_env;
+        if (tpu_env > 0 && !seed_mode) {
+            sp.TPU = static_cast<int32_t>(tpu_env < sp.GT ? tpu_env : sp.GT);
+            sp.n_chunks = (sp.GT + sp.TPU - 1) / sp.TPU;
+            sp.n_units = sp.n_chunks * sp.NT;
+        }
+    }
     sp.na = ws->na; sp.wl = ws->wl; sp.wr = ws->wr; sp.margin = ws->margin; sp.rowmap = ws->rowmap;
     sp.gthr = ws->gthr; sp.cand = ws->cand; sp.rowcnt = ws->rowcnt; sp.cand_cap = static_cast<int32_t>(ws->cand_cap);
     sp.ovf = ws->ovf; sp.ovf_cap = static_cast<int32_t>(ws->ovf_cap);
@@ -965,6 +1031,7 @@ int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probe
     rp.ctr = ws->counters; rp.gthr = ws->gthr;
     rp.best = ws->best; rp.rowflag = ws->rowflag; rp.flaglist = ws->flaglist;
     rp.ovf = ws->ovf; rp.ovf_cap = static_cast<int32_t>(ws->ovf_cap);
+    rp.margin = ws->margin; rp.planR = pl.R; rp.planBN = pl.BN; rp.planHalo = pl.halo;
 
     ws->last_tiles = 0;
     ws->last_bn = pl.BN;

@@ -132,12 +132,15 @@ def case_episode():
     return ok and e1 < 1e-6 and e2
 
 
-def case_perf():
+def case_perf(clustered=False):
     """Quick timing of the screening path on the bench workload (cfg-2, E=256)."""
     E, n_way, S, D, G, seed = 256, 14, 8, 2048, 11200, 31
-    rng = np.random.default_rng(seed)
-    A = synth.segment_features(seed, E * n_way * S, D)
-    gal = synth.segment_features(seed + 1, G, D)
+    if clustered:
+        A = synth.episode_batch(seed, E, n_way, 1, S, D)["probe"].reshape(-1, D)
+        gal = synth.gallery(seed + 50, G, D, centroid_seed=seed)
+    else:
+        A = synth.segment_features(seed, E * n_way * S, D)
+        gal = synth.segment_features(seed + 1, G, D)
     dA, dG = torch.from_numpy(A).cuda(), torch.from_numpy(gal).cuda()
     cache = ev.GalleryFeatureCache(dG)
     ws = ev.MatchWorkspace(A.shape[0], D)
@@ -152,10 +155,21 @@ def case_perf():
     e.record(); torch.cuda.synchronize()
     ms = s.elapsed_time(e) / 5
     fl = 2.0 * A.shape[0] * G * D
-    print(f"  match P={A.shape[0]} G={G} D={D}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  stats={ws.stats()}")
+    ws.set_timing(True)
+    for _ in range(5):
+        ev.match_segments(cache, ws, dA, rpe)
+    torch.cuda.synchronize()
+    kms, kn = ws.screen_ms()
+    print(f"  match P={A.shape[0]} G={G} D={D}: {ms:.3f} ms/call ({fl / ms / 1e9:.1f} TFLOP/s); screening kernel "
+          f"{kms / kn:.3f} ms ({fl / (kms / kn) / 1e9:.1f} TFLOP/s)  order={os.environ.get('EOSVR_ORDER', '0')} "
+          f"tpu={os.environ.get('EOSVR_TPU', 'auto')}  stats={ws.stats()}")
     oid, _ = O.c_match(A[:rpe], gal, rpe)
     print("  first episode idx equal:", np.array_equal(idx[:rpe].cpu().numpy(), oid))
     return True
+
+
+def case_perf_clustered():
+    return case_perf(True)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,55 @@
+"""Multi-GPU parity check (launch with torchrun): the gallery sharded by segment over all ranks must give
+bit-identical winners / scores / predictions to the un-sharded single-GPU answer, including planted ties
+that straddle shard boundaries.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tools/multi_gpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import eosvr_b200 as ev  # noqa: E402
+import synth  # noqa: E402
+from eosvr_b200.dist import shard_range  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    E, n_way, S, D, G = 32, 14, 8, 2048, 11200
+    ep = synth.episode_batch(7, E, n_way, 1, S, D)
+    gal = synth.gallery(57, G, D, centroid_seed=7)
+    # exact duplicates placed in different shards: the lowest GLOBAL index must win everywhere
+    gal[G - 5] = gal[40]
+    gal[G // 2 + 3] = gal[41]
+    probes, y, q = (torch.from_numpy(ep[k]).to(dev) for k in ("probe", "support_y", "query"))
+    full = ev.GalleryFeatureCache(torch.from_numpy(gal).to(dev))
+    ref = ev.EpisodePipeline(full, n_way, 1, S, E).run(probes, y, q)
+    b, e = shard_range(G, rank, world)
+    shard = ev.GalleryFeatureCache(torch.from_numpy(gal[b:e]).to(dev), global_offset=b)
+    pipe = ev.EpisodePipeline(shard, n_way, 1, S, E, group=dist.group.WORLD)
+    out = pipe.run(probes, y, q)
+    torch.cuda.synchronize()
+    ok = all(torch.equal(ref[k], out[k]) for k in ("idx", "score", "pred", "dist"))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"multi_gpu_check world={world} shards={[shard_range(G, r, world) for r in range(world)]} "
+              f"identical_to_single_gpu={bool(flag.item())} acc={float((out['pred'].cpu().numpy() == ep['query_y']).mean()):.3f}",
+              flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()
