@@ -8,9 +8,9 @@ from eosvr_b200._lib import (EosvrError, lib, lib_path, load_library, ORIG_CLIP_
                              ORIG_REF_QUIRK, SCREEN_BF16, SCREEN_F16)
 from eosvr_b200.matcher import (EpisodePipeline, GalleryFeatureCache, MatchWorkspace,  # noqa: F401
                                 episode_score, gather_winner_rows, match_segments, match_segments_exact, merge_top1, proto_score,
-                                segment_features, splice_augmented)
+                                segment_features, splice_augmented, temporal_smooth, cosine_predict)
 
 __all__ = ["EosvrError", "lib", "lib_path", "load_library", "GalleryFeatureCache", "MatchWorkspace",
            "EpisodePipeline", "episode_score", "gather_winner_rows", "match_segments", "match_segments_exact", "merge_top1", "proto_score",
-           "segment_features", "splice_augmented", "ORIG_REF_QUIRK", "ORIG_CLIP_MEAN", "SCREEN_F16",
+           "segment_features", "splice_augmented", "temporal_smooth", "cosine_predict", "ORIG_REF_QUIRK", "ORIG_CLIP_MEAN", "SCREEN_F16",
            "SCREEN_BF16"]

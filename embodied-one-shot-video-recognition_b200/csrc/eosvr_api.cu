@@ -351,6 +351,24 @@ int eosvr_episode_score(const float *d_probes, const float *d_winner_rows, const
                                 max_proto, d_dist, d_prob, d_pred, d_nproto, static_cast<cudaStream_t>(stream));
 }
 
+int eosvr_temporal_smooth(const double *d_dist64, int64_t P, int64_t G, int32_t rows_per_episode, float lam1,
+                          float lam2, float *d_out, void *stream)
+{
+    if (P < 0 || G < 0 || rows_per_episode < 1 || (P * G > 0 && (!d_dist64 || !d_out))) { set_error("temporal_smooth: bad arguments"); return EOSVR_EINVAL; }
+    int rc = eosvr_device_check();
+    if (rc) return rc;
+    return launch_temporal_smooth(d_dist64, P, G, rows_per_episode, lam1, lam2, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int eosvr_cosine_predict(const float *d_support, const float *d_query, int64_t E, int32_t R, int32_t Q, int32_t D,
+                         float *d_sim, int64_t *d_best, void *stream)
+{
+    if (E < 0 || R < 1 || Q < 1 || D < 1 || (E > 0 && (!d_support || !d_query || !d_best))) { set_error("cosine_predict: bad arguments"); return EOSVR_EINVAL; }
+    int rc = eosvr_device_check();
+    if (rc) return rc;
+    return launch_cosine_predict(d_support, d_query, E, R, Q, D, d_sim, d_best, static_cast<cudaStream_t>(stream));
+}
+
 int eosvr_segment_features(const float *d_frames, int64_t N, int32_t seg_len, int32_t D, int32_t l2, float *d_out,
                            void *stream)
 {

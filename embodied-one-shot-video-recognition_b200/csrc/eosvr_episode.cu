@@ -348,6 +348,94 @@ int launch_episode_score(const float *probes, const float *wrows, const float *g
     return EOSVR_OK;
 }
 
+// -------------------------------------------------------------------------------------------
+// Materialised temporal smoothing: TestNetwork.temporal_convolution_flating_layer
+// (network_test.py:103-117, TemporalLayer models.py:42-56) on an explicit [P,G] float64 distance matrix
+// (the reference-shaped call; the matcher never materialises this matrix).  Same float32 FMA chain as the
+// exact re-rank: float32 cast, acc = lam1*d[p-1]; acc = fma(lam2, d[p], acc); acc = fma(lam1, d[p+1], acc),
+// zero padding at the ends of each block of rows_per_episode rows.
+// -------------------------------------------------------------------------------------------
+__global__ void k_temporal_smooth(const double *__restrict__ d64, int64_t P, int64_t G, int rpe, float lam1,
+                                  float lam2, float *__restrict__ out)
+{
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= P * G) return;
+    const int64_t p = i / G;
+    const int r = static_cast<int>(p % rpe);
+    const bool hl = r > 0, hr = (r + 1 < rpe) && (p + 1 < P);
+    const float dl = hl ? static_cast<float>(d64[i - G]) : 0.f;
+    const float dc = static_cast<float>(d64[i]);
+    const float dr = hr ? static_cast<float>(d64[i + G]) : 0.f;
+    float acc = __fmul_rn(lam1, dl);
+    acc = __fmaf_rn(lam2, dc, acc);
+    acc = __fmaf_rn(lam1, dr, acc);
+    out[i] = acc;
+}
+
+int launch_temporal_smooth(const double *d64, int64_t P, int64_t G, int32_t rpe, float lam1, float lam2,
+                           float *out, cudaStream_t st)
+{
+    if (P * G == 0) return EOSVR_OK;
+    const int threads = 256;
+    k_temporal_smooth<<<static_cast<unsigned>((P * G + threads - 1) / threads), threads, 0, st>>>(d64, P, G, rpe,
+                                                                                               lam1, lam2, out);
+    EOSVR_CUDA(cudaGetLastError());
+    EOSVR_COUNT_LAUNCH(1);
+    return EOSVR_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// Cosine scoring: Classifier('cosine').predict, classifier.py:117-120 -- cosine similarity of every query
+// to every SUPPORT ROW and the index of the best row (not its label); lowest index on
+// ties.  One block per (episode, query); float64 accumulation, float32 result.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_cosine_predict(const float *__restrict__ sup, const float *__restrict__ query, int R, int Q, int D,
+                 float *__restrict__ sim, int64_t *__restrict__ best)
+{
+    __shared__ float s_best[8];
+    __shared__ int s_idx[8];
+    const int64_t eq = blockIdx.x;                 // e*Q + q
+    const int64_t e = eq / Q;
+    const float *qv = query + eq * D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double qq = 0.0;
+    for (int k = lane; k < D; k += 32) qq += static_cast<double>(qv[k]) * static_cast<double>(qv[k]);
+    for (int o = 16; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    float bestv = -INFINITY; int besti = 0x7fffffff;
+    for (int r = warp; r < R; r += 8) {
+        const float *sv = sup + (e * R + r) * D;
+        double dot = 0.0, ss = 0.0;
+        for (int k = lane; k < D; k += 32) {
+            const double a = sv[k], b = qv[k];
+            dot += a * b; ss += a * a;
+        }
+        for (int o = 16; o > 0; o >>= 1) { dot += __shfl_xor_sync(0xffffffffu, dot, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+        const double den = sqrt(qq) * sqrt(ss);
+        const float c = den > 0.0 ? static_cast<float>(dot / den) : 0.f;
+        if (sim && lane == 0) sim[eq * R + r] = c;
+        if (c > bestv) { bestv = c; besti = r; }   // rows ascend within a warp: first maximum kept
+    }
+    if (lane == 0) { s_best[warp] = bestv; s_idx[warp] = besti; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float bv = s_best[0]; int bi = s_idx[0];
+        for (int w = 1; w < 8; ++w)
+            if (s_best[w] > bv || (s_best[w] == bv && s_idx[w] < bi)) { bv = s_best[w]; bi = s_idx[w]; }
+        best[eq] = bi;
+    }
+}
+
+int launch_cosine_predict(const float *sup, const float *query, int64_t E, int32_t R, int32_t Q, int32_t D,
+                          float *sim, int64_t *best, cudaStream_t st)
+{
+    if (E * Q == 0) return EOSVR_OK;
+    k_cosine_predict<<<static_cast<unsigned>(E * Q), 256, 0, st>>>(sup, query, R, Q, D, sim, best);
+    EOSVR_CUDA(cudaGetLastError());
+    EOSVR_COUNT_LAUNCH(1);
+    return EOSVR_OK;
+}
+
 // One warp per output segment row.
 __global__ void k_segment_features(const float *__restrict__ frames, int64_t N, int seg_len, int D, int l2,
                                    float *__restrict__ out)

@@ -140,6 +140,10 @@ int launch_episode_score(const float *probes, const float *wrows, const float *g
 int launch_proto_score(const float *sup, const float *sup_y, const float *query, int64_t E, int32_t R,
                        int32_t Q, int32_t D, int32_t max_proto, float *dist, float *prob, int64_t *pred,
                        int32_t *nproto, cudaStream_t st);
+int launch_temporal_smooth(const double *d64, int64_t P, int64_t G, int32_t rpe, float lam1, float lam2,
+                           float *out, cudaStream_t st);
+int launch_cosine_predict(const float *sup, const float *query, int64_t E, int32_t R, int32_t Q, int32_t D,
+                          float *sim, int64_t *best, cudaStream_t st);
 int launch_segment_features(const float *frames, int64_t N, int32_t seg_len, int32_t D, int32_t l2,
                             float *out, cudaStream_t st);
 int encode_tmap_2d(CUtensorMap *m, const void *base, int fmt, uint64_t rows, uint64_t cols,

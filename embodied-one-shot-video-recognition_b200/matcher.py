@@ -263,6 +263,33 @@ def episode_score(probes: torch.Tensor, support_y: torch.Tensor, query: torch.Te
     return dict(pred=pred, dist=dist, prob=prob, nproto=nproto)
 
 
+def temporal_smooth(dist64: torch.Tensor, rows_per_episode: int | None = None, lam1: float = LAMDA1,
+                    lam2: float = LAMDA2, stream=None) -> torch.Tensor:
+    """network_test.py:103-117 on an explicit float64 [P,G] CUDA distance matrix -> float32 [P,G]."""
+    if not dist64.is_cuda or dist64.dtype != torch.float64 or dist64.dim() != 2:
+        raise ValueError("dist64 must be a CUDA float64 [P,G] tensor")
+    dist64 = dist64.contiguous()
+    P, G = int(dist64.shape[0]), int(dist64.shape[1])
+    out = torch.empty(P, G, dtype=torch.float32, device=dist64.device)
+    with torch.cuda.device(dist64.device):
+        check(lib().eosvr_temporal_smooth(_ptr(dist64), P, G, int(rows_per_episode or max(P, 1)), float(lam1),
+                                          float(lam2), _ptr(out), _stream_ptr(stream)), "eosvr_temporal_smooth")
+    return out
+
+
+def cosine_predict(support: torch.Tensor, query: torch.Tensor, want_sim: bool = False, stream=None):
+    """classifier.py:117-120 for E episodes: support [E,R,D], query [E,Q,D] -> best support-row index [E,Q]."""
+    support, query = _dev_f32(support, "support"), _dev_f32(query, "query")
+    E, R, D = (int(x) for x in support.shape)
+    Q = int(query.shape[1])
+    best = torch.empty(E, Q, dtype=torch.int64, device=support.device)
+    sim = torch.empty(E, Q, R, dtype=torch.float32, device=support.device) if want_sim else None
+    with torch.cuda.device(support.device):
+        check(lib().eosvr_cosine_predict(_ptr(support), _ptr(query), E, R, Q, D, _ptr(sim), _ptr(best),
+                                         _stream_ptr(stream)), "eosvr_cosine_predict")
+    return (best, sim) if want_sim else best
+
+
 def segment_features(frames: torch.Tensor, seg_len: int, l2: bool = True, stream=None) -> torch.Tensor:
     """network_test.py:187-189 / :203-205 (+ per-frame L2 of :79-80): [N*seg_len, D] -> [N, D]."""
     frames = _dev_f32(frames, "frames")

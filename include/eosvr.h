@@ -159,6 +159,18 @@ int eosvr_episode_score(const float *d_probes, const float *d_winner_rows, const
                         int32_t max_proto, float *d_dist, float *d_prob, int64_t *d_pred,
                         int32_t *d_nproto, void *stream);
 
+/* ---- reference-shaped helpers ------------------------------------------------------------
+ * eosvr_temporal_smooth: TestNetwork.temporal_convolution_flating_layer (network_test.py:103-117,
+ * models.py:42-56) on an explicit float64 distance matrix d_dist64 [P,G] -> float32 [P,G]; blocks of
+ * rows_per_episode rows are zero-padded separately (the reference passes one episode: rows_per_episode = P).
+ * eosvr_cosine_predict: Classifier('cosine').predict (classifier.py:117-120): cosine similarity of each
+ * query [E,Q,D] to each support row [E,R,D]; d_best[E,Q] = index of the best SUPPORT ROW (lowest index on
+ * ties), optional d_sim [E,Q,R]. */
+int eosvr_temporal_smooth(const double *d_dist64, int64_t P, int64_t G, int32_t rows_per_episode,
+                          float lam1, float lam2, float *d_out, void *stream);
+int eosvr_cosine_predict(const float *d_support, const float *d_query, int64_t E, int32_t R, int32_t Q,
+                         int32_t D, float *d_sim, int64_t *d_best, void *stream);
+
 /* ---- gallery / probe cache builder -------------------------------------------------
  * Replaces np.resize + np.mean of network_test.py:188-189 / :204-205 (+ per-frame
  * F.normalize of :79-80 when l2 != 0): d_frames [N*seg_len, D] -> d_out [N, D]. */
