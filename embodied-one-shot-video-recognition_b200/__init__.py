@@ -10,7 +10,16 @@ from eosvr_b200.matcher import (EpisodePipeline, GalleryFeatureCache, MatchWorks
                                 episode_score, gather_winner_rows, match_segments, match_segments_exact, merge_top1, proto_score,
                                 segment_features, splice_augmented, temporal_smooth, cosine_predict)
 
-__all__ = ["EosvrError", "lib", "lib_path", "load_library", "GalleryFeatureCache", "MatchWorkspace",
+
+
+def dropin_path() -> str:
+    """Directory holding the drop-in modules with the reference's names (network_test, classifier,
+    episode_novel_dataloader, generate_gallery_videos, models, utils); put it on sys.path."""
+    import os
+    return os.path.join(os.path.dirname(lib_path()), "dropin")
+
+
+__all__ = ["dropin_path", "EosvrError", "lib", "lib_path", "load_library", "GalleryFeatureCache", "MatchWorkspace",
            "EpisodePipeline", "episode_score", "gather_winner_rows", "match_segments", "match_segments_exact", "merge_top1", "proto_score",
            "segment_features", "splice_augmented", "temporal_smooth", "cosine_predict", "ORIG_REF_QUIRK", "ORIG_CLIP_MEAN", "SCREEN_F16",
            "SCREEN_BF16"]
