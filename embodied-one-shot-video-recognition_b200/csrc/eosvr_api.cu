@@ -111,6 +111,7 @@ int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtyp
     }
     rc = launch_gallery_prep(g, static_cast<cudaStream_t>(stream));
     if (!rc) rc = encode_tmap_2d(&g->tmapA, g->h16, screen_fmt, static_cast<uint64_t>(Gpad), static_cast<uint64_t>(g->Dp), kBM, kBK, 1);
+    if (!rc) rc = encode_tmap_2d(&g->tmapAH, g->h16, screen_fmt, static_cast<uint64_t>(Gpad), static_cast<uint64_t>(g->Dp), kBM / 2, kBK, 1);
     // strided seed sample: seed_tiles tiles of rows {0, stride, 2*stride, ...}
     // (an ODD stride so that periodic class layouts of the gallery cannot alias with the sample)
     const int64_t GT = Gpad / kPairM;
@@ -122,6 +123,8 @@ int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtyp
     if (g->seed_stride > 1 && (g->seed_stride & 1) == 0) g->seed_stride -= 1;
     if (!rc) rc = encode_tmap_2d(&g->tmapSeed, g->h16, screen_fmt, static_cast<uint64_t>(st_tiles * kPairM),
                                  static_cast<uint64_t>(g->Dp), kBM, kBK, static_cast<uint64_t>(g->seed_stride));
+    if (!rc) rc = encode_tmap_2d(&g->tmapSeedH, g->h16, screen_fmt, static_cast<uint64_t>(st_tiles * kPairM),
+                                 static_cast<uint64_t>(g->Dp), kBM / 2, kBK, static_cast<uint64_t>(g->seed_stride));
     if (rc) { eosvr_gallery_destroy(g); return rc; }
     *out = g;
     return EOSVR_OK;
@@ -302,6 +305,18 @@ int eosvr_match_stats(eosvr_workspace_t *ws, void *stream, int64_t out[8])
     out[5] = ws->last_bn;
     out[6] = static_cast<int64_t>(c.n_unsafe);
     out[7] = c.ovf_count;
+    return EOSVR_OK;
+}
+
+int eosvr_workspace_debug_cycles(eosvr_workspace_t *ws, void *stream, int64_t out[6])
+{
+    if (!ws || !out) { set_error("debug_cycles: NULL argument"); return EOSVR_EINVAL; }
+    Counters c;
+    EOSVR_CUDA(cudaMemcpyAsync(&c, ws->counters, sizeof(c), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    EOSVR_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    out[0] = static_cast<int64_t>(c.cyc_epi_busy); out[1] = static_cast<int64_t>(c.cyc_epi_wait);
+    out[2] = static_cast<int64_t>(c.cyc_mma_wait_full); out[3] = static_cast<int64_t>(c.cyc_mma_wait_acc);
+    out[4] = static_cast<int64_t>(c.cyc_prod_wait); out[5] = static_cast<int64_t>(c.cyc_total);
     return EOSVR_OK;
 }
 

@@ -14,7 +14,10 @@ constexpr int kBM = 128;          // gallery rows per CTA and tile (one TMEM lan
 constexpr int kPairM = 256;       // gallery rows per CTA pair and tile (UMMA M with cta_group::2)
 constexpr int kBK = 64;           // K elements per pipeline stage (128-byte rows, SWIZZLE_128B)
 constexpr int kMaxBN = 256;       // probe columns per tile (UMMA N), multiple of 16
-constexpr int kStages = 6;        // TMA -> MMA smem ring (16 KiB A + 16 KiB B-half per stage and CTA)
+constexpr int kSub = 2;           // K blocks per pipeline stage: 4*kSub MMAs are issued per tcgen05.commit (a commit
+                                  // costs the issuing thread ~700 cycles; tools/bench_micro/mma_rate.cu)
+constexpr int kStages = 3;        // TMA -> MMA smem ring (kSub x (16 KiB A + 16 KiB B-half) per stage and CTA)
+constexpr int kIssuers = 2;       // MMA issuer warps (alternate pipeline stages)
 constexpr int kAccStages = 2;     // TMEM accumulator double buffer (2 x 256 columns)
 constexpr int kTmemCols = 512;
 constexpr int kEpiWarps = 8;      // warps 4..11
@@ -60,6 +63,8 @@ struct Counters {
     unsigned int n_flag_rows;        // rows sent to the exact fallback
     unsigned int xfloor_bits;        // max over columns of the cancellation guard (x domain)
     unsigned int ovf_count;          // entries appended to the shared spill-over buffer
+    // cycle accounting of the screening kernel (EOSVR_EXP bit 16; measurement only), summed over CTAs
+    unsigned long long cyc_epi_busy, cyc_epi_wait, cyc_mma_wait_full, cyc_mma_wait_acc, cyc_prod_wait, cyc_total;
 };
 
 }  // namespace eosvr
@@ -70,6 +75,7 @@ struct eosvr_gallery {
     int32_t seed_tiles;      // gallery tiles of the strided seed pass
     int64_t seed_stride;     // row stride of the seed pass
     CUtensorMap tmapSeed;
+    CUtensorMap tmapAH, tmapSeedH;   // same tensors with half-height (64-row) boxes: multicast halves of a slab
     int32_t D, Dp;           // Dp = D rounded up to kBK
     int64_t offset;          // global index of row 0
     int32_t screen_fmt;

@@ -20,6 +20,7 @@
 #include <cuda_bf16.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "eosvr_internal.h"
 #include "eosvr_ptx.cuh"
@@ -237,6 +238,8 @@ __global__ void k_reset(Counters *ctr, unsigned long long *best, int32_t *rowfla
     if (i == 0) {
         ctr->cand_count = 0; ctr->n_exact = 0; ctr->n_unsafe = 0;
         ctr->overflow = flag_all ? 1u : 0u; ctr->n_flag_rows = 0; ctr->xfloor_bits = 0; ctr->ovf_count = 0;
+        ctr->cyc_epi_busy = ctr->cyc_epi_wait = ctr->cyc_mma_wait_full = ctr->cyc_mma_wait_acc = 0;
+        ctr->cyc_prod_wait = ctr->cyc_total = 0;
     }
     if (i < P) { best[i] = ~0ull; rowflag[i] = flag_all; rowcnt[i] = 0; gthr[i] = 0x7f800000u; }
 }
@@ -252,7 +255,8 @@ struct ScreenParams {
     int64_t NT, GT;
     int32_t TPU;            // gallery tiles per work unit
     int64_t n_chunks;       // gallery chunks (of TPU tiles)
-    int64_t n_units;        // n_chunks * NT, chunk-major: concurrent CTAs share a gallery chunk
+    int64_t NTG;            // probe tile groups: NT / (CTA pairs per cluster)
+    int64_t n_units;        // n_chunks * NTG, chunk-major: concurrent clusters share a gallery chunk
     int32_t order;          // unit order: 0 chunk-major, 1 probe-tile-major, 2 diagonal (rotated chunks)
     int64_t g_stride;       // gallery row stride (1; > 1 in the seed pass)
     int32_t seed_mode;      // 1: only tighten the thresholds, append nothing
@@ -268,6 +272,8 @@ struct ScreenParams {
     int32_t *rowflag;
     uint32_t idesc;
     float *dbg;             // optional [P,G] dump of the screening values
+    int32_t exp_mode;       // experiments (EOSVR_EXP): 1 = epilogue releases the accumulator untouched,
+                            // 2 = producer skips the TMA loads, 4 = MMA issuer skips the MMAs
 };
 
 struct __align__(16) ScreenSmemTail {
@@ -277,19 +283,24 @@ struct __align__(16) ScreenSmemTail {
     float mg[kMaxBN];
     unsigned int thr[kMaxBN];
     int32_t row[kMaxBN];
-    uint64_t full[kStages];
+    uint64_t full[kIssuers * kStages];   // indexed by (running stage number) % (kIssuers*kStages): consecutive fills of
+                                         // a stage go to alternate MMA issuers, and a parity wait is only safe on a
+                                         // barrier whose every phase the waiter observes
     uint64_t empty[kStages];
     uint64_t tfull[kAccStages];
     uint64_t tempty[kAccStages];
+    uint64_t tfirst[kAccStages];      // the overwriting first stage of a tile has completed
     uint32_t tmem_base;
 };
 
 constexpr int kABytes = kBM * kBK * 2;              // 16 KiB: this CTA's 128 gallery rows
 constexpr int kBBytes = (kMaxBN / 2) * kBK * 2;     // 16 KiB: this CTA's half of the probe tile
-constexpr size_t kScreenSmem = 1024 + static_cast<size_t>(kStages) * (kABytes + kBBytes) + sizeof(ScreenSmemTail);
+constexpr int kAStage = kSub * kABytes;             // one pipeline stage = kSub K blocks of each operand
+constexpr int kBStage = kSub * kBBytes;
+constexpr size_t kScreenSmem = 1024 + static_cast<size_t>(kStages) * (kAStage + kBStage) + sizeof(ScreenSmemTail);
 
 struct UnitIter {
-    int64_t u, jt, gt0, gt1;
+    int64_t u, jt, gt0, gt1;    // jt: probe tile GROUP of the unit (pair q of the cluster takes tile jt*NP + q)
 };
 
 // Work units are chunk-major: unit u = chunk * NT + probe_tile.  CTAs running at the same time work on
@@ -303,8 +314,8 @@ __device__ __forceinline__ bool decode_unit(const ScreenParams &p, int64_t u, Un
         it.jt = u / p.n_chunks;
         chunk = u % p.n_chunks;
     } else {
-        chunk = u / p.NT;
-        it.jt = u % p.NT;
+        chunk = u / p.NTG;
+        it.jt = u % p.NTG;
         if (p.order == 2) chunk = (chunk + it.jt) % p.n_chunks;   // every (tile, chunk) still visited once
     }
     it.gt0 = chunk * p.TPU;
@@ -312,26 +323,43 @@ __device__ __forceinline__ bool decode_unit(const ScreenParams &p, int64_t u, Un
     return it.gt0 < it.gt1;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+// NP = CTA pairs per cluster (cluster size 2*NP).  With NP = 2 the two pairs of a cluster screen the SAME
+// gallery tile against two different probe tiles: every CTA fetches half of its 128-row gallery slab and
+// multicasts it to the CTA of equal parity in the other pair, so the gallery operand crosses L2 -> SM once
+// per cluster instead of once per pair (the kernel is bound by operand delivery).
+template <int NP>
+__global__ void __launch_bounds__(kThreads, 1)
 k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ScreenParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sA = smem;
-    uint8_t *sB = smem + kStages * kABytes;
-    ScreenSmemTail *tl = reinterpret_cast<ScreenSmemTail *>(smem + kStages * (kABytes + kBBytes));
+    uint8_t *sB = smem + kStages * kAStage;
+    ScreenSmemTail *tl = reinterpret_cast<ScreenSmemTail *>(smem + kStages * (kAStage + kBStage));
+    const int KS = (p.KB + kSub - 1) / kSub;            // pipeline stages per gallery tile
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();            // 0 = leader (issues the MMAs), 1 = peer
-    const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t rank = crank & 1u;                   // 0 = leader of its pair (issues the MMAs), 1 = peer
+    const uint32_t pq = crank >> 1;                     // pair within the cluster
+    const uint32_t leader = crank & ~1u;                // cluster rank of this pair's leader
+    const int64_t pair = blockIdx.x / (2 * NP), npairs = gridDim.x / (2 * NP);   // cluster index / count
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
-        for (int s = 0; s < kStages; ++s) { mbar_init(&tl->full[s], 1); mbar_init(&tl->empty[s], 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(&tl->tfull[s], 1); mbar_init(&tl->tempty[s], 2 * kEpiWarps); }
+        // NP > 1: every CTA collects its own bytes on its own full barrier and the peer relays its completion
+        // to the leader (second arrival); the stage is free once the MMAs of ALL pairs have read it.
+        const uint32_t full_count = (NP > 1 && rank == 0) ? 2u : 1u;
+        for (int s = 0; s < kIssuers * kStages; ++s) mbar_init(&tl->full[s], full_count);
+        for (int s = 0; s < kStages; ++s) mbar_init(&tl->empty[s], NP);
+        for (int s = 0; s < kAccStages; ++s) {
+            mbar_init(&tl->tfull[s], kIssuers);          // one commit per MMA issuer warp
+            mbar_init(&tl->tempty[s], 2 * kEpiWarps);
+            mbar_init(&tl->tfirst[s], 1);
+        }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc_2sm(&tl->tmem_base, kTmemCols);
@@ -339,61 +367,135 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     cluster_sync();
     tc_fence_after();
     const uint32_t tmem_base = tl->tmem_base;
+    const bool prof = (p.exp_mode & 16) != 0;
 
+    // Warps 0, 1 and 3 run their loops with the WHOLE warp (warp-uniform control flow and operands: no
+    // per-instruction uniformisation loops around UTMALDG / UTCHMMA / UTCBAR); lane 0 issues.
     if (warp == 0) {
-        // ===== TMA producer (both CTAs): own 128 gallery rows + own half of the probe tile; the bytes of
-        //       both CTAs complete on the LEADER's full barrier =====
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            const int32_t bhalf = p.BN >> 1;
-            const uint32_t tx_pair = 2u * (kABytes + static_cast<uint32_t>(bhalf) * kBK * 2);
-            for (int64_t u = pair; u < p.n_units; u += npairs) {
-                UnitIter it;
-                if (!decode_unit(p, u, it)) continue;
-                for (int64_t gt = it.gt0; gt < it.gt1; ++gt) {
-                    for (int kb = 0; kb < p.KB; ++kb) {
-                        mbar_wait(&tl->empty[stage], phase ^ 1);
-                        const uint32_t lbar = mapa(smem_u32(&tl->full[stage]), 0);
-                        // only the leader arrives (expecting the bytes of BOTH CTAs); the peer just issues its
-                        // loads -- it cannot run ahead of the phase because its stage is freed by the leader's
-                        // MMA commit
-                        if (rank == 0) mbar_arrive_expect_tx(&tl->full[stage], tx_pair);
-                        tma_load_2d_2sm(sA + stage * kABytes, &tmA, lbar, kb * kBK,
-                                        static_cast<int32_t>(gt * kPairM + rank * kBM));
-                        tma_load_2d_2sm(sB + stage * kBBytes, &tmB, lbar, kb * kBK,
-                                        static_cast<int32_t>(it.jt * p.BN + rank * bhalf));
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        // ===== TMA producer (every CTA): own gallery rows + own half of the pair's probe tile =====
+        int stage = 0; uint32_t phase = 0;
+        int fb = 0;                                   // full-barrier slot = running stage number % (kIssuers*kStages)
+        const int32_t bhalf = p.BN >> 1;
+        const uint32_t tx_cta = kABytes + static_cast<uint32_t>(bhalf) * kBK * 2;
+        uint16_t mc_mask = 0;
+        for (int k = 0; k < NP; ++k) mc_mask |= static_cast<uint16_t>(1u << (2 * k + rank));
+        unsigned long long w_prod = 0;
+        const long long t_begin = clock64();
+        const uint32_t lbar0 = mapa(smem_u32(&tl->full[0]), 0);
+        for (int64_t u = pair; u < p.n_units; u += npairs) {
+            UnitIter it;
+            if (!decode_unit(p, u, it)) continue;
+            const int32_t brow = static_cast<int32_t>((it.jt * NP + pq) * p.BN + rank * bhalf);
+            for (int64_t gt = it.gt0; gt < it.gt1; ++gt) {
+                const int32_t arow = static_cast<int32_t>(gt * kPairM + rank * kBM + (NP > 1 ? pq * (kBM / NP) : 0));
+                for (int ks = 0; ks < KS; ++ks) {
+                    const int nsub = min(kSub, p.KB - ks * kSub);
+                    if (prof) { const long long t0 = clock64(); mbar_wait(&tl->empty[stage], phase ^ 1); w_prod += clock64() - t0; }
+                    else mbar_wait(&tl->empty[stage], phase ^ 1);
+                    if (lane == 0) {
+                        if (p.exp_mode & 2) {
+                            if (NP > 1 || rank == 0) mbar_arrive(&tl->full[fb]);
+                        } else if (NP == 1) {
+                            // the bytes of both CTAs complete on the LEADER's full barrier: only the leader
+                            // arrives; the peer cannot run ahead of the phase because its stage is freed by
+                            // the leader's MMA commit
+                            const uint32_t lbar = lbar0 + fb * static_cast<uint32_t>(sizeof(uint64_t));
+                            if (rank == 0) mbar_arrive_expect_tx(&tl->full[fb], 2u * tx_cta * nsub);
+                            for (int sb = 0; sb < nsub; ++sb) {
+                                const int32_t kc = (ks * kSub + sb) * kBK;
+                                tma_load_2d_2sm(sA + stage * kAStage + sb * kABytes, &tmA, lbar, kc, arow);
+                                tma_load_2d_2sm(sB + stage * kBStage + sb * kBBytes, &tmB, lbar, kc, brow);
+                            }
+                        } else {
+                            mbar_arrive_expect_tx(&tl->full[fb], tx_cta * nsub);
+                            for (int sb = 0; sb < nsub; ++sb) {
+                                const int32_t kc = (ks * kSub + sb) * kBK;
+                                tma_load_2d_mc(sA + stage * kAStage + sb * kABytes + pq * (kABytes / NP), &tmA,
+                                               &tl->full[fb], kc, arow, mc_mask);
+                                tma_load_2d(sB + stage * kBStage + sb * kBBytes, &tmB, &tl->full[fb], kc, brow);
+                            }
+                        }
                     }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++fb == kIssuers * kStages) fb = 0;
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer: one thread of the leader CTA drives the tensor cores of both SMs =====
-        if (lane == 0 && rank == 0) {
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t accphase = 0;
-            for (int64_t u = pair; u < p.n_units; u += npairs) {
-                UnitIter it;
-                if (!decode_unit(p, u, it)) continue;
-                for (int64_t gt = it.gt0; gt < it.gt1; ++gt) {
-                    mbar_wait(&tl->tempty[acc], accphase ^ 1);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * kMaxBN;
-                    for (int kb = 0; kb < p.KB; ++kb) {
-                        mbar_wait(&tl->full[stage], phase);
-                        tc_fence_after();
-                        const uint32_t a0 = smem_u32(sA + stage * kABytes);
-                        const uint32_t b0 = smem_u32(sB + stage * kBBytes);
-#pragma unroll
-                        for (int k = 0; k < kBK / 16; ++k)
-                            mma_f16_ss_2sm(d_tmem, umma_desc_sw128(a0, k * 32), umma_desc_sw128(b0, k * 32),
-                                           p.idesc, (kb | k) != 0 ? 1u : 0u);
-                        mma_commit_2sm(&tl->empty[stage], 3);       // frees the stage in both CTAs
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
-                    }
-                    mma_commit_2sm(&tl->tfull[acc], 3);             // accumulators ready in both CTAs
-                    if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
+        if (prof && lane == 0) {
+            atomicAdd(&p.ctr->cyc_prod_wait, w_prod);
+            if (rank == 0) atomicAdd(&p.ctr->cyc_total, static_cast<unsigned long long>(clock64() - t_begin));
+        }
+    } else if ((warp == 1 || warp == 3) && rank == 0) {
+        // ===== MMA issuers: two warps of the pair's leader drive the tensor cores of both SMs.  A tcgen05.commit
+        //       blocks its issuing thread for ~600 cycles and a UTCHMMA for ~70 (tools/bench_micro/mma_rate.cu), so
+        //       ONE issuer cannot keep the pipe busy at 8 MMAs per commit; the two warps take alternate pipeline
+        //       stages of the same accumulator.  The first stage of a tile overwrites the accumulator: its owner
+        //       commits to tfirst[acc] and the other warp waits for that before accumulating on top. =====
+        const int w = warp == 3 ? 1 : 0;
+        int64_t seq = 0;                                  // running stage number of this pair
+        int acc = 0; uint32_t accphase = 0;
+        const uint16_t all_mask = static_cast<uint16_t>((1u << (2 * NP)) - 1u);
+        const uint16_t pair_mask = static_cast<uint16_t>(3u << leader);
+        const uint16_t self_mask = static_cast<uint16_t>(1u << leader);
+        unsigned long long w_full = 0, w_acc = 0;
+        for (int64_t u = pair; u < p.n_units; u += npairs) {
+            UnitIter it;
+            if (!decode_unit(p, u, it)) continue;
+            for (int64_t gt = it.gt0; gt < it.gt1; ++gt) {
+                const bool first_owner = (seq & 1) == w;  // this warp issues the tile's first (overwriting) stage
+                if (first_owner || KS == 1) {               // (KS == 1: the idle warp must not run ahead of the phase)
+                    if (prof) { const long long t0 = clock64(); mbar_wait(&tl->tempty[acc], accphase ^ 1); w_acc += clock64() - t0; }
+                    else mbar_wait(&tl->tempty[acc], accphase ^ 1);
+                } else if (KS > 1) {
+                    mbar_wait(&tl->tfirst[acc], accphase);
                 }
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * kMaxBN;
+                for (int ks = 0; ks < KS; ++ks, ++seq) {
+                    if ((seq & 1) != w) continue;
+                    const int stage = static_cast<int>(seq % kStages);
+                    const int nsub = min(kSub, p.KB - ks * kSub);
+                    const int fb = static_cast<int>(seq % (kIssuers * kStages));
+                    const uint32_t fphase = static_cast<uint32_t>(seq / (kIssuers * kStages)) & 1u;
+                    if (prof) { const long long t0 = clock64(); mbar_wait(&tl->full[fb], fphase); w_full += clock64() - t0; }
+                    else mbar_wait(&tl->full[fb], fphase);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(sA + stage * kAStage);
+                    const uint32_t b0 = smem_u32(sB + stage * kBStage);
+                    if (lane == 0) {
+                        if (!(p.exp_mode & 4)) {
+                            for (int sb = 0; sb < nsub; ++sb) {
+#pragma unroll
+                                for (int k = 0; k < kBK / 16; ++k)
+                                    mma_f16_ss_2sm(d_tmem, umma_desc_sw128(a0 + sb * kABytes, k * 32),
+                                                   umma_desc_sw128(b0 + sb * kBBytes, k * 32), p.idesc,
+                                                   (ks | sb | k) != 0 ? 1u : 0u);
+                            }
+                        }
+                        mma_commit_2sm(&tl->empty[stage], all_mask);    // one of the NP arrivals that free the stage
+                        if (ks == 0 && KS > 1) mma_commit_2sm(&tl->tfirst[acc], self_mask);
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) mma_commit_2sm(&tl->tfull[acc], pair_mask);   // this warp's share of the tile is done
+                __syncwarp();
+                if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
+            }
+        }
+        if (prof && lane == 0) { atomicAdd(&p.ctr->cyc_mma_wait_full, w_full); atomicAdd(&p.ctr->cyc_mma_wait_acc, w_acc); }
+    } else if (NP > 1 && warp == 1 && rank == 1) {
+        // ===== relay (peer CTA): tell the leader when this CTA's stage has landed =====
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t lfull0 = mapa(smem_u32(&tl->full[0]), leader);
+        for (int64_t u = pair; u < p.n_units; u += npairs) {
+            UnitIter it;
+            if (!decode_unit(p, u, it)) continue;
+            for (int64_t n = (it.gt1 - it.gt0) * KS; n > 0; --n) {
+                mbar_wait(&tl->full[stage], phase);
+                if (lane == 0) mbar_arrive_cluster(lfull0 + stage * static_cast<uint32_t>(sizeof(uint64_t)));
+                __syncwarp();
+                if (++stage == kIssuers * kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -409,15 +511,16 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float xfloor = __uint_as_float(p.ctr->xfloor_bits);
         const float dfloor = sqrtf(xfloor) * 1.000001f;
         int acc = 0; uint32_t accphase = 0;
-        const uint32_t tempty_leader0 = mapa(smem_u32(&tl->tempty[0]), 0);
-        const uint32_t tempty_leader1 = mapa(smem_u32(&tl->tempty[1]), 0);
+        const uint32_t tempty_leader0 = mapa(smem_u32(&tl->tempty[0]), leader);
+        const uint32_t tempty_leader1 = mapa(smem_u32(&tl->tempty[1]), leader);
+        unsigned long long e_busy = 0, e_wait = 0;
         for (int64_t u = pair; u < p.n_units; u += npairs) {
             UnitIter it;
             if (!decode_unit(p, u, it)) continue;
             // per-unit column arrays -> smem
             named_bar_sync(1, 32 * kEpiWarps);
             if (te < BN) {
-                const int64_t c = it.jt * BN + te;
+                const int64_t c = (it.jt * NP + pq) * BN + te;
                 tl->na[te] = p.na[c];
                 tl->wl[te] = p.wl[c];
                 tl->wr[te] = p.wr[c];
@@ -435,13 +538,22 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int32_t rm = tl->row[te];
                     if (rm >= 0) atomicMin(&tl->thr[te], *reinterpret_cast<volatile unsigned int *>(p.gthr + rm));
                 }
-                mbar_wait(&tl->tfull[acc], accphase);
+                long long t_e0 = 0;
+                if (prof) { const long long t0 = clock64(); mbar_wait(&tl->tfull[acc], accphase); t_e0 = clock64(); e_wait += t_e0 - t0; }
+                else mbar_wait(&tl->tfull[acc], accphase);
                 tc_fence_after();
                 const int64_t g = (gt * kPairM + rank * kBM + q * 32 + lane) * p.g_stride;
                 const float nb = p.gnorm[g];
                 const uint32_t trow = tmem_base + static_cast<uint32_t>(acc) * kMaxBN + (static_cast<uint32_t>(q * 32) << 16);
 
                 float dprev = kBig;
+                if (p.exp_mode & 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
+                    if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
+                    continue;
+                }
                 if (cbeg > 0) {
                     uint32_t v;
                     tmem_ld_x1(trow + cbeg * kChunk - 1, v);
@@ -593,8 +705,10 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
                 if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
+                if (prof) e_busy += clock64() - t_e0;
             }
         }
+        if (prof && lane == 0) { atomicAdd(&p.ctr->cyc_epi_busy, e_busy); atomicAdd(&p.ctr->cyc_epi_wait, e_wait); }
     }
 
     tc_fence_before();
@@ -956,13 +1070,54 @@ int launch_merge(const uint64_t *gathered, int32_t nshards, int64_t P, uint64_t 
 // -------------------------------------------------------------------------------------------
 static int g_num_sms = 0;
 
-static int launch_screen(const eosvr_gallery *g, eosvr_workspace *ws, const MatchPlan &pl, const CUtensorMap &tmA,
-                         const CUtensorMap &tmB, int64_t gallery_tiles, int64_t g_stride, int seed_mode, int64_t P,
+static int g_max_clusters[3] = {0, 0, 0};   // co-resident clusters of k_match_screen<NP>, NP = 1, 2
+
+template <int NP>
+static int launch_screen_np(const CUtensorMap &tmA, const CUtensorMap &tmB, const ScreenParams &sp, cudaStream_t st)
+{
+    auto kern = k_match_screen<NP>;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2 * NP; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = kScreenSmem;
+    cfg.stream = st;
+    if (g_max_clusters[NP] == 0) {
+        EOSVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kScreenSmem)));
+        cfg.gridDim = dim3(static_cast<unsigned>(g_num_sms / (2 * NP) * (2 * NP)), 1, 1);
+        int n = 0;
+        EOSVR_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+        if (n < 1) { set_error("k_match_screen<%d>: no cluster of %d CTAs can be resident", NP, 2 * NP); return EOSVR_ECUDA; }
+        g_max_clusters[NP] = n;
+    }
+    const int64_t ncl = sp.n_units < g_max_clusters[NP] ? sp.n_units : g_max_clusters[NP];
+    cfg.gridDim = dim3(static_cast<unsigned>(ncl * 2 * NP), 1, 1);
+    EOSVR_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, sp));
+    return EOSVR_OK;
+}
+
+// pairs per cluster of the next screening launches: 2 when there are at least two probe tiles (the pairs of a
+// cluster share the gallery tile), else 1.  EOSVR_NP=1|2 overrides (experiments).
+static int choose_np(int64_t NT)
+{
+    static int np_env = -1;
+    if (np_env < 0) { const char *e = getenv("EOSVR_NP"); np_env = e ? atoi(e) : 0; }
+    if (np_env == 1) return 1;
+    return NT >= 2 ? 2 : 1;
+}
+
+static int launch_screen(const eosvr_gallery *g, eosvr_workspace *ws, const MatchPlan &pl, int np, bool seed,
+                         const CUtensorMap &tmB, int64_t gallery_tiles, int64_t g_stride, int64_t P,
                          bool timed, cudaStream_t st)
 {
     ScreenParams sp;
     sp.gnorm = g->gnorm; sp.G = g->G; sp.KB = g->Dp / kBK; sp.BN = pl.BN; sp.NT = pl.NT;
+    sp.NTG = pl.NT / np;
     sp.GT = gallery_tiles;
+    const int seed_mode = seed ? 1 : 0;
     const int64_t total_tiles = sp.NT * sp.GT;
     int64_t tpu = total_tiles / (static_cast<int64_t>(g_num_sms / 2) * 6);
     if (tpu < 1) tpu = 1;
@@ -970,7 +1125,7 @@ static int launch_screen(const eosvr_gallery *g, eosvr_workspace *ws, const Matc
     if (tpu > sp.GT) tpu = sp.GT;
     sp.TPU = static_cast<int32_t>(tpu);
     sp.n_chunks = (sp.GT + tpu - 1) / tpu;
-    sp.n_units = sp.n_chunks * sp.NT;
+    sp.n_units = sp.n_chunks * sp.NTG;
     sp.g_stride = g_stride; sp.seed_mode = seed_mode;
     {
         static int order_env = -1, tpu_env = -1;
@@ -980,7 +1135,7 @@ static int launch_screen(const eosvr_gallery *g, eosvr_workspace *ws, const Matc
         if (tpu_env > 0 && !seed_mode) {
             sp.TPU = static_cast<int32_t>(tpu_env < sp.GT ? tpu_env : sp.GT);
             sp.n_chunks = (sp.GT + sp.TPU - 1) / sp.TPU;
-            sp.n_units = sp.n_chunks * sp.NT;
+            sp.n_units = sp.n_chunks * sp.NTG;
         }
     }
     sp.na = ws->na; sp.wl = ws->wl; sp.wr = ws->wr; sp.margin = ws->margin; sp.rowmap = ws->rowmap;
@@ -989,12 +1144,17 @@ static int launch_screen(const eosvr_gallery *g, eosvr_workspace *ws, const Matc
     sp.ctr = ws->counters; sp.rowflag = ws->rowflag;
     sp.idesc = umma_idesc_f16(g->screen_fmt == EOSVR_SCREEN_F16 ? 0 : 1, kPairM, pl.BN);
     sp.dbg = (!seed_mode && ws->dbg && ws->dbg_elems >= P * g->G) ? ws->dbg : nullptr;
-    const int64_t max_pairs = g_num_sms / 2;
-    const unsigned grid = 2u * static_cast<unsigned>(sp.n_units < max_pairs ? sp.n_units : max_pairs);
+    {
+        static int exp_env = -1;
+        if (exp_env < 0) { const char *e = getenv("EOSVR_EXP"); exp_env = e ? atoi(e) : 0; }
+        sp.exp_mode = exp_env;
+    }
     const bool rec = timed && ws->timing_on && ws->timing_calls < kTimingRing;
     if (rec) EOSVR_CUDA(cudaEventRecord(ws->ev0[ws->timing_calls], st));
-    k_match_screen<<<grid, kThreads, kScreenSmem, st>>>(tmA, tmB, sp);
-    EOSVR_CUDA(cudaGetLastError());
+    int rc;
+    if (np == 2) rc = launch_screen_np<2>(seed ? g->tmapSeedH : g->tmapAH, tmB, sp, st);
+    else rc = launch_screen_np<1>(seed ? g->tmapSeed : g->tmapA, tmB, sp, st);
+    if (rc) return rc;
     if (rec) { EOSVR_CUDA(cudaEventRecord(ws->ev1[ws->timing_calls], st)); ++ws->timing_calls; }
     EOSVR_COUNT_LAUNCH(1);
     return EOSVR_OK;
@@ -1010,7 +1170,9 @@ int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probe
         EOSVR_CUDA(cudaGetDevice(&dev));
         EOSVR_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    const MatchPlan pl = make_plan(P, rpe);
+    MatchPlan pl = make_plan(P, rpe);
+    const int np = exact_only ? 1 : choose_np(pl.NT);
+    pl.NT = (pl.NT + np - 1) / np * np;           // pad with empty probe tiles: every pair of a cluster has one
     const int64_t ncol = pl.NT * pl.BN;
     if (ncol > ws->cap_rows) {
         set_error("workspace too small: plan needs %lld rows, capacity %lld", (long long)ncol, (long long)ws->cap_rows);
@@ -1053,16 +1215,14 @@ int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probe
         int rc = encode_tmap_2d(&tmB, ws->q16, g->screen_fmt, static_cast<uint64_t>(ncol),
                                 static_cast<uint64_t>(g->Dp), static_cast<uint32_t>(pl.BN / 2), kBK);
         if (rc) return rc;
-        EOSVR_CUDA(cudaFuncSetAttribute(k_match_screen, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(kScreenSmem)));
         const int64_t GT = (g->G + kPairM - 1) / kPairM;   // 256-row tiles of the CTA pair
         // seed pass over a strided sample of the gallery: tightens every probe row's threshold before the
         // full pass so that concurrent CTAs do not flood the candidate lists
         if (g->seed_tiles > 0 && GT > g->seed_tiles) {
-            rc = launch_screen(g, ws, pl, g->tmapSeed, tmB, g->seed_tiles, g->seed_stride, 1, P, false, st);
+            rc = launch_screen(g, ws, pl, np, true, tmB, g->seed_tiles, g->seed_stride, P, false, st);
             if (rc) return rc;
         }
-        rc = launch_screen(g, ws, pl, g->tmapA, tmB, GT, 1, 0, P, true, st);
+        rc = launch_screen(g, ws, pl, np, false, tmB, GT, 1, P, true, st);
         if (rc) return rc;
         ws->last_tiles = pl.NT * GT;
 

@@ -78,6 +78,19 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// Multicast variant: the box lands at the same CTA-relative offset in every CTA of cta_mask, and each of
+// those CTAs gets the complete_tx on the mbarrier at the same CTA-relative offset.
+__device__ __forceinline__ void tma_load_2d_mc(void *smem_dst, const CUtensorMap *m, uint64_t *bar,
+                                               int32_t c0, int32_t c1, uint16_t cta_mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)),
+          "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+
 // ---- tcgen05 ------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before()
 {

@@ -120,6 +120,13 @@ class MatchWorkspace:
         keys = ["candidates", "exact_evals", "fallback_rows", "cand_capacity", "tiles", "mma_n", "unsafe", "spilled"]
         return dict(zip(keys, [int(v) for v in out]))
 
+    def debug_cycles(self, stream=None) -> dict:
+        """Cycle accounting of the last screening kernel (needs EOSVR_EXP bit 16 in the environment)."""
+        out = (ctypes.c_int64 * 6)()
+        check(lib().eosvr_workspace_debug_cycles(self._h, _stream_ptr(stream), out), "eosvr_workspace_debug_cycles")
+        keys = ["epi_busy", "epi_wait", "mma_wait_full", "mma_wait_acc", "prod_wait", "total"]
+        return dict(zip(keys, [int(v) for v in out]))
+
     def close(self):
         if self._h:
             lib().eosvr_workspace_destroy(self._h)

@@ -194,6 +194,12 @@ int      eosvr_plan(int64_t P, int32_t rows_per_episode, int64_t out[4]);
  * eosvr_match calls into a caller-owned device buffer of `elems` floats; NULL disables. */
 int eosvr_workspace_set_debug(eosvr_workspace_t *ws, float *d_dump, int64_t elems);
 
+/* Cycle accounting of the last screening kernel when the environment variable EOSVR_EXP has bit 16 set
+ * (measurement only; sums over CTAs): out = {epilogue busy, epilogue waiting for accumulators, MMA issuer
+ * waiting for operands, MMA issuer waiting for a free accumulator, TMA producers waiting for a free stage,
+ * kernel cycles summed over pair leaders}. */
+int eosvr_workspace_debug_cycles(eosvr_workspace_t *ws, void *stream, int64_t out[6]);
+
 #ifdef __cplusplus
 }
 #endif

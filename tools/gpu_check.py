@@ -94,7 +94,7 @@ def case_match_batch():
 
 def case_match_halo():
     # rows_per_episode > 256 -> halo columns
-    return _case_match(2, 75, 4, 256, 1500, 7)
+    return _case_match(2, 60, 5, 256, 1500, 7)
 
 
 def case_match_lam():
@@ -163,6 +163,14 @@ def case_perf(clustered=False):
     print(f"  match P={A.shape[0]} G={G} D={D}: {ms:.3f} ms/call ({fl / ms / 1e9:.1f} TFLOP/s); screening kernel "
           f"{kms / kn:.3f} ms ({fl / (kms / kn) / 1e9:.1f} TFLOP/s)  order={os.environ.get('EOSVR_ORDER', '0')} "
           f"tpu={os.environ.get('EOSVR_TPU', 'auto')}  stats={ws.stats()}")
+    if int(os.environ.get("EOSVR_EXP", "0")) & 16:
+        c = ws.debug_cycles()
+        tot = max(c["total"], 1)
+        n_lead, n_cta, n_epi = 74, 148, 148 * 8
+        print("  cycles per pair (kernel): %.0f;  fractions of kernel time: epi_busy %.3f  epi_wait %.3f  mma_wait_full %.3f"
+              "  mma_wait_acc %.3f  prod_wait %.3f" % (tot / n_lead, c["epi_busy"] / n_epi / (tot / n_lead),
+              c["epi_wait"] / n_epi / (tot / n_lead), c["mma_wait_full"] / tot, c["mma_wait_acc"] / tot,
+              c["prod_wait"] / n_cta / (tot / n_lead)))
     oid, _ = O.c_match(A[:rpe], gal, rpe)
     print("  first episode idx equal:", np.array_equal(idx[:rpe].cpu().numpy(), oid))
     return True
