@@ -14,14 +14,17 @@ constexpr int kBM = 128;          // gallery rows per CTA and tile (one TMEM lan
 constexpr int kPairM = 256;       // gallery rows per CTA pair and tile (UMMA M with cta_group::2)
 constexpr int kBK = 64;           // K elements per pipeline stage (128-byte rows, SWIZZLE_128B)
 constexpr int kMaxBN = 256;       // probe columns per tile (UMMA N), multiple of 16
-constexpr int kSub = 2;           // K blocks per pipeline stage: 4*kSub MMAs are issued per tcgen05.commit (a commit
-                                  // costs the issuing thread ~700 cycles; tools/bench_micro/mma_rate.cu)
-constexpr int kStages = 3;        // TMA -> MMA smem ring (kSub x (16 KiB A + 16 KiB B-half) per stage and CTA)
-constexpr int kIssuers = 2;       // MMA issuer warps (alternate pipeline stages)
+constexpr int kSub = 1;           // K blocks per pipeline stage (4*kSub MMAs per tcgen05.commit)
+constexpr int kStages = 6;        // TMA -> MMA smem ring (kSub x (16 KiB A + 16 KiB B-half) per stage and CTA)
+constexpr int kIssuers = 3;       // MMA issuer warps 1..3 of the pair's leader; stage s belongs to issuer s % kIssuers.
+                                  // A tcgen05.commit blocks its thread for ~600 cycles and a UTCHMMA for ~70
+                                  // (tools/bench_micro/mma_rate.cu): one thread sustains only ~1/3 of the MMA rate.
 constexpr int kAccStages = 2;     // TMEM accumulator double buffer (2 x 256 columns)
 constexpr int kTmemCols = 512;
 constexpr int kEpiWarps = 8;      // warps 4..11
-constexpr int kThreads = 128 + 32 * kEpiWarps;
+constexpr int kProdBWarp = 4 + kEpiWarps;   // warp 12: second TMA producer (probe operand); warp 0 loads the gallery
+constexpr int kThreads = 128 + 32 * kEpiWarps + 32;
+static_assert(kStages % kIssuers == 0, "every stage barrier must have a single consumer warp");
 constexpr int kChunk = 16;        // TMEM columns per tcgen05.ld
 constexpr int kMaxSeedTiles = 2;  // strided gallery tiles screened first to seed the per-probe thresholds
 constexpr float kPadNorm = 1.0e30f;

@@ -276,6 +276,13 @@ struct ScreenParams {
                             // 2 = producer skips the TMA loads, 4 = MMA issuer skips the MMAs
 };
 
+struct StagedCand {
+    int32_t rm;         // probe row
+    int32_t g;          // gallery row (local to the shard)
+    uint32_t tbits;
+};
+constexpr int kWarpStage = 64;
+
 struct __align__(16) ScreenSmemTail {
     float na[kMaxBN];
     float wl[kMaxBN];
@@ -283,14 +290,17 @@ struct __align__(16) ScreenSmemTail {
     float mg[kMaxBN];
     unsigned int thr[kMaxBN];
     int32_t row[kMaxBN];
-    uint64_t full[kIssuers * kStages];   // indexed by (running stage number) % (kIssuers*kStages): consecutive fills of
-                                         // a stage go to alternate MMA issuers, and a parity wait is only safe on a
-                                         // barrier whose every phase the waiter observes
+    uint64_t full[kStages];           // stage s is always consumed by issuer s % kIssuers: a parity wait is only safe
+                                      // on a barrier whose every phase the waiter observes
     uint64_t empty[kStages];
     uint64_t tfull[kAccStages];
     uint64_t tempty[kAccStages];
     uint64_t tfirst[kAccStages];      // the overwriting first stage of a tile has completed
     uint32_t tmem_base;
+    // candidate staging: every epilogue warp parks its candidates in shared memory and hands them to the
+    // per-row lists 32 at a time (one global atomicAdd per lane, all in flight together) instead of stalling on
+    // one atomic round trip per column
+    StagedCand stage[kEpiWarps][kWarpStage];
 };
 
 constexpr int kABytes = kBM * kBK * 2;              // 16 KiB: this CTA's 128 gallery rows
@@ -327,6 +337,39 @@ __device__ __forceinline__ bool decode_unit(const ScreenParams &p, int64_t u, Un
 // gallery tile against two different probe tiles: every CTA fetches half of its 128-row gallery slab and
 // multicasts it to the CTA of equal parity in the other pair, so the gallery operand crosses L2 -> SM once
 // per cluster instead of once per pair (the kernel is bound by operand delivery).
+// Store candidate (g, tbits) of probe row rm at list position pos; full lists spill to the shared buffer and only
+// if that is full too is the row handed to the exhaustive exact kernel.
+__device__ __forceinline__ void put_candidate(const ScreenParams &p, int32_t rm, unsigned pos, int32_t g, uint32_t tbits)
+{
+    if (pos < static_cast<unsigned>(p.cand_cap)) {
+        Cand cd;
+        cd.g = g; cd.tbits = tbits;
+        p.cand[static_cast<int64_t>(rm) * p.cand_cap + pos] = cd;
+    } else {
+        const unsigned op = atomicAdd(&p.ctr->ovf_count, 1u);
+        if (op < static_cast<unsigned>(p.ovf_cap)) {
+            OvfCand oc;
+            oc.p = rm; oc.g = g; oc.tbits = tbits; oc.pad = 0;
+            p.ovf[op] = oc;
+        } else {
+            p.rowflag[rm] = 1;
+            p.ctr->overflow = 1u;
+        }
+    }
+}
+
+// Hand the n (< 64) candidates parked by a warp to their rows' lists: one atomicAdd per lane, all in flight together.
+__device__ __forceinline__ void flush_staged(const ScreenParams &p, const StagedCand *st, int n, int lane)
+{
+    __syncwarp();
+    for (int e = lane; e < n; e += 32) {
+        const StagedCand sc = st[e];
+        const unsigned pos = atomicAdd(p.rowcnt + sc.rm, 1u);
+        put_candidate(p, sc.rm, pos, sc.g, sc.tbits);
+    }
+    __syncwarp();
+}
+
 template <int NP>
 __global__ void __launch_bounds__(kThreads, 1)
 k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -353,8 +396,7 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // NP > 1: every CTA collects its own bytes on its own full barrier and the peer relays its completion
         // to the leader (second arrival); the stage is free once the MMAs of ALL pairs have read it.
         const uint32_t full_count = (NP > 1 && rank == 0) ? 2u : 1u;
-        for (int s = 0; s < kIssuers * kStages; ++s) mbar_init(&tl->full[s], full_count);
-        for (int s = 0; s < kStages; ++s) mbar_init(&tl->empty[s], NP);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&tl->full[s], full_count); mbar_init(&tl->empty[s], NP); }
         for (int s = 0; s < kAccStages; ++s) {
             mbar_init(&tl->tfull[s], kIssuers);          // one commit per MMA issuer warp
             mbar_init(&tl->tempty[s], 2 * kEpiWarps);
@@ -369,12 +411,13 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = tl->tmem_base;
     const bool prof = (p.exp_mode & 16) != 0;
 
-    // Warps 0, 1 and 3 run their loops with the WHOLE warp (warp-uniform control flow and operands: no
-    // per-instruction uniformisation loops around UTMALDG / UTCHMMA / UTCBAR); lane 0 issues.
-    if (warp == 0) {
-        // ===== TMA producer (every CTA): own gallery rows + own half of the pair's probe tile =====
+    // Producer and issuer warps run their loops with the whole warp; lane 0 issues.
+    if (warp == 0 || warp == kProdBWarp) {
+        // ===== TMA producers (every CTA): warp 0 loads the CTA's gallery rows (A), warp 12 its half of the pair's
+        //       probe tile (B) -- a UTMALDG occupies its issuing thread for ~150 cycles, so one thread per operand.
+        //       Warp 0 also posts the byte count of the whole stage. =====
+        const bool isA = warp == 0;
         int stage = 0; uint32_t phase = 0;
-        int fb = 0;                                   // full-barrier slot = running stage number % (kIssuers*kStages)
         const int32_t bhalf = p.BN >> 1;
         const uint32_t tx_cta = kABytes + static_cast<uint32_t>(bhalf) * kBK * 2;
         uint16_t mc_mask = 0;
@@ -394,45 +437,43 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     else mbar_wait(&tl->empty[stage], phase ^ 1);
                     if (lane == 0) {
                         if (p.exp_mode & 2) {
-                            if (NP > 1 || rank == 0) mbar_arrive(&tl->full[fb]);
+                            if (isA && (NP > 1 || rank == 0)) mbar_arrive(&tl->full[stage]);
                         } else if (NP == 1) {
                             // the bytes of both CTAs complete on the LEADER's full barrier: only the leader
                             // arrives; the peer cannot run ahead of the phase because its stage is freed by
                             // the leader's MMA commit
-                            const uint32_t lbar = lbar0 + fb * static_cast<uint32_t>(sizeof(uint64_t));
-                            if (rank == 0) mbar_arrive_expect_tx(&tl->full[fb], 2u * tx_cta * nsub);
+                            const uint32_t lbar = lbar0 + stage * static_cast<uint32_t>(sizeof(uint64_t));
+                            if (isA && rank == 0) mbar_arrive_expect_tx(&tl->full[stage], 2u * tx_cta * nsub);
                             for (int sb = 0; sb < nsub; ++sb) {
                                 const int32_t kc = (ks * kSub + sb) * kBK;
-                                tma_load_2d_2sm(sA + stage * kAStage + sb * kABytes, &tmA, lbar, kc, arow);
-                                tma_load_2d_2sm(sB + stage * kBStage + sb * kBBytes, &tmB, lbar, kc, brow);
+                                if (isA) tma_load_2d_2sm(sA + stage * kAStage + sb * kABytes, &tmA, lbar, kc, arow);
+                                else tma_load_2d_2sm(sB + stage * kBStage + sb * kBBytes, &tmB, lbar, kc, brow);
                             }
                         } else {
-                            mbar_arrive_expect_tx(&tl->full[fb], tx_cta * nsub);
+                            if (isA) mbar_arrive_expect_tx(&tl->full[stage], tx_cta * nsub);
                             for (int sb = 0; sb < nsub; ++sb) {
                                 const int32_t kc = (ks * kSub + sb) * kBK;
-                                tma_load_2d_mc(sA + stage * kAStage + sb * kABytes + pq * (kABytes / NP), &tmA,
-                                               &tl->full[fb], kc, arow, mc_mask);
-                                tma_load_2d(sB + stage * kBStage + sb * kBBytes, &tmB, &tl->full[fb], kc, brow);
+                                if (isA) tma_load_2d_mc(sA + stage * kAStage + sb * kABytes + pq * (kABytes / NP), &tmA,
+                                                        &tl->full[stage], kc, arow, mc_mask);
+                                else tma_load_2d(sB + stage * kBStage + sb * kBBytes, &tmB, &tl->full[stage], kc, brow);
                             }
                         }
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
-                    if (++fb == kIssuers * kStages) fb = 0;
                 }
             }
         }
-        if (prof && lane == 0) {
+        if (prof && lane == 0 && isA) {
             atomicAdd(&p.ctr->cyc_prod_wait, w_prod);
             if (rank == 0) atomicAdd(&p.ctr->cyc_total, static_cast<unsigned long long>(clock64() - t_begin));
         }
-    } else if ((warp == 1 || warp == 3) && rank == 0) {
-        // ===== MMA issuers: two warps of the pair's leader drive the tensor cores of both SMs.  A tcgen05.commit
-        //       blocks its issuing thread for ~600 cycles and a UTCHMMA for ~70 (tools/bench_micro/mma_rate.cu), so
-        //       ONE issuer cannot keep the pipe busy at 8 MMAs per commit; the two warps take alternate pipeline
-        //       stages of the same accumulator.  The first stage of a tile overwrites the accumulator: its owner
-        //       commits to tfirst[acc] and the other warp waits for that before accumulating on top. =====
-        const int w = warp == 3 ? 1 : 0;
+    } else if (warp >= 1 && warp <= kIssuers && rank == 0) {
+        // ===== MMA issuers: kIssuers warps of the pair's leader drive the tensor cores of both SMs, taking the
+        //       pipeline stages round-robin (stage s -> issuer s % kIssuers) into the same accumulator.  The first
+        //       stage of a tile overwrites the accumulator: its owner commits to tfirst[acc] and the other warps wait
+        //       for that before accumulating on top.  Every issuer observes every phase of tempty / tfirst. =====
+        const int w = warp - 1;
         int64_t seq = 0;                                  // running stage number of this pair
         int acc = 0; uint32_t accphase = 0;
         const uint16_t all_mask = static_cast<uint16_t>((1u << (2 * NP)) - 1u);
@@ -443,23 +484,19 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             UnitIter it;
             if (!decode_unit(p, u, it)) continue;
             for (int64_t gt = it.gt0; gt < it.gt1; ++gt) {
-                const bool first_owner = (seq & 1) == w;  // this warp issues the tile's first (overwriting) stage
-                if (first_owner || KS == 1) {               // (KS == 1: the idle warp must not run ahead of the phase)
-                    if (prof) { const long long t0 = clock64(); mbar_wait(&tl->tempty[acc], accphase ^ 1); w_acc += clock64() - t0; }
-                    else mbar_wait(&tl->tempty[acc], accphase ^ 1);
-                } else if (KS > 1) {
-                    mbar_wait(&tl->tfirst[acc], accphase);
-                }
+                const bool first_owner = static_cast<int>(seq % kIssuers) == w;   // issues the overwriting stage
+                if (prof) { const long long t0 = clock64(); mbar_wait(&tl->tempty[acc], accphase ^ 1); w_acc += clock64() - t0; }
+                else mbar_wait(&tl->tempty[acc], accphase ^ 1);
+                if (!first_owner) mbar_wait(&tl->tfirst[acc], accphase);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * kMaxBN;
                 for (int ks = 0; ks < KS; ++ks, ++seq) {
-                    if ((seq & 1) != w) continue;
+                    if (static_cast<int>(seq % kIssuers) != w) continue;
                     const int stage = static_cast<int>(seq % kStages);
+                    const uint32_t phase = static_cast<uint32_t>(seq / kStages) & 1u;
                     const int nsub = min(kSub, p.KB - ks * kSub);
-                    const int fb = static_cast<int>(seq % (kIssuers * kStages));
-                    const uint32_t fphase = static_cast<uint32_t>(seq / (kIssuers * kStages)) & 1u;
-                    if (prof) { const long long t0 = clock64(); mbar_wait(&tl->full[fb], fphase); w_full += clock64() - t0; }
-                    else mbar_wait(&tl->full[fb], fphase);
+                    if (prof) { const long long t0 = clock64(); mbar_wait(&tl->full[stage], phase); w_full += clock64() - t0; }
+                    else mbar_wait(&tl->full[stage], phase);
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(sA + stage * kAStage);
                     const uint32_t b0 = smem_u32(sB + stage * kBStage);
@@ -474,16 +511,18 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                         mma_commit_2sm(&tl->empty[stage], all_mask);    // one of the NP arrivals that free the stage
-                        if (ks == 0 && KS > 1) mma_commit_2sm(&tl->tfirst[acc], self_mask);
+                        if (ks == 0) mma_commit_2sm(&tl->tfirst[acc], self_mask);
                     }
                     __syncwarp();
                 }
+                if (first_owner) mbar_wait(&tl->tfirst[acc], accphase);     // long complete; keeps the phase observed
                 if (lane == 0) mma_commit_2sm(&tl->tfull[acc], pair_mask);   // this warp's share of the tile is done
                 __syncwarp();
                 if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
             }
         }
-        if (prof && lane == 0) { atomicAdd(&p.ctr->cyc_mma_wait_full, w_full); atomicAdd(&p.ctr->cyc_mma_wait_acc, w_acc); }
+        if (prof && lane == 0 && w == 0) atomicAdd(&p.ctr->cyc_mma_wait_acc, w_acc);
+        if (prof && lane == 0) atomicAdd(&p.ctr->cyc_mma_wait_full, w_full);
     } else if (NP > 1 && warp == 1 && rank == 1) {
         // ===== relay (peer CTA): tell the leader when this CTA's stage has landed =====
         int stage = 0; uint32_t phase = 0;
@@ -495,10 +534,10 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&tl->full[stage], phase);
                 if (lane == 0) mbar_arrive_cluster(lfull0 + stage * static_cast<uint32_t>(sizeof(uint64_t)));
                 __syncwarp();
-                if (++stage == kIssuers * kStages) { stage = 0; phase ^= 1; }
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 4 + kEpiWarps) {
         // ===== epilogue: 8 warps, warp%4 selects the TMEM lane quadrant, (warp-4)/4 the column half =====
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
@@ -514,6 +553,8 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t tempty_leader0 = mapa(smem_u32(&tl->tempty[0]), leader);
         const uint32_t tempty_leader1 = mapa(smem_u32(&tl->tempty[1]), leader);
         unsigned long long e_busy = 0, e_wait = 0;
+        StagedCand *wstage = tl->stage[warp - 4];
+        int wn = 0;                                       // candidates parked by this warp (warp-uniform)
         for (int64_t u = pair; u < p.n_units; u += npairs) {
             UnitIter it;
             if (!decode_unit(p, u, it)) continue;
@@ -614,11 +655,13 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     const bool guard = (minx < xfloor) || (fminf(dprev_in, dn) < dfloor);
-                    if (__any_sync(0xffffffffu, any || guard)) {
-                        // ---- rare path (whole warp).  Only the columns in which some lane is below its
-                        //      threshold (or, if the cancellation guard fired, all columns) are visited:
-                        //      tighten the threshold with the warp minimum first, then append what is still
-                        //      below it with one atomicAdd per warp and column ----
+                    if (__any_sync(0xffffffffu, any || guard) && !(p.exp_mode & 32)) {
+                        // ---- rare path (whole warp, kept small: one loop body, no unrolling).  Only the columns in
+                        //      which some lane is below its threshold (or, if the cancellation guard fired, all
+                        //      columns) are visited.  The column and its two neighbours are read again from TMEM
+                        //      (same arithmetic, same bits as above) so no register array is indexed dynamically.
+                        //      First tighten the threshold with the warp minimum, then park what is still below it
+                        //      in the warp's staging buffer. ----
                         unsigned cm = 0;
                         {
                             const float4 *th4b = reinterpret_cast<const float4 *>(tl->thr + c0);
@@ -634,21 +677,29 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (guard) cm = 0xFFFFu;
                         cm = __reduce_or_sync(0xffffffffu, cm);
                         const bool rowok = g < p.G;
-#pragma unroll
-                        for (int j = 0; j < kChunk; ++j) {
-                            if (!(cm & (1u << j))) continue;               // warp-uniform
-                            const int c = c0 + j;
+#pragma unroll 1
+                        while (cm) {
+                            const int c = c0 + __ffs(cm) - 1;              // warp-uniform
+                            cm &= cm - 1;
                             const int32_t rm = tl->row[c];
                             if (rm < 0) continue;                          // warp-uniform
-                            const float dl = j ? d[j - 1] : dprev_in;
-                            const float dr = (j < kChunk - 1) ? d[j + 1] : dn;
-                            const float m3 = fminf(d[j], fminf(tl->wl[c] > 0.f ? dl : kBig,
-                                                               tl->wr[c] > 0.f ? dr : kBig));
+                            uint32_t vc, vl = 0, vr = 0;
+                            const bool hl = c > 0, hr = c + 1 < BN;
+                            tmem_ld_x1(trow + c, vc);
+                            if (hl) tmem_ld_x1(trow + c - 1, vl);
+                            if (hr) tmem_ld_x1(trow + c + 1, vr);
+                            tmem_ld_wait();
+                            const float dj = sqrt_approx(fmaxf(fmaf(-2.f, __uint_as_float(vc), nb) + tl->na[c], 0.f));
+                            const float dl = hl ? sqrt_approx(fmaxf(fmaf(-2.f, __uint_as_float(vl), nb) + tl->na[c - 1], 0.f)) : kBig;
+                            const float dr = hr ? sqrt_approx(fmaxf(fmaf(-2.f, __uint_as_float(vr), nb) + tl->na[c + 1], 0.f)) : kBig;
+                            const float wlc = tl->wl[c], wrc = tl->wr[c];
+                            const float tj = fmaf(wlc, dl, fmaf(wrc, dr, dj));
+                            const float m3 = fminf(dj, fminf(wlc > 0.f ? dl : kBig, wrc > 0.f ? dr : kBig));
                             const bool uns = rowok && (m3 < dfloor);
                             float thr = __uint_as_float(*reinterpret_cast<volatile unsigned int *>(&tl->thr[c]));
-                            bool pass = rowok && !uns && (t[j] <= thr);
+                            bool pass = rowok && !uns && (tj <= thr);
                             if (__ballot_sync(0xffffffffu, pass)) {
-                                float mn = pass ? t[j] : kBig;
+                                float mn = pass ? tj : kBig;
 #pragma unroll
                                 for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
                                 const float nt = fmaf(mn, kSlopMul, tl->mg[c]);
@@ -659,37 +710,20 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     }
                                     thr = nt;
                                 }
-                                pass = pass && (t[j] <= thr);
+                                pass = pass && (tj <= thr);
                             }
                             if (p.seed_mode) continue;
                             const bool app = pass || uns;
                             const unsigned ma = __ballot_sync(0xffffffffu, app);
                             if (ma) {
-                                unsigned base = 0;
-                                if (lane == 0) base = atomicAdd(p.rowcnt + rm, static_cast<unsigned>(__popc(ma)));
-                                base = __shfl_sync(0xffffffffu, base, 0);
                                 if (app) {
-                                    const unsigned pos = base + __popc(ma & ((1u << lane) - 1u));
-                                    if (pos < static_cast<unsigned>(p.cand_cap)) {
-                                        Cand cd;
-                                        cd.g = static_cast<int32_t>(g);
-                                        cd.tbits = uns ? kCandUnsafe : __float_as_uint(t[j]);
-                                        p.cand[static_cast<int64_t>(rm) * p.cand_cap + pos] = cd;
-                                    } else {
-                                        // row list full: spill to the shared buffer; only if that is full
-                                        // too is the row handed to the exhaustive exact kernel
-                                        const unsigned op = atomicAdd(&p.ctr->ovf_count, 1u);
-                                        if (op < static_cast<unsigned>(p.ovf_cap)) {
-                                            OvfCand oc;
-                                            oc.p = rm; oc.g = static_cast<int32_t>(g);
-                                            oc.tbits = uns ? kCandUnsafe : __float_as_uint(t[j]); oc.pad = 0;
-                                            p.ovf[op] = oc;
-                                        } else {
-                                            p.rowflag[rm] = 1;
-                                            p.ctr->overflow = 1u;
-                                        }
-                                    }
+                                    StagedCand sc;
+                                    sc.rm = rm; sc.g = static_cast<int32_t>(g);
+                                    sc.tbits = uns ? kCandUnsafe : __float_as_uint(tj);
+                                    wstage[wn + __popc(ma & ((1u << lane) - 1u))] = sc;
                                 }
+                                wn += __popc(ma);
+                                if (wn >= 32) { flush_staged(p, wstage, wn, lane); wn = 0; }
                             }
                         }
                     }
@@ -708,6 +742,7 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (prof) e_busy += clock64() - t_e0;
             }
         }
+        if (wn) flush_staged(p, wstage, wn, lane);
         if (prof && lane == 0) { atomicAdd(&p.ctr->cyc_epi_busy, e_busy); atomicAdd(&p.ctr->cyc_epi_wait, e_wait); }
     }
 
