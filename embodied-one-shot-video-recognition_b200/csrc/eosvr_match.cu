@@ -864,26 +864,33 @@ __global__ void k_rerank(const RerankParams p)
     }
 }
 
-// Block-per-row re-rank for D <= 128*EPT: the three probe rows the taps need are converted to float64
-// ONCE and kept in registers (EPT elements per thread and row); every surviving candidate then costs one
-// pass over its gallery row.  (fp32->fp64 conversions run at 16/clk/SM, so converting the probe rows per
-// candidate, as the warp-per-row kernel does, is what bounds it.)
+// Block-per-row re-rank, warp-per-candidate.  The three probe rows the taps need are staged in shared memory
+// once per row; then, in two steps:
+//   (1) float32 pre-filter: the candidates still below the row's threshold are sorted by screening value and the
+//       block's warps pull them in ascending order, each warp evaluating one candidate with float32 direct
+//       differences (relative error of the smoothed value < kF32Rel, orders of magnitude tighter than the 16-bit
+//       screening) and tightening the shared bound; a warp stops as soon as the next screening value cannot win;
+//   (2) the candidates within 2*kF32Rel of the best float32 value -- the winner and its exact ties, normally ONE
+//       candidate -- are evaluated exactly as the reference does (float64 direct differences -> float32 ->
+//       float32 FMA chain) and merged by packed 64-bit atomicMin.
+// No block-wide barrier sits between candidates, the gallery-row loads of the warps overlap, and float64 work
+// (conversions run at 16/clk/SM) is spent only where it decides the answer.
 constexpr int kRrThreads = 128;
-constexpr int kRrBatch = 2;
+constexpr float kF32Rel = 32.0f / 16777216.0f;   // 32 ulp: |t32 - t_reference| <= kF32Rel * t
 
-template <int EPT>
 __global__ void __launch_bounds__(kRrThreads)
 k_rerank_rows(const RerankParams p)
 {
-    static_assert(EPT % 4 == 0, "EPT must be a multiple of 4 (float4 loads)");
+    extern __shared__ float4 s_probe4[];          // [3][D/4]: rows p-1, p, p+1
     __shared__ int32_t s_g[kRrThreads], s_g2[kRrThreads];
     __shared__ float s_t[kRrThreads], s_t2[kRrThreads];
     __shared__ int s_warpcnt[kRrThreads / 32];
-    __shared__ double s_part[kRrThreads / 32][kRrBatch * 3];
-    __shared__ float s_bound;
+    __shared__ unsigned int s_bound, s_best32;    // float bits of positive values: unsigned order == float order
+    __shared__ int s_next, s_n32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int D = p.D;
+    const int D = p.D, D4 = p.D >> 2;
     unsigned long long appended = 0, done = 0, unsafe_n = 0;
+    const float inv_lam2 = 1.0f / p.lam2;
 
     for (int64_t row = blockIdx.x; row < p.P; row += gridDim.x) {
         const unsigned cnt = p.rowcnt[row];
@@ -892,30 +899,18 @@ k_rerank_rows(const RerankParams p)
         if (n == 0) continue;                                           // block-uniform
         const int r = static_cast<int>(row % p.rpe);
         const bool hl = r > 0, hr = (r + 1 < p.rpe) && (row + 1 < p.P);
-        const float *a1p = p.probes + row * D;
-        const float *a0p = hl ? a1p - D : a1p;
-        const float *a2p = hr ? a1p + D : a1p;
-        double a0[EPT], a1[EPT], a2[EPT];
-#pragma unroll
-        for (int i = 0; i < EPT / 4; ++i) {
-            const int k = 4 * (tid + kRrThreads * i);
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
-            if (k < D) {
-                v0 = *reinterpret_cast<const float4 *>(a0p + k);
-                v1 = *reinterpret_cast<const float4 *>(a1p + k);
-                v2 = *reinterpret_cast<const float4 *>(a2p + k);
-            }
-            a0[4 * i] = v0.x; a0[4 * i + 1] = v0.y; a0[4 * i + 2] = v0.z; a0[4 * i + 3] = v0.w;
-            a1[4 * i] = v1.x; a1[4 * i + 1] = v1.y; a1[4 * i + 2] = v1.z; a1[4 * i + 3] = v1.w;
-            a2[4 * i] = v2.x; a2[4 * i + 1] = v2.y; a2[4 * i + 2] = v2.z; a2[4 * i + 3] = v2.w;
+        const float4 *a1p = reinterpret_cast<const float4 *>(p.probes + row * D);
+        const float4 *a0p = hl ? a1p - D4 : a1p;
+        const float4 *a2p = hr ? a1p + D4 : a1p;
+        for (int k = tid; k < D4; k += kRrThreads) {
+            s_probe4[k] = a0p[k]; s_probe4[D4 + k] = a1p[k]; s_probe4[2 * D4 + k] = a2p[k];
         }
         const float thr = __uint_as_float(p.gthr[row]);
         // one-sided error bound of this row's screening values (half of the two-sided threshold margin)
         const float eps1 = 0.5f * p.margin[(row / p.planR) * p.planBN + p.planHalo + (row % p.planR)];
-        const float inv_lam2 = 1.0f / p.lam2;
         const Cand *list = p.cand + row * p.cand_cap;
         unsigned long long loc = ~0ull;
-        if (tid == 0) s_bound = thr;            // screening-domain bound; tightened by every exact value found
+        if (tid == 0) { s_bound = __float_as_uint(thr); s_best32 = 0x7f800000u; }
         __syncthreads();
 
         for (int b0 = 0; b0 < n; b0 += kRrThreads) {
@@ -926,7 +921,7 @@ k_rerank_rows(const RerankParams p)
             if (in) c = list[b0 + tid];
             const bool isuns = in && c.tbits == kCandUnsafe;
             const float tv = isuns ? -INFINITY : __uint_as_float(c.tbits);
-            const bool keep = in && (isuns || tv <= s_bound);
+            const bool keep = in && (isuns || tv <= __uint_as_float(s_bound));
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             if (lane == 0) s_warpcnt[warp] = __popc(m);
             __syncthreads();
@@ -948,76 +943,93 @@ k_rerank_rows(const RerankParams p)
                 }
                 s_g2[rank] = s_g[tid]; s_t2[rank] = mine;
             }
+            if (tid == 0) { s_next = 0; s_n32 = 0; }
             __syncthreads();
-            // ---- exact evaluation in ascending order; stop once the next screening value cannot win:
-            //      every candidate that could tie or beat the best exact value t* so far has
-            //      t~ <= t*/lam2 + eps1 ----
-            for (int j0 = 0; j0 < ns; j0 += kRrBatch) {
-                if (s_t2[j0] > s_bound) break;                          // block-uniform (smem, after a sync)
-                double s[kRrBatch][3];
-                const float *gp[kRrBatch];
-#pragma unroll
-                for (int b = 0; b < kRrBatch; ++b) {
-                    s[b][0] = s[b][1] = s[b][2] = 0.0;
-                    const int jj = j0 + b < ns ? j0 + b : j0;
-                    gp[b] = p.gal + static_cast<int64_t>(s_g2[jj]) * D;
+            // ---- (1) float32 evaluation, one candidate per warp, ascending screening value.  Every candidate that
+            //      could tie or beat the best exact value t* has t~ <= t*/lam2 + eps1, and t* <= best32*(1+kF32Rel):
+            //      once a warp's next candidate is above the shared bound, so are all later ones. ----
+            for (;;) {
+                int j = 0;
+                if (lane == 0) j = atomicAdd(&s_next, 1);
+                j = __shfl_sync(0xffffffffu, j, 0);
+                if (j >= ns) break;
+                if (s_t2[j] > __uint_as_float(*reinterpret_cast<volatile unsigned int *>(&s_bound))) break;
+                const int32_t g = s_g2[j];
+                const float4 *gp = reinterpret_cast<const float4 *>(p.gal + static_cast<int64_t>(g) * D);
+                float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+#pragma unroll 4
+                for (int k = lane; k < D4; k += 32) {
+                    const float4 b = gp[k];
+                    const float4 q0 = s_probe4[k], q1 = s_probe4[D4 + k], q2 = s_probe4[2 * D4 + k];
+                    float e;
+                    e = q0.x - b.x; x0 = fmaf(e, e, x0); e = q0.y - b.y; x0 = fmaf(e, e, x0);
+                    e = q0.z - b.z; x0 = fmaf(e, e, x0); e = q0.w - b.w; x0 = fmaf(e, e, x0);
+                    e = q1.x - b.x; x1 = fmaf(e, e, x1); e = q1.y - b.y; x1 = fmaf(e, e, x1);
+                    e = q1.z - b.z; x1 = fmaf(e, e, x1); e = q1.w - b.w; x1 = fmaf(e, e, x1);
+                    e = q2.x - b.x; x2 = fmaf(e, e, x2); e = q2.y - b.y; x2 = fmaf(e, e, x2);
+                    e = q2.z - b.z; x2 = fmaf(e, e, x2); e = q2.w - b.w; x2 = fmaf(e, e, x2);
                 }
 #pragma unroll
-                for (int i = 0; i < EPT / 4; ++i) {
-                    const int k = 4 * (tid + kRrThreads * i);
-                    if (k < D) {
-#pragma unroll
-                        for (int b = 0; b < kRrBatch; ++b) {
-                            const float4 bv = *reinterpret_cast<const float4 *>(gp[b] + k);
-                            const double bb[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const double e0 = a0[4 * i + e] - bb[e];
-                                const double e1 = a1[4 * i + e] - bb[e];
-                                const double e2 = a2[4 * i + e] - bb[e];
-                                s[b][0] += e0 * e0; s[b][1] += e1 * e1; s[b][2] += e2 * e2;
-                            }
-                        }
-                    }
+                for (int o = 16; o > 0; o >>= 1) {
+                    x0 += __shfl_xor_sync(0xffffffffu, x0, o);
+                    x1 += __shfl_xor_sync(0xffffffffu, x1, o);
+                    x2 += __shfl_xor_sync(0xffffffffu, x2, o);
                 }
-#pragma unroll
-                for (int b = 0; b < kRrBatch; ++b)
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        const double v = warp_sum(s[b][q]);
-                        if (lane == 0) s_part[warp][b * 3 + q] = v;
-                    }
-                __syncthreads();
-                if (tid == 0) {
-                    float bound = s_bound;
-#pragma unroll
-                    for (int b = 0; b < kRrBatch; ++b) {
-                        if (j0 + b >= ns) break;
-                        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-#pragma unroll
-                        for (int w = 0; w < kRrThreads / 32; ++w) {
-                            t0 += s_part[w][b * 3]; t1 += s_part[w][b * 3 + 1]; t2 += s_part[w][b * 3 + 2];
-                        }
-                        const float d0 = hl ? static_cast<float>(sqrt(t0)) : 0.f;
-                        const float d1 = static_cast<float>(sqrt(t1));
-                        const float d2 = hr ? static_cast<float>(sqrt(t2)) : 0.f;
-                        float acc = __fmul_rn(p.lam1, d0);
-                        acc = __fmaf_rn(p.lam2, d1, acc);
-                        acc = __fmaf_rn(p.lam1, d2, acc);
-                        const unsigned long long v = pack_score_idx(acc, static_cast<uint32_t>(p.offset + s_g2[j0 + b]));
-                        loc = v < loc ? v : loc;
-                        bound = fminf(bound, fmaf(acc * inv_lam2, 1.00002f, eps1));
-                        ++done;
-                    }
-                    s_bound = bound;
+                if (lane == 0) {
+                    const float d0 = hl ? sqrtf(x0) : 0.f;
+                    const float d1 = sqrtf(x1);
+                    const float d2 = hr ? sqrtf(x2) : 0.f;
+                    float acc = __fmul_rn(p.lam1, d0);
+                    acc = __fmaf_rn(p.lam2, d1, acc);
+                    acc = __fmaf_rn(p.lam1, d2, acc);
+                    const int i32 = atomicAdd(&s_n32, 1);
+                    s_g[i32] = g; s_t[i32] = acc;
+                    atomicMin(&s_best32, __float_as_uint(acc));
+                    atomicMin(&s_bound, __float_as_uint(fmaf(acc * (1.0f + kF32Rel) * inv_lam2, 1.00002f, eps1)));
                 }
-                __syncthreads();
             }
+            __syncthreads();
+            // ---- (2) exact evaluation of everything within the float32 error of the best float32 value ----
+            const int n32 = s_n32;
+            const float cut = __uint_as_float(s_best32) * (1.0f + 2.0f * kF32Rel);
+            for (int j = warp; j < n32; j += kRrThreads / 32) {
+                if (!(s_t[j] <= cut)) continue;                          // warp-uniform
+                const int32_t g = s_g[j];
+                const float4 *gp = reinterpret_cast<const float4 *>(p.gal + static_cast<int64_t>(g) * D);
+                double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+                for (int k = lane; k < D4; k += 32) {
+                    const float4 b = gp[k];
+                    const float4 q0 = s_probe4[k], q1 = s_probe4[D4 + k], q2 = s_probe4[2 * D4 + k];
+                    const double bb[4] = {b.x, b.y, b.z, b.w};
+                    const float qq0[4] = {q0.x, q0.y, q0.z, q0.w}, qq1[4] = {q1.x, q1.y, q1.z, q1.w},
+                                qq2[4] = {q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const double e0 = static_cast<double>(qq0[e]) - bb[e];
+                        const double e1 = static_cast<double>(qq1[e]) - bb[e];
+                        const double e2 = static_cast<double>(qq2[e]) - bb[e];
+                        y0 += e0 * e0; y1 += e1 * e1; y2 += e2 * e2;
+                    }
+                }
+                y0 = warp_sum(y0); y1 = warp_sum(y1); y2 = warp_sum(y2);
+                if (lane == 0) {
+                    const float d0 = hl ? static_cast<float>(sqrt(y0)) : 0.f;
+                    const float d1 = static_cast<float>(sqrt(y1));
+                    const float d2 = hr ? static_cast<float>(sqrt(y2)) : 0.f;
+                    float acc = __fmul_rn(p.lam1, d0);
+                    acc = __fmaf_rn(p.lam2, d1, acc);
+                    acc = __fmaf_rn(p.lam1, d2, acc);
+                    const unsigned long long v = pack_score_idx(acc, static_cast<uint32_t>(p.offset + g));
+                    loc = v < loc ? v : loc;
+                    ++done;
+                }
+            }
+            __syncthreads();
         }
-        if (tid == 0 && loc != ~0ull) atomicMin(p.best + row, loc);
-        __syncthreads();
+        if (lane == 0 && loc != ~0ull) atomicMin(p.best + row, loc);
+        __syncthreads();                                                 // s_probe4 is reused by the next row
     }
-    if (tid == 0) {
+    if (lane == 0) {
         if (appended) atomicAdd(&p.ctr->cand_count, appended);
         if (done) atomicAdd(&p.ctr->n_exact, done);
     }
@@ -1134,14 +1146,14 @@ static int launch_screen_np(const CUtensorMap &tmA, const CUtensorMap &tmB, cons
     return EOSVR_OK;
 }
 
-// pairs per cluster of the next screening launches: 2 when there are at least two probe tiles (the pairs of a
-// cluster share the gallery tile), else 1.  EOSVR_NP=1|2 overrides (experiments).
+// pairs per cluster of the next screening launches.  Two pairs sharing (multicasting) the gallery slab halve its
+// L2 reads but measured 3-6 % SLOWER on B200 (the kernel is not L2-bound), so the default is
+// one pair; EOSVR_NP=2 selects the 2-pair cluster for experiments when there are at least two probe tiles.
 static int choose_np(int64_t NT)
 {
     static int np_env = -1;
     if (np_env < 0) { const char *e = getenv("EOSVR_NP"); np_env = e ? atoi(e) : 0; }
-    if (np_env == 1) return 1;
-    return NT >= 2 ? 2 : 1;
+    return (np_env == 2 && NT >= 2) ? 2 : 1;
 }
 
 static int launch_screen(const eosvr_gallery *g, eosvr_workspace *ws, const MatchPlan &pl, int np, bool seed,
@@ -1261,10 +1273,16 @@ int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probe
         if (rc) return rc;
         ws->last_tiles = pl.NT * GT;
 
-        const unsigned rr_grid = static_cast<unsigned>(P < static_cast<int64_t>(g_num_sms) * 16 ? P : g_num_sms * 16);
-        if ((g->D & 3) == 0 && g->D <= 512) k_rerank_rows<4><<<rr_grid, kRrThreads, 0, st>>>(rp);
-        else if ((g->D & 3) == 0 && g->D <= 1024) k_rerank_rows<8><<<rr_grid, kRrThreads, 0, st>>>(rp);
-        else if ((g->D & 3) == 0 && g->D <= 2048) k_rerank_rows<16><<<rr_grid, kRrThreads, 0, st>>>(rp);
+        const unsigned rr_grid = static_cast<unsigned>(P < static_cast<int64_t>(g_num_sms) * 32 ? P : g_num_sms * 32);
+        const size_t rr_smem = static_cast<size_t>(3) * g->D * sizeof(float);
+        if ((g->D & 3) == 0 && rr_smem <= 96 * 1024) {
+            static bool rr_attr = false;
+            if (!rr_attr) {
+                EOSVR_CUDA(cudaFuncSetAttribute(k_rerank_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                rr_attr = true;
+            }
+            k_rerank_rows<<<rr_grid, kRrThreads, rr_smem, st>>>(rp);
+        }
         else k_rerank<<<g_num_sms * 8, 256, 0, st>>>(rp);
         EOSVR_CUDA(cudaGetLastError());
         k_rerank_ovf<<<g_num_sms * 4, 256, 0, st>>>(rp);
