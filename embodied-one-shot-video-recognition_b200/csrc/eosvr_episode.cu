@@ -321,6 +321,178 @@ k_episode_score(const float *__restrict__ probes, const float *__restrict__ wrow
     if (tid == 0 && nproto_out) nproto_out[e] = np;
 }
 
+// -------------------------------------------------------------------------------------------
+// Split variant of the fused kernel for D % 4 == 0 and S in {2,4,8}: grid (E, nsplit), every block
+// folds one slice of the feature axis with float4 loads and writes its float64 partial sums of squared
+// query-prototype differences; k_episode_final adds the slices in a fixed order (deterministic) and
+// finishes sqrt / softmax / arg-max.  Same float32 evaluation order per feature as k_episode_score, so
+// prototypes are bit-equal; only the float64 summation order over features differs (as it already does
+// from scipy's).  One block per episode left most of the 148 SMs idle at E = 256.
+// -------------------------------------------------------------------------------------------
+constexpr int kEpThreads = 128;
+
+template <int S_T>
+__global__ void __launch_bounds__(kEpThreads)
+k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wrows, const float *__restrict__ gal,
+                  int64_t G, int64_t goff, const int64_t *__restrict__ idx, const float *__restrict__ sup_y,
+                  const float *__restrict__ query, int n, int Q, int D, int orig_mode, int max_proto, int nsplit,
+                  double *__restrict__ partial, int32_t *__restrict__ np_out)
+{
+    __shared__ int16_t s_cls[kMaxClips];
+    __shared__ int16_t s_order[kMaxClips];
+    __shared__ int16_t s_start[kMaxProto + 1];
+    __shared__ float s_pid[kMaxProto];
+    __shared__ int s_np;
+    __shared__ double s_red[kEpThreads / 32][kMaxQ];
+
+    const int64_t e = blockIdx.x;
+    const int sp = blockIdx.y;
+    const int D4 = D >> 2;
+    const float4 *Pe = reinterpret_cast<const float4 *>(probes + e * n * S_T * D);
+    const float *Y = sup_y + e * n;
+    const float4 *Qp = reinterpret_cast<const float4 *>(query + e * Q * D);
+    const float4 *gal4 = reinterpret_cast<const float4 *>(gal);
+    const float4 *wr4 = reinterpret_cast<const float4 *>(wrows);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        int np = 0;
+        for (int i = 0; i < n; ++i) {                     // classifier.py:21-29 (every row of clip i carries Y[i])
+            const float y = Y[i];
+            int c = -1;
+            for (int j = 0; j < np; ++j) if (s_pid[j] == y) { c = j; break; }
+            if (c < 0) { if (np < max_proto) { c = np; s_pid[np++] = y; } else c = -1; }
+            s_cls[i] = static_cast<int16_t>(c);
+        }
+        int pos = 0;
+        for (int c = 0; c < np; ++c) {
+            s_start[c] = static_cast<int16_t>(pos);
+            for (int i = 0; i < n; ++i) if (s_cls[i] == c) s_order[pos++] = static_cast<int16_t>(i);
+        }
+        s_start[np] = static_cast<int16_t>(pos);
+        s_np = np;
+        if (sp == 0) np_out[e] = np;
+    }
+    __syncthreads();
+    const int np = s_np;
+    const float fS = static_cast<float>(S_T);
+    const int per = (D4 + nsplit - 1) / nsplit;
+    const int k0 = sp * per, k1 = min(D4, k0 + per);
+
+    for (int c = 0; c < np; ++c) {
+        double part[kMaxQ];
+#pragma unroll
+        for (int q = 0; q < kMaxQ; ++q) part[q] = 0.0;
+        const int i0 = s_start[c], i1 = s_start[c + 1];
+        for (int k = k0 + tid; k < k1; k += kEpThreads) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            int cnt = 0;
+            for (int ii = i0; ii < i1; ++ii) {
+                const int i = s_order[ii];
+                const float4 *pc = Pe + static_cast<int64_t>(i) * S_T * D4 + k;
+                const int64_t wbase = (e * n + i) * S_T;
+                float pr[S_T][4], w[S_T][4];
+#pragma unroll
+                for (int s = 0; s < S_T; ++s) {
+                    const float4 v = pc[static_cast<int64_t>(s) * D4];
+                    pr[s][0] = v.x; pr[s][1] = v.y; pr[s][2] = v.z; pr[s][3] = v.w;
+                }
+#pragma unroll
+                for (int s = 0; s < S_T; ++s) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (wrows) v = wr4[(wbase + s) * D4 + k];
+                    else {
+                        const int64_t g = idx[wbase + s] - goff;
+                        if (g >= 0 && g < G) v = gal4[g * D4 + k];
+                    }
+                    w[s][0] = v.x; w[s][1] = v.y; w[s][2] = v.z; w[s][3] = v.w;
+                }
+                float o[4];
+                if (orig_mode == EOSVR_ORIG_REF_QUIRK) {                       // network_test.py:229
+                    const float4 v = Pe[static_cast<int64_t>(i) * D4 + k];
+                    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        float a = pr[0][x];
+#pragma unroll
+                        for (int s = 1; s < S_T; ++s) a = __fadd_rn(a, pr[s][x]);
+                        o[x] = __fdiv_rn(a, fS);
+                    }
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x) acc[x] = cnt ? __fadd_rn(acc[x], o[x]) : o[x];
+                ++cnt;
+#pragma unroll
+                for (int s = 0; s < S_T; ++s) {
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        float a = (s == 0) ? w[0][x] : pr[0][x];
+#pragma unroll
+                        for (int s2 = 1; s2 < S_T; ++s2) a = __fadd_rn(a, (s2 == s) ? w[s2][x] : pr[s2][x]);
+                        acc[x] = __fadd_rn(acc[x], __fdiv_rn(a, fS));
+                    }
+                    ++cnt;
+                }
+            }
+            const float fc = static_cast<float>(cnt);
+#pragma unroll
+            for (int q = 0; q < kMaxQ; ++q) {
+                if (q < Q) {
+                    const float4 qv = Qp[static_cast<int64_t>(q) * D4 + k];
+                    const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const double df = static_cast<double>(qq[x]) - static_cast<double>(__fdiv_rn(acc[x], fc));
+                        part[q] += df * df;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kMaxQ; ++q) {
+            double v = part[q];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_red[warp][q] = v;
+        }
+        __syncthreads();
+        if (tid < Q) {
+            double v = 0.0;
+            for (int w = 0; w < kEpThreads / 32; ++w) v += s_red[w][tid];
+            partial[((e * nsplit + sp) * max_proto + c) * kMaxQ + tid] = v;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_episode_final(const double *__restrict__ partial, const int32_t *__restrict__ np_in, int Q,
+                                int max_proto, int nsplit, float *__restrict__ dist, float *__restrict__ prob,
+                                int64_t *__restrict__ pred, int32_t *__restrict__ nproto_out)
+{
+    const int64_t e = blockIdx.x;
+    const int q = threadIdx.x;
+    const int np = np_in[e];
+    if (q == 0 && nproto_out) nproto_out[e] = np;
+    if (q >= Q) return;
+    float d[kMaxProto];
+    float mx = 0.f; int best = 0;
+    for (int c = 0; c < np; ++c) {
+        double v = 0.0;
+        for (int sp = 0; sp < nsplit; ++sp) v += partial[((e * nsplit + sp) * max_proto + c) * kMaxQ + q];
+        d[c] = static_cast<float>(sqrt(v));                  // classifier.py:66 float32 cast
+        if (c == 0) mx = -d[0];
+        else { if (-d[c] > mx) mx = -d[c]; if (d[c] < d[best]) best = c; }
+    }
+    float sum = 0.f;
+    for (int c = 0; c < np; ++c) sum += expf(-d[c] - mx);
+    for (int c = 0; c < max_proto; ++c) {
+        const int64_t o = (e * Q + q) * max_proto + c;
+        if (dist) dist[o] = c < np ? d[c] : INFINITY;
+        if (prob) prob[o] = c < np ? expf(-d[c] - mx) / sum : 0.f;
+    }
+    if (pred) pred[e * Q + q] = best;
+}
+
 int launch_episode_score(const float *probes, const float *wrows, const float *gal, int64_t G, int64_t goff,
                          const int64_t *idx, const float *sup_y, const float *query, int64_t E, int32_t n,
                          int32_t S, int32_t Q, int32_t D, int32_t orig_mode, int32_t max_proto, float *dist,
@@ -330,6 +502,30 @@ int launch_episode_score(const float *probes, const float *wrows, const float *g
     if (n < 1 || n > kMaxClips || S < 1 || Q < 1 || Q > kMaxQ || max_proto < 1 || max_proto > kMaxProto) {
         set_error("episode_score: need 1<=n<=%d, S>=1, 1<=Q<=%d, 1<=max_proto<=%d", kMaxClips, kMaxQ, kMaxProto);
         return EOSVR_EINVAL;
+    }
+    if ((D & 3) == 0 && (S == 2 || S == 4 || S == 8) && D >= 256) {
+        int nsplit = D / 512;                 // >= 128 float4 columns per block
+        if (nsplit < 1) nsplit = 1;
+        if (nsplit > 8) nsplit = 8;
+        double *partial = nullptr;
+        const size_t pbytes = static_cast<size_t>(E) * nsplit * max_proto * kMaxQ * sizeof(double);
+        const size_t nbytes = (static_cast<size_t>(E) * sizeof(int32_t) + 255) / 256 * 256;
+        char *scratch = nullptr;
+        EOSVR_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&scratch), nbytes + pbytes, st));   // stream-ordered, re-entrant
+        int32_t *np_buf = reinterpret_cast<int32_t *>(scratch);
+        partial = reinterpret_cast<double *>(scratch + nbytes);
+        dim3 pgrid(static_cast<unsigned>(E), static_cast<unsigned>(nsplit));
+#define EOSVR_EPP_LAUNCH(ST)                                                                                      \
+        k_episode_partial<ST><<<pgrid, kEpThreads, 0, st>>>(probes, wrows, gal, G, goff, idx, sup_y, query, n, Q, D,  \
+                                                           orig_mode, max_proto, nsplit, partial, np_buf)
+        if (S == 2) EOSVR_EPP_LAUNCH(2); else if (S == 4) EOSVR_EPP_LAUNCH(4); else EOSVR_EPP_LAUNCH(8);
+#undef EOSVR_EPP_LAUNCH
+        EOSVR_CUDA(cudaGetLastError());
+        k_episode_final<<<static_cast<unsigned>(E), 32, 0, st>>>(partial, np_buf, Q, max_proto, nsplit, dist, prob, pred, nproto);
+        EOSVR_CUDA(cudaGetLastError());
+        EOSVR_CUDA(cudaFreeAsync(scratch, st));
+        EOSVR_COUNT_LAUNCH(2);
+        return EOSVR_OK;
     }
     const unsigned grid = static_cast<unsigned>(E);
 #define EOSVR_EP_LAUNCH(ST)                                                                                    \
