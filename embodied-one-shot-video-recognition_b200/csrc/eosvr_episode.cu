@@ -10,9 +10,35 @@
 // ("Bit-level evaluation orders").
 #include <math.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "eosvr_internal.h"
 
 namespace eosvr {
+
+// Grow-only scratch per (device, stream): calls on one stream are ordered, calls on different streams get
+// different buffers, so the library stays re-entrant without a workspace argument and without stream-ordered
+// allocations on the hot path (cudaMallocAsync / cudaFreeAsync cost milliseconds per call when other streams
+// are busy).  Freed at process exit.
+static void *stream_scratch(cudaStream_t st, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, std::pair<void *, size_t>> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    auto &slot = cache[std::make_pair(dev, st)];
+    if (slot.second < bytes) {
+        if (slot.first) cudaFree(slot.first);            // synchronises; only when the scratch grows
+        slot.first = nullptr; slot.second = 0;
+        const size_t want = bytes + bytes / 2;
+        if (cudaMalloc(&slot.first, want) != cudaSuccess) { cudaGetLastError(); slot.first = nullptr; return nullptr; }
+        slot.second = want;
+    }
+    return slot.first;
+}
 
 // grid: (E*n, 1+S); block: 128 threads striding D.
 // out[e, i*(1+S) + j, :]:  j = 0 "original" row, j = 1+s the clip with segment s replaced.
@@ -510,8 +536,8 @@ int launch_episode_score(const float *probes, const float *wrows, const float *g
         double *partial = nullptr;
         const size_t pbytes = static_cast<size_t>(E) * nsplit * max_proto * kMaxQ * sizeof(double);
         const size_t nbytes = (static_cast<size_t>(E) * sizeof(int32_t) + 255) / 256 * 256;
-        char *scratch = nullptr;
-        EOSVR_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&scratch), nbytes + pbytes, st));   // stream-ordered, re-entrant
+        char *scratch = static_cast<char *>(stream_scratch(st, nbytes + pbytes));
+        if (!scratch) { set_error("episode_score: scratch allocation of %zu bytes failed", nbytes + pbytes); return EOSVR_ENOMEM; }
         int32_t *np_buf = reinterpret_cast<int32_t *>(scratch);
         partial = reinterpret_cast<double *>(scratch + nbytes);
         dim3 pgrid(static_cast<unsigned>(E), static_cast<unsigned>(nsplit));
@@ -523,7 +549,6 @@ int launch_episode_score(const float *probes, const float *wrows, const float *g
         EOSVR_CUDA(cudaGetLastError());
         k_episode_final<<<static_cast<unsigned>(E), 32, 0, st>>>(partial, np_buf, Q, max_proto, nsplit, dist, prob, pred, nproto);
         EOSVR_CUDA(cudaGetLastError());
-        EOSVR_CUDA(cudaFreeAsync(scratch, st));
         EOSVR_COUNT_LAUNCH(2);
         return EOSVR_OK;
     }

@@ -306,6 +306,24 @@ def test_kshot5_and_multi_query():
         assert np.array_equal(r["pred"][e].cpu().numpy(), o["pred"])
 
 
+def test_run_host_pipelined_equals_device_run():
+    """The host-buffer entry point (chunked H2D copies overlapped with matching) returns exactly what one
+    device-resident call returns, for uneven chunking, a single chunk and repeated calls on reused buffers."""
+    E, n_way, S, D, G = 11, 5, 4, 256, 2000
+    gal = synth.gallery(91, G, D, centroid_seed=41)
+    cache = ev.GalleryFeatureCache(_cuda(gal))
+    pipe = ev.EpisodePipeline(cache, n_way, 1, S, E)
+    for seed, chunks in ((41, 3), (42, 1), (43, 8), (44, 64)):
+        ep = synth.episode_batch(seed, E, n_way, 1, S, D)
+        r = pipe.run(_cuda(ep["probe"]), _cuda(ep["support_y"]), _cuda(ep["query"]))
+        host = [torch.from_numpy(ep[k]).pin_memory() for k in ("probe", "support_y", "query")]
+        h = pipe.run_host(*host, chunks=chunks)
+        assert not h["pred"].is_cuda and not h["idx"].is_cuda
+        assert torch.equal(h["pred"], r["pred"].cpu()) and torch.equal(h["idx"], r["idx"].cpu())
+        h2 = pipe.run_host(*[t.clone() for t in host], chunks=chunks)          # pageable host memory works too
+        assert torch.equal(h2["pred"], r["pred"].cpu()) and torch.equal(h2["idx"], r["idx"].cpu())
+
+
 def test_segment_features():
     f = synth.frame_features(5, 64, 96)
     a = ev.segment_features(_cuda(f), 2, True).cpu().numpy()
