@@ -5,7 +5,7 @@ episode scoring behind a C ABI (include/eosvr.h), with a PyTorch/ctypes host lay
 Import as ``eosvr_b200``.
 """
 from eosvr_b200._lib import (EosvrError, lib, lib_path, load_library, ORIG_CLIP_MEAN,  # noqa: F401
-                             ORIG_REF_QUIRK, SCREEN_BF16, SCREEN_F16)
+                             ORIG_REF_QUIRK, SCREEN_BF16, SCREEN_F16, METRIC_COSINE, METRIC_EUCLID_TEMPORAL)
 from eosvr_b200.matcher import (EpisodePipeline, GalleryFeatureCache, MatchWorkspace,  # noqa: F401
                                 episode_score, gather_winner_rows, match_segments, match_segments_exact, merge_top1, proto_score,
                                 segment_features, splice_augmented, temporal_smooth, cosine_predict)
@@ -22,4 +22,4 @@ def dropin_path() -> str:
 __all__ = ["dropin_path", "EosvrError", "lib", "lib_path", "load_library", "GalleryFeatureCache", "MatchWorkspace",
            "EpisodePipeline", "episode_score", "gather_winner_rows", "match_segments", "match_segments_exact", "merge_top1", "proto_score",
            "segment_features", "splice_augmented", "temporal_smooth", "cosine_predict", "ORIG_REF_QUIRK", "ORIG_CLIP_MEAN", "SCREEN_F16",
-           "SCREEN_BF16"]
+           "SCREEN_BF16", "METRIC_COSINE", "METRIC_EUCLID_TEMPORAL"]

@@ -10,7 +10,7 @@ import os
 
 ORIG_REF_QUIRK, ORIG_CLIP_MEAN = 0, 1
 SCREEN_F16, SCREEN_BF16 = 0, 1
-METRIC_EUCLID_TEMPORAL = 0
+METRIC_EUCLID_TEMPORAL, METRIC_COSINE = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
 
 #include "eosvr_internal.h"
@@ -57,6 +58,48 @@ int encode_tmap_2d(CUtensorMap *m, const void *base, int fmt, uint64_t rows, uin
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+static void free_screen_copy(eosvr_screen_copy *c)
+{
+    if (!c) return;
+    if (c->h16) cudaFree(c->h16);
+    if (c->gnorm) cudaFree(c->gnorm);
+    if (c->scalars) cudaFree(c->scalars);
+    if (c->ready) cudaEventDestroy(c->ready);
+    delete c;
+}
+
+// Build (once, under the handle's mutex) the L2-normalised screening copy the cosine metric reads.  The build
+// kernel runs on `st`; later calls on other streams wait for c->ready.
+int build_cosine_copy(eosvr_gallery *g, cudaStream_t st)
+{
+    std::lock_guard<std::mutex> lock(*static_cast<std::mutex *>(g->cos_mutex));
+    if (g->cos) return EOSVR_OK;
+    eosvr_screen_copy *c = new (std::nothrow) eosvr_screen_copy();
+    if (!c) { set_error("out of host memory"); return EOSVR_ENOMEM; }
+    memset(c, 0, sizeof(*c));
+    const int64_t Gpad = (g->G + kPairM - 1) / kPairM * kPairM;
+    if (cudaMalloc(&c->h16, static_cast<size_t>(Gpad) * g->Dp * 2) != cudaSuccess ||
+        cudaMalloc(&c->gnorm, static_cast<size_t>(Gpad) * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&c->scalars, 4 * sizeof(float)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cosine screening copy: device allocation failed (%lld rows x %d)", (long long)Gpad, g->Dp);
+        free_screen_copy(c);
+        return EOSVR_ENOMEM;
+    }
+    int rc = launch_gallery_prep_cos(g, c, st);
+    const uint64_t rows = static_cast<uint64_t>(Gpad), cols = static_cast<uint64_t>(g->Dp);
+    const uint64_t srows = static_cast<uint64_t>(g->seed_tiles) * kPairM, sstr = static_cast<uint64_t>(g->seed_stride);
+    if (!rc) rc = encode_tmap_2d(&c->tmapA, c->h16, g->screen_fmt, rows, cols, kBM, kBK, 1);
+    if (!rc) rc = encode_tmap_2d(&c->tmapAH, c->h16, g->screen_fmt, rows, cols, kBM / 2, kBK, 1);
+    if (!rc) rc = encode_tmap_2d(&c->tmapSeed, c->h16, g->screen_fmt, srows, cols, kBM, kBK, sstr);
+    if (!rc) rc = encode_tmap_2d(&c->tmapSeedH, c->h16, g->screen_fmt, srows, cols, kBM / 2, kBK, sstr);
+    if (!rc && cudaEventRecord(c->ready, st) != cudaSuccess) { set_error("cudaEventRecord failed"); rc = EOSVR_ECUDA; }
+    if (rc) { free_screen_copy(c); return rc; }
+    g->cos = c;
+    return EOSVR_OK;
+}
+
 }  // namespace eosvr
 
 using namespace eosvr;
@@ -100,6 +143,8 @@ int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtyp
     g->G = G; g->D = D; g->Dp = (D + kBK - 1) / kBK * kBK;
     g->offset = global_offset; g->screen_fmt = screen_fmt;
     cudaGetDevice(&g->device);
+    g->cos_mutex = new (std::nothrow) std::mutex();
+    if (!g->cos_mutex) { delete g; set_error("out of host memory"); return EOSVR_ENOMEM; }
     const int64_t Gpad = (G + kPairM - 1) / kPairM * kPairM;
     if (cudaMalloc(&g->h16, static_cast<size_t>(Gpad) * g->Dp * 2) != cudaSuccess ||
         cudaMalloc(&g->gnorm, static_cast<size_t>(Gpad) * sizeof(float)) != cudaSuccess ||
@@ -136,6 +181,8 @@ int eosvr_gallery_destroy(eosvr_gallery_t *g)
     if (g->h16) cudaFree(g->h16);
     if (g->gnorm) cudaFree(g->gnorm);
     if (g->scalars) cudaFree(g->scalars);
+    free_screen_copy(g->cos);
+    delete static_cast<std::mutex *>(g->cos_mutex);
     delete g;
     return EOSVR_OK;
 }
@@ -265,8 +312,8 @@ static int check_match_args(const eosvr_gallery_t *g, eosvr_workspace_t *ws, con
     if (P > ws->maxP) { set_error("match: P=%lld exceeds workspace max_probe_rows=%lld", (long long)P, (long long)ws->maxP); return EOSVR_EINVAL; }
     if (ws->D != g->D) { set_error("match: workspace D=%d != gallery D=%d", ws->D, g->D); return EOSVR_EINVAL; }
     if (rpe < 1) { set_error("match: rows_per_episode must be >= 1"); return EOSVR_EINVAL; }
-    if (metric != EOSVR_METRIC_EUCLID_TEMPORAL) { set_error("match: unsupported metric %d", metric); return EOSVR_EINVAL; }
-    if (!(lam2 > 0.f) || !(lam1 >= 0.f)) { set_error("match: need lam2 > 0 and lam1 >= 0"); return EOSVR_EINVAL; }
+    if (metric != EOSVR_METRIC_EUCLID_TEMPORAL && metric != EOSVR_METRIC_COSINE) { set_error("match: unsupported metric %d", metric); return EOSVR_EINVAL; }
+    if (metric == EOSVR_METRIC_EUCLID_TEMPORAL && (!(lam2 > 0.f) || !(lam1 >= 0.f))) { set_error("match: need lam2 > 0 and lam1 >= 0"); return EOSVR_EINVAL; }
     if (P > 0 && !d_out_packed) { set_error("match: d_out_packed is required"); return EOSVR_EINVAL; }
     return EOSVR_OK;
 }
@@ -277,8 +324,9 @@ int eosvr_match(const eosvr_gallery_t *g, eosvr_workspace_t *ws, const float *d_
 {
     int rc = check_match_args(g, ws, d_probes, P, rows_per_episode, metric, lam1, lam2, d_out_packed);
     if (rc) return rc;
-    return launch_match(g, ws, d_probes, P, rows_per_episode, lam1, lam2, false, d_out_packed, d_out_score,
-                        d_out_idx, static_cast<cudaStream_t>(stream));
+    // (the handle is logically const: the cosine screening copy is a lazily built cache behind a mutex)
+    return launch_match(const_cast<eosvr_gallery_t *>(g), ws, d_probes, P, rows_per_episode, metric, lam1, lam2, false,
+                        d_out_packed, d_out_score, d_out_idx, static_cast<cudaStream_t>(stream));
 }
 
 int eosvr_match_exact(const eosvr_gallery_t *g, eosvr_workspace_t *ws, const float *d_probes, int64_t P,
@@ -287,8 +335,8 @@ int eosvr_match_exact(const eosvr_gallery_t *g, eosvr_workspace_t *ws, const flo
 {
     int rc = check_match_args(g, ws, d_probes, P, rows_per_episode, metric, lam1, lam2, d_out_packed);
     if (rc) return rc;
-    return launch_match(g, ws, d_probes, P, rows_per_episode, lam1, lam2, true, d_out_packed, d_out_score,
-                        d_out_idx, static_cast<cudaStream_t>(stream));
+    return launch_match(const_cast<eosvr_gallery_t *>(g), ws, d_probes, P, rows_per_episode, metric, lam1, lam2, true,
+                        d_out_packed, d_out_score, d_out_idx, static_cast<cudaStream_t>(stream));
 }
 
 int eosvr_match_stats(eosvr_workspace_t *ws, void *stream, int64_t out[8])

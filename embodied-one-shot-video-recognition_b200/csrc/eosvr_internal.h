@@ -72,6 +72,15 @@ struct Counters {
 
 }  // namespace eosvr
 
+// 16-bit screening copy of the gallery + side arrays + tensor maps (one per metric)
+struct eosvr_screen_copy {
+    void *h16;               // [Gpad, Dp] fp16/bf16
+    float *gnorm;            // [Gpad] squared norm of the screened row (kPadNorm beyond G)
+    float *scalars;          // [4] error-bound scalars
+    CUtensorMap tmapA, tmapSeed, tmapAH, tmapSeedH;
+    cudaEvent_t ready;       // recorded after the build kernel (lazily built copies)
+};
+
 struct eosvr_gallery {
     const float *feats;      // [G,D] float32, caller-owned
     int64_t G;
@@ -87,6 +96,8 @@ struct eosvr_gallery {
     float *scalars;          // [4]: max ||b||^2, max ||b_lo||^2, max ||b_hi||^2 (float bits, >= 0)
     CUtensorMap tmapA;
     int device;
+    eosvr_screen_copy *cos;  // L2-normalised rows for the cosine metric; built by the first cosine match
+    void *cos_mutex;         // std::mutex guarding the lazy build
 };
 
 struct eosvr_workspace {
@@ -134,8 +145,10 @@ struct MatchPlan {
 MatchPlan make_plan(int64_t P, int32_t rpe);
 
 int launch_gallery_prep(eosvr_gallery *g, cudaStream_t st);
-int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int64_t P,
-                 int32_t rpe, float lam1, float lam2, bool exact_only, uint64_t *out_packed,
+int build_cosine_copy(eosvr_gallery *g, cudaStream_t st);      // eosvr_api.cu
+int launch_gallery_prep_cos(const eosvr_gallery *g, eosvr_screen_copy *c, cudaStream_t st);
+int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int64_t P,
+                 int32_t rpe, int32_t metric, float lam1, float lam2, bool exact_only, uint64_t *out_packed,
                  float *out_score, int64_t *out_idx, cudaStream_t st);
 int launch_merge(const uint64_t *gathered, int32_t nshards, int64_t P, uint64_t *out_packed,
                  float *out_score, int64_t *out_idx, cudaStream_t st);

@@ -70,7 +70,10 @@ __device__ __forceinline__ void atomic_max_posf(float *addr, float v)
     atomicMax(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
 }
 
-template <typename T16>
+// NORM: screen the L2-normalised row (cosine metric).  The bound scalars are taken against the exactly
+// normalised row (float64), the stored copy is the 16-bit rounding of the float32 product x * (1/|x|); a zero
+// row stays zero and gets squared norm 1 so that |a' - 0|^2 = 2 - 2*0, consistent with cosine 0.
+template <typename T16, bool NORM>
 __global__ void k_gallery_prep(const float *__restrict__ feats, int64_t G, int64_t Gpad, int D, int Dp,
                                T16 *__restrict__ h16, float *__restrict__ gnorm, float *__restrict__ scalars)
 {
@@ -84,18 +87,27 @@ __global__ void k_gallery_prep(const float *__restrict__ feats, int64_t G, int64
         return;
     }
     const float *src = feats + row * D;
+    double rn = 1.0; float rnf = 1.f;
+    if (NORM) {
+        double q = 0.0;
+        for (int k = lane; k < D; k += 32) q += static_cast<double>(src[k]) * static_cast<double>(src[k]);
+        q = warp_sum(q);
+        rn = q > 0.0 ? 1.0 / sqrt(q) : 0.0;
+        rnf = static_cast<float>(rn);
+    }
     double s = 0.0, sh = 0.0, sl = 0.0;
     for (int k = lane; k < Dp; k += 32) {
         float x = k < D ? src[k] : 0.f;
-        T16 h = to16<T16>(x);
+        T16 h = to16<T16>(NORM ? __fmul_rn(x, rnf) : x);
         dst[k] = h;
-        double xd = x, hd = from16(h);
+        double xd = NORM ? static_cast<double>(x) * rn : static_cast<double>(x), hd = from16(h);
         s += xd * xd;
         sh += hd * hd;
         sl += (xd - hd) * (xd - hd);
     }
     s = warp_sum(s); sh = warp_sum(sh); sl = warp_sum(sl);
     if (lane == 0) {
+        if (NORM && rn == 0.0) s = 1.0;
         gnorm[row] = static_cast<float>(s);
         atomic_max_posf(scalars + 0, __double2float_ru(s));
         atomic_max_posf(scalars + 1, __double2float_ru(sl));
@@ -103,20 +115,31 @@ __global__ void k_gallery_prep(const float *__restrict__ feats, int64_t G, int64
     }
 }
 
-int launch_gallery_prep(eosvr_gallery *g, cudaStream_t st)
+template <bool NORM>
+static int launch_gallery_prep_t(const eosvr_gallery *g, void *h16, float *gnorm, float *scalars, cudaStream_t st)
 {
     const int64_t Gpad = (g->G + kPairM - 1) / kPairM * kPairM;
-    EOSVR_CUDA(cudaMemsetAsync(g->scalars, 0, 4 * sizeof(float), st));
+    EOSVR_CUDA(cudaMemsetAsync(scalars, 0, 4 * sizeof(float), st));
     const int threads = 256;
     const int64_t blocks = (Gpad * 32 + threads - 1) / threads;
     if (g->screen_fmt == EOSVR_SCREEN_F16)
-        k_gallery_prep<__half><<<static_cast<unsigned>(blocks), threads, 0, st>>>(
-            g->feats, g->G, Gpad, g->D, g->Dp, static_cast<__half *>(g->h16), g->gnorm, g->scalars);
+        k_gallery_prep<__half, NORM><<<static_cast<unsigned>(blocks), threads, 0, st>>>(
+            g->feats, g->G, Gpad, g->D, g->Dp, static_cast<__half *>(h16), gnorm, scalars);
     else
-        k_gallery_prep<__nv_bfloat16><<<static_cast<unsigned>(blocks), threads, 0, st>>>(
-            g->feats, g->G, Gpad, g->D, g->Dp, static_cast<__nv_bfloat16 *>(g->h16), g->gnorm, g->scalars);
+        k_gallery_prep<__nv_bfloat16, NORM><<<static_cast<unsigned>(blocks), threads, 0, st>>>(
+            g->feats, g->G, Gpad, g->D, g->Dp, static_cast<__nv_bfloat16 *>(h16), gnorm, scalars);
     EOSVR_CUDA(cudaGetLastError());
     return EOSVR_OK;
+}
+
+int launch_gallery_prep(eosvr_gallery *g, cudaStream_t st)
+{
+    return launch_gallery_prep_t<false>(g, g->h16, g->gnorm, g->scalars, st);
+}
+
+int launch_gallery_prep_cos(const eosvr_gallery *g, eosvr_screen_copy *c, cudaStream_t st)
+{
+    return launch_gallery_prep_t<true>(g, c->h16, c->gnorm, c->scalars, st);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -163,7 +186,7 @@ __device__ __forceinline__ int64_t plan_row_of(const PlanDev &pl, int64_t col, b
 
 // One warp per plan column: convert the probe row to the 16-bit screening format, compute the
 // squared norm and the per-column error bound E2 (see DESIGN.md "Error bound").
-template <typename T16>
+template <typename T16, bool NORM>
 __global__ void k_probe_prep(const float *__restrict__ probes, PlanDev pl, int D, int Dp,
                              const float *__restrict__ gscal, T16 *__restrict__ q16,
                              float *__restrict__ na, float *__restrict__ epsd, int32_t *__restrict__ rowmap,
@@ -181,17 +204,26 @@ __global__ void k_probe_prep(const float *__restrict__ probes, PlanDev pl, int D
         return;
     }
     const float *src = probes + p * D;
+    double rn = 1.0; float rnf = 1.f;
+    if (NORM) {                                          // cosine metric: screen the L2-normalised row
+        double q = 0.0;
+        for (int k = lane; k < D; k += 32) q += static_cast<double>(src[k]) * static_cast<double>(src[k]);
+        q = warp_sum(q);
+        rn = q > 0.0 ? 1.0 / sqrt(q) : 0.0;
+        rnf = static_cast<float>(rn);
+    }
     double s = 0.0, sh = 0.0, sl = 0.0;
     for (int k = lane; k < Dp; k += 32) {
         float x = k < D ? src[k] : 0.f;
-        T16 h = to16<T16>(x);
+        T16 h = to16<T16>(NORM ? __fmul_rn(x, rnf) : x);
         dst[k] = h;
-        double xd = x, hd = from16(h);
+        double xd = NORM ? static_cast<double>(x) * rn : static_cast<double>(x), hd = from16(h);
         s += xd * xd;
         sh += hd * hd;
         sl += (xd - hd) * (xd - hd);
     }
     s = warp_sum(s); sh = warp_sum(sh); sl = warp_sum(sl);
+    if (NORM && rn == 0.0) s = 1.0;                      // zero row: |0 - b'|^2 + ... = 2 - 2*0
     if (lane == 0) {
         const double B2 = gscal[0], Bl2 = gscal[1], Bh2 = gscal[2];
         const double ulp = 1.0 / 4194304.0;   // 2^-22
@@ -788,6 +820,7 @@ struct RerankParams {
     const float *gal;
     int64_t P, G, offset;
     int32_t D, rpe;
+    int32_t metric;          // EOSVR_METRIC_*; the cosine metric works in the score domain s = -cosine (a minimum)
     float lam1, lam2;
     const Cand *cand;
     const unsigned int *rowcnt;
@@ -803,6 +836,26 @@ struct RerankParams {
     int32_t planR, planBN, planHalo;
 };
 
+// Cosine metric, exactly: float64 dot / (|a| |b|) on the original rows (0 for a zero row), rounded to
+// float32; returned negated (score domain).  Warp-cooperative; all lanes return the value.
+__device__ __forceinline__ float exact_negcos(const float *__restrict__ a, const float *__restrict__ b, int D, int lane)
+{
+    double dot = 0.0, na = 0.0, nb = 0.0;
+    for (int k = lane; k < D; k += 32) {
+        const double x = a[k], y = b[k];
+        dot += x * y; na += x * x; nb += y * y;
+    }
+    dot = warp_sum(dot); na = warp_sum(na); nb = warp_sum(nb);
+    const double den = sqrt(na) * sqrt(nb);
+    return 0.f - (den > 0.0 ? static_cast<float>(dot / den) : 0.f);   // 0 - c: never -0 (packed order)
+}
+
+__device__ __forceinline__ float exact_score(const RerankParams &p, int64_t row, int64_t g, int lane)
+{
+    if (p.metric == EOSVR_METRIC_COSINE) return exact_negcos(p.probes + row * p.D, p.gal + g * p.D, p.D, lane);
+    return exact_t(p.probes, p.P, p.D, p.rpe, row, p.gal + g * p.D, p.lam1, p.lam2, lane);
+}
+
 // Spill-over candidates (row lists that filled up): one warp per entry.  Exits at once when empty.
 __global__ void k_rerank_ovf(const RerankParams p)
 {
@@ -815,8 +868,7 @@ __global__ void k_rerank_ovf(const RerankParams p)
     for (int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < n; w += nw) {
         const OvfCand c = p.ovf[w];
         if (c.tbits != kCandUnsafe && __uint_as_float(c.tbits) > __uint_as_float(p.gthr[c.p])) continue;
-        const float t = exact_t(p.probes, p.P, p.D, p.rpe, c.p, p.gal + static_cast<int64_t>(c.g) * p.D,
-                                p.lam1, p.lam2, lane);
+        const float t = exact_score(p, c.p, c.g, lane);
         if (lane == 0) { atomicMin(p.best + c.p, pack_score_idx(t, static_cast<uint32_t>(p.offset + c.g))); ++done; }
     }
     if (lane == 0 && done) atomicAdd(&p.ctr->n_exact, done);
@@ -848,8 +900,7 @@ __global__ void k_rerank(const RerankParams p)
                 m &= m - 1;
                 const int32_t g = __shfl_sync(0xffffffffu, c.g, src);
                 const uint32_t tb = __shfl_sync(0xffffffffu, c.tbits, src);
-                const float t = exact_t(p.probes, p.P, p.D, p.rpe, row, p.gal + static_cast<int64_t>(g) * p.D,
-                                        p.lam1, p.lam2, lane);
+                const float t = exact_score(p, row, g, lane);
                 const unsigned long long v = pack_score_idx(t, static_cast<uint32_t>(p.offset + g));
                 loc = v < loc ? v : loc;
                 ++done; uns += (tb == kCandUnsafe);
@@ -878,10 +929,25 @@ __global__ void k_rerank(const RerankParams p)
 constexpr int kRrThreads = 128;
 constexpr float kF32Rel = 32.0f / 16777216.0f;   // 32 ulp: |t32 - t_reference| <= kF32Rel * t
 
+constexpr float kF32AbsCos = 64.0f / 16777216.0f;   // |cos32 - cos_reference| <= 64 ulp(1) absolute
+
+__device__ __forceinline__ unsigned int f2o(float x)    // order-preserving float -> unsigned
+{
+    const unsigned int b = __float_as_uint(x);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float o2f(unsigned int b)
+{
+    return __uint_as_float((b & 0x80000000u) ? (b & 0x7FFFFFFFu) : ~b);
+}
+
+// COS = cosine metric: one probe row is staged, the score is s = -cosine (so both metrics minimise), the
+// screening value of a candidate is ~ sqrt(2 + 2 s) and the float32 error is absolute (kF32AbsCos).
+template <bool COS>
 __global__ void __launch_bounds__(kRrThreads)
 k_rerank_rows(const RerankParams p)
 {
-    extern __shared__ float4 s_probe4[];          // [3][D/4]: rows p-1, p, p+1
+    extern __shared__ float4 s_probe4[];          // [3][D/4]: rows p-1, p, p+1  (COS: [D/4], row p)
     __shared__ int32_t s_g[kRrThreads], s_g2[kRrThreads];
     __shared__ float s_t[kRrThreads], s_t2[kRrThreads];
     __shared__ int s_warpcnt[kRrThreads / 32];
@@ -903,14 +969,15 @@ k_rerank_rows(const RerankParams p)
         const float4 *a0p = hl ? a1p - D4 : a1p;
         const float4 *a2p = hr ? a1p + D4 : a1p;
         for (int k = tid; k < D4; k += kRrThreads) {
-            s_probe4[k] = a0p[k]; s_probe4[D4 + k] = a1p[k]; s_probe4[2 * D4 + k] = a2p[k];
+            if (COS) s_probe4[k] = a1p[k];
+            else { s_probe4[k] = a0p[k]; s_probe4[D4 + k] = a1p[k]; s_probe4[2 * D4 + k] = a2p[k]; }
         }
         const float thr = __uint_as_float(p.gthr[row]);
         // one-sided error bound of this row's screening values (half of the two-sided threshold margin)
         const float eps1 = 0.5f * p.margin[(row / p.planR) * p.planBN + p.planHalo + (row % p.planR)];
         const Cand *list = p.cand + row * p.cand_cap;
         unsigned long long loc = ~0ull;
-        if (tid == 0) { s_bound = __float_as_uint(thr); s_best32 = 0x7f800000u; }
+        if (tid == 0) { s_bound = __float_as_uint(thr); s_best32 = f2o(INFINITY); }
         __syncthreads();
 
         for (int b0 = 0; b0 < n; b0 += kRrThreads) {
@@ -957,17 +1024,28 @@ k_rerank_rows(const RerankParams p)
                 const int32_t g = s_g2[j];
                 const float4 *gp = reinterpret_cast<const float4 *>(p.gal + static_cast<int64_t>(g) * D);
                 float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+                if (COS) {
 #pragma unroll 4
-                for (int k = lane; k < D4; k += 32) {
-                    const float4 b = gp[k];
-                    const float4 q0 = s_probe4[k], q1 = s_probe4[D4 + k], q2 = s_probe4[2 * D4 + k];
-                    float e;
-                    e = q0.x - b.x; x0 = fmaf(e, e, x0); e = q0.y - b.y; x0 = fmaf(e, e, x0);
-                    e = q0.z - b.z; x0 = fmaf(e, e, x0); e = q0.w - b.w; x0 = fmaf(e, e, x0);
-                    e = q1.x - b.x; x1 = fmaf(e, e, x1); e = q1.y - b.y; x1 = fmaf(e, e, x1);
-                    e = q1.z - b.z; x1 = fmaf(e, e, x1); e = q1.w - b.w; x1 = fmaf(e, e, x1);
-                    e = q2.x - b.x; x2 = fmaf(e, e, x2); e = q2.y - b.y; x2 = fmaf(e, e, x2);
-                    e = q2.z - b.z; x2 = fmaf(e, e, x2); e = q2.w - b.w; x2 = fmaf(e, e, x2);
+                    for (int k = lane; k < D4; k += 32) {
+                        const float4 b = gp[k];
+                        const float4 q = s_probe4[k];
+                        x0 = fmaf(q.x, b.x, x0); x0 = fmaf(q.y, b.y, x0); x0 = fmaf(q.z, b.z, x0); x0 = fmaf(q.w, b.w, x0);
+                        x1 = fmaf(b.x, b.x, x1); x1 = fmaf(b.y, b.y, x1); x1 = fmaf(b.z, b.z, x1); x1 = fmaf(b.w, b.w, x1);
+                        x2 = fmaf(q.x, q.x, x2); x2 = fmaf(q.y, q.y, x2); x2 = fmaf(q.z, q.z, x2); x2 = fmaf(q.w, q.w, x2);
+                    }
+                } else {
+#pragma unroll 4
+                    for (int k = lane; k < D4; k += 32) {
+                        const float4 b = gp[k];
+                        const float4 q0 = s_probe4[k], q1 = s_probe4[D4 + k], q2 = s_probe4[2 * D4 + k];
+                        float e;
+                        e = q0.x - b.x; x0 = fmaf(e, e, x0); e = q0.y - b.y; x0 = fmaf(e, e, x0);
+                        e = q0.z - b.z; x0 = fmaf(e, e, x0); e = q0.w - b.w; x0 = fmaf(e, e, x0);
+                        e = q1.x - b.x; x1 = fmaf(e, e, x1); e = q1.y - b.y; x1 = fmaf(e, e, x1);
+                        e = q1.z - b.z; x1 = fmaf(e, e, x1); e = q1.w - b.w; x1 = fmaf(e, e, x1);
+                        e = q2.x - b.x; x2 = fmaf(e, e, x2); e = q2.y - b.y; x2 = fmaf(e, e, x2);
+                        e = q2.z - b.z; x2 = fmaf(e, e, x2); e = q2.w - b.w; x2 = fmaf(e, e, x2);
+                    }
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -976,49 +1054,76 @@ k_rerank_rows(const RerankParams p)
                     x2 += __shfl_xor_sync(0xffffffffu, x2, o);
                 }
                 if (lane == 0) {
-                    const float d0 = hl ? sqrtf(x0) : 0.f;
-                    const float d1 = sqrtf(x1);
-                    const float d2 = hr ? sqrtf(x2) : 0.f;
-                    float acc = __fmul_rn(p.lam1, d0);
-                    acc = __fmaf_rn(p.lam2, d1, acc);
-                    acc = __fmaf_rn(p.lam1, d2, acc);
+                    float acc, nb;
+                    if (COS) {
+                        const float den = sqrtf(x2) * sqrtf(x1);
+                        acc = 0.f - (den > 0.f ? x0 / den : 0.f);
+                        // a candidate that ties or beats the best cosine c* >= -(acc + kF32AbsCos) has normalised
+                        // distance <= sqrt(2 - 2 c*)
+                        nb = fmaf(sqrtf(fmaxf(2.0f + 2.0f * (acc + 2.0f * kF32AbsCos), 0.f)), 1.000001f, eps1);
+                    } else {
+                        const float d0 = hl ? sqrtf(x0) : 0.f;
+                        const float d1 = sqrtf(x1);
+                        const float d2 = hr ? sqrtf(x2) : 0.f;
+                        acc = __fmul_rn(p.lam1, d0);
+                        acc = __fmaf_rn(p.lam2, d1, acc);
+                        acc = __fmaf_rn(p.lam1, d2, acc);
+                        nb = fmaf(acc * (1.0f + kF32Rel) * inv_lam2, 1.00002f, eps1);
+                    }
                     const int i32 = atomicAdd(&s_n32, 1);
                     s_g[i32] = g; s_t[i32] = acc;
-                    atomicMin(&s_best32, __float_as_uint(acc));
-                    atomicMin(&s_bound, __float_as_uint(fmaf(acc * (1.0f + kF32Rel) * inv_lam2, 1.00002f, eps1)));
+                    atomicMin(&s_best32, f2o(acc));
+                    atomicMin(&s_bound, __float_as_uint(nb));
                 }
             }
             __syncthreads();
             // ---- (2) exact evaluation of everything within the float32 error of the best float32 value ----
             const int n32 = s_n32;
-            const float cut = __uint_as_float(s_best32) * (1.0f + 2.0f * kF32Rel);
+            const float best32 = o2f(s_best32);
+            const float cut = COS ? best32 + 2.0f * kF32AbsCos : best32 * (1.0f + 2.0f * kF32Rel);
             for (int j = warp; j < n32; j += kRrThreads / 32) {
                 if (!(s_t[j] <= cut)) continue;                          // warp-uniform
                 const int32_t g = s_g[j];
                 const float4 *gp = reinterpret_cast<const float4 *>(p.gal + static_cast<int64_t>(g) * D);
                 double y0 = 0.0, y1 = 0.0, y2 = 0.0;
-                for (int k = lane; k < D4; k += 32) {
-                    const float4 b = gp[k];
-                    const float4 q0 = s_probe4[k], q1 = s_probe4[D4 + k], q2 = s_probe4[2 * D4 + k];
-                    const double bb[4] = {b.x, b.y, b.z, b.w};
-                    const float qq0[4] = {q0.x, q0.y, q0.z, q0.w}, qq1[4] = {q1.x, q1.y, q1.z, q1.w},
-                                qq2[4] = {q2.x, q2.y, q2.z, q2.w};
+                if (COS) {
+                    for (int k = lane; k < D4; k += 32) {
+                        const float4 b = gp[k];
+                        const float4 q = s_probe4[k];
+                        const double bb[4] = {b.x, b.y, b.z, b.w}, qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const double e0 = static_cast<double>(qq0[e]) - bb[e];
-                        const double e1 = static_cast<double>(qq1[e]) - bb[e];
-                        const double e2 = static_cast<double>(qq2[e]) - bb[e];
-                        y0 += e0 * e0; y1 += e1 * e1; y2 += e2 * e2;
+                        for (int e = 0; e < 4; ++e) { y0 += qq[e] * bb[e]; y1 += bb[e] * bb[e]; y2 += qq[e] * qq[e]; }
+                    }
+                } else {
+                    for (int k = lane; k < D4; k += 32) {
+                        const float4 b = gp[k];
+                        const float4 q0 = s_probe4[k], q1 = s_probe4[D4 + k], q2 = s_probe4[2 * D4 + k];
+                        const double bb[4] = {b.x, b.y, b.z, b.w};
+                        const float qq0[4] = {q0.x, q0.y, q0.z, q0.w}, qq1[4] = {q1.x, q1.y, q1.z, q1.w},
+                                    qq2[4] = {q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const double e0 = static_cast<double>(qq0[e]) - bb[e];
+                            const double e1 = static_cast<double>(qq1[e]) - bb[e];
+                            const double e2 = static_cast<double>(qq2[e]) - bb[e];
+                            y0 += e0 * e0; y1 += e1 * e1; y2 += e2 * e2;
+                        }
                     }
                 }
                 y0 = warp_sum(y0); y1 = warp_sum(y1); y2 = warp_sum(y2);
                 if (lane == 0) {
-                    const float d0 = hl ? static_cast<float>(sqrt(y0)) : 0.f;
-                    const float d1 = static_cast<float>(sqrt(y1));
-                    const float d2 = hr ? static_cast<float>(sqrt(y2)) : 0.f;
-                    float acc = __fmul_rn(p.lam1, d0);
-                    acc = __fmaf_rn(p.lam2, d1, acc);
-                    acc = __fmaf_rn(p.lam1, d2, acc);
+                    float acc;
+                    if (COS) {
+                        const double den = sqrt(y2) * sqrt(y1);
+                        acc = 0.f - (den > 0.0 ? static_cast<float>(y0 / den) : 0.f);
+                    } else {
+                        const float d0 = hl ? static_cast<float>(sqrt(y0)) : 0.f;
+                        const float d1 = static_cast<float>(sqrt(y1));
+                        const float d2 = hr ? static_cast<float>(sqrt(y2)) : 0.f;
+                        acc = __fmul_rn(p.lam1, d0);
+                        acc = __fmaf_rn(p.lam2, d1, acc);
+                        acc = __fmaf_rn(p.lam1, d2, acc);
+                    }
                     const unsigned long long v = pack_score_idx(acc, static_cast<uint32_t>(p.offset + g));
                     loc = v < loc ? v : loc;
                     ++done;
@@ -1066,7 +1171,7 @@ __global__ void k_exact_fallback(const RerankParams p)
         const int64_t g0 = (w % nstrips) * kStrip, g1 = min(g0 + kStrip, p.G);
         unsigned long long loc = ~0ull;
         for (int64_t g = g0; g < g1; ++g) {
-            const float t = exact_t(p.probes, p.P, p.D, p.rpe, row, p.gal + g * p.D, p.lam1, p.lam2, lane);
+            const float t = exact_score(p, row, g, lane);
             const unsigned long long v = pack_score_idx(t, static_cast<uint32_t>(p.offset + g));
             loc = v < loc ? v : loc;
         }
@@ -1074,14 +1179,14 @@ __global__ void k_exact_fallback(const RerankParams p)
     }
 }
 
-__global__ void k_finalize(const unsigned long long *__restrict__ best, int64_t P,
+__global__ void k_finalize(const unsigned long long *__restrict__ best, int64_t P, int negate,
                            uint64_t *out_packed, float *out_score, int64_t *out_idx)
 {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= P) return;
     const unsigned long long v = best[i];
     if (out_packed) out_packed[i] = v;
-    if (out_score) out_score[i] = (v == ~0ull) ? __int_as_float(0x7fc00000) : unpack_score(v);
+    if (out_score) out_score[i] = (v == ~0ull) ? __int_as_float(0x7fc00000) : (negate ? -unpack_score(v) : unpack_score(v));
     if (out_idx) out_idx[i] = (v == ~0ull) ? -1 : static_cast<int64_t>(v & 0xFFFFFFFFull);
 }
 
@@ -1156,12 +1261,17 @@ static int choose_np(int64_t NT)
     return (np_env == 2 && NT >= 2) ? 2 : 1;
 }
 
-static int launch_screen(const eosvr_gallery *g, eosvr_workspace *ws, const MatchPlan &pl, int np, bool seed,
-                         const CUtensorMap &tmB, int64_t gallery_tiles, int64_t g_stride, int64_t P,
+struct ScreenView {          // the screening copy of the gallery a launch reads (one per metric)
+    const float *gnorm;
+    const CUtensorMap *tmapA, *tmapSeed, *tmapAH, *tmapSeedH;
+};
+
+static int launch_screen(const eosvr_gallery *g, const ScreenView &sv, eosvr_workspace *ws, const MatchPlan &pl, int np,
+                         bool seed, const CUtensorMap &tmB, int64_t gallery_tiles, int64_t g_stride, int64_t P,
                          bool timed, cudaStream_t st)
 {
     ScreenParams sp;
-    sp.gnorm = g->gnorm; sp.G = g->G; sp.KB = g->Dp / kBK; sp.BN = pl.BN; sp.NT = pl.NT;
+    sp.gnorm = sv.gnorm; sp.G = g->G; sp.KB = g->Dp / kBK; sp.BN = pl.BN; sp.NT = pl.NT;
     sp.NTG = pl.NT / np;
     sp.GT = gallery_tiles;
     const int seed_mode = seed ? 1 : 0;
@@ -1199,19 +1309,30 @@ static int launch_screen(const eosvr_gallery *g, eosvr_workspace *ws, const Matc
     const bool rec = timed && ws->timing_on && ws->timing_calls < kTimingRing;
     if (rec) EOSVR_CUDA(cudaEventRecord(ws->ev0[ws->timing_calls], st));
     int rc;
-    if (np == 2) rc = launch_screen_np<2>(seed ? g->tmapSeedH : g->tmapAH, tmB, sp, st);
-    else rc = launch_screen_np<1>(seed ? g->tmapSeed : g->tmapA, tmB, sp, st);
+    if (np == 2) rc = launch_screen_np<2>(seed ? *sv.tmapSeedH : *sv.tmapAH, tmB, sp, st);
+    else rc = launch_screen_np<1>(seed ? *sv.tmapSeed : *sv.tmapA, tmB, sp, st);
     if (rc) return rc;
     if (rec) { EOSVR_CUDA(cudaEventRecord(ws->ev1[ws->timing_calls], st)); ++ws->timing_calls; }
     EOSVR_COUNT_LAUNCH(1);
     return EOSVR_OK;
 }
 
-int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int64_t P,
-                 int32_t rpe, float lam1, float lam2, bool exact_only, uint64_t *out_packed,
+int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int64_t P,
+                 int32_t rpe, int32_t metric, float lam1, float lam2, bool exact_only, uint64_t *out_packed,
                  float *out_score, int64_t *out_idx, cudaStream_t st)
 {
     if (P == 0) return EOSVR_OK;
+    const bool cosm = metric == EOSVR_METRIC_COSINE;
+    if (cosm) { lam1 = 0.f; lam2 = 1.f; rpe = 1; }          // no temporal taps: every probe row stands alone
+    ScreenView sv{g->gnorm, &g->tmapA, &g->tmapSeed, &g->tmapAH, &g->tmapSeedH};
+    const float *scalars = g->scalars;
+    if (cosm && !exact_only) {
+        int rc = build_cosine_copy(g, st);                  // first cosine call builds the normalised copy
+        if (rc) return rc;
+        EOSVR_CUDA(cudaStreamWaitEvent(st, g->cos->ready, 0));
+        sv = ScreenView{g->cos->gnorm, &g->cos->tmapA, &g->cos->tmapSeed, &g->cos->tmapAH, &g->cos->tmapSeedH};
+        scalars = g->cos->scalars;
+    }
     if (g_num_sms == 0) {
         int dev = 0;
         EOSVR_CUDA(cudaGetDevice(&dev));
@@ -1235,7 +1356,7 @@ int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probe
 
     RerankParams rp;
     rp.probes = probes; rp.gal = g->feats; rp.P = P; rp.G = g->G; rp.offset = g->offset;
-    rp.D = g->D; rp.rpe = rpe; rp.lam1 = lam1; rp.lam2 = lam2;
+    rp.D = g->D; rp.rpe = rpe; rp.metric = metric; rp.lam1 = lam1; rp.lam2 = lam2;
     rp.cand = ws->cand; rp.rowcnt = ws->rowcnt; rp.cand_cap = static_cast<int32_t>(ws->cand_cap);
     rp.ctr = ws->counters; rp.gthr = ws->gthr;
     rp.best = ws->best; rp.rowflag = ws->rowflag; rp.flaglist = ws->flaglist;
@@ -1246,12 +1367,12 @@ int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probe
     ws->last_bn = pl.BN;
     if (!exact_only) {
         const unsigned pblocks = static_cast<unsigned>((ncol * 32 + threads - 1) / threads);
-        if (g->screen_fmt == EOSVR_SCREEN_F16)
-            k_probe_prep<__half><<<pblocks, threads, 0, st>>>(probes, pd, g->D, g->Dp, g->scalars,
-                static_cast<__half *>(ws->q16), ws->na, ws->epsd, ws->rowmap, ws->counters);
-        else
-            k_probe_prep<__nv_bfloat16><<<pblocks, threads, 0, st>>>(probes, pd, g->D, g->Dp, g->scalars,
-                static_cast<__nv_bfloat16 *>(ws->q16), ws->na, ws->epsd, ws->rowmap, ws->counters);
+#define EOSVR_PROBE_PREP(T16, NORM)                                                                              \
+        k_probe_prep<T16, NORM><<<pblocks, threads, 0, st>>>(probes, pd, g->D, g->Dp, scalars,                     \
+            static_cast<T16 *>(ws->q16), ws->na, ws->epsd, ws->rowmap, ws->counters)
+        if (g->screen_fmt == EOSVR_SCREEN_F16) { if (cosm) EOSVR_PROBE_PREP(__half, true); else EOSVR_PROBE_PREP(__half, false); }
+        else { if (cosm) EOSVR_PROBE_PREP(__nv_bfloat16, true); else EOSVR_PROBE_PREP(__nv_bfloat16, false); }
+#undef EOSVR_PROBE_PREP
         EOSVR_CUDA(cudaGetLastError());
         k_column_plan<<<static_cast<unsigned>((ncol + threads - 1) / threads), threads, 0, st>>>(
             pd, lam1 / lam2, ws->epsd, ws->wl, ws->wr, ws->margin);
@@ -1266,22 +1387,24 @@ int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probe
         // seed pass over a strided sample of the gallery: tightens every probe row's threshold before the
         // full pass so that concurrent CTAs do not flood the candidate lists
         if (g->seed_tiles > 0 && GT > g->seed_tiles) {
-            rc = launch_screen(g, ws, pl, np, true, tmB, g->seed_tiles, g->seed_stride, P, false, st);
+            rc = launch_screen(g, sv, ws, pl, np, true, tmB, g->seed_tiles, g->seed_stride, P, false, st);
             if (rc) return rc;
         }
-        rc = launch_screen(g, ws, pl, np, false, tmB, GT, 1, P, true, st);
+        rc = launch_screen(g, sv, ws, pl, np, false, tmB, GT, 1, P, true, st);
         if (rc) return rc;
         ws->last_tiles = pl.NT * GT;
 
         const unsigned rr_grid = static_cast<unsigned>(P < static_cast<int64_t>(g_num_sms) * 32 ? P : g_num_sms * 32);
-        const size_t rr_smem = static_cast<size_t>(3) * g->D * sizeof(float);
+        const size_t rr_smem = static_cast<size_t>(cosm ? 1 : 3) * g->D * sizeof(float);
         if ((g->D & 3) == 0 && rr_smem <= 96 * 1024) {
             static bool rr_attr = false;
             if (!rr_attr) {
-                EOSVR_CUDA(cudaFuncSetAttribute(k_rerank_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                EOSVR_CUDA(cudaFuncSetAttribute(k_rerank_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                EOSVR_CUDA(cudaFuncSetAttribute(k_rerank_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
                 rr_attr = true;
             }
-            k_rerank_rows<<<rr_grid, kRrThreads, rr_smem, st>>>(rp);
+            if (cosm) k_rerank_rows<true><<<rr_grid, kRrThreads, rr_smem, st>>>(rp);
+            else k_rerank_rows<false><<<rr_grid, kRrThreads, rr_smem, st>>>(rp);
         }
         else k_rerank<<<g_num_sms * 8, 256, 0, st>>>(rp);
         EOSVR_CUDA(cudaGetLastError());
@@ -1294,7 +1417,7 @@ int launch_match(const eosvr_gallery *g, eosvr_workspace *ws, const float *probe
     k_exact_fallback<<<g_num_sms * 8, 256, 0, st>>>(rp);
     EOSVR_CUDA(cudaGetLastError());
     k_finalize<<<static_cast<unsigned>((P + threads - 1) / threads), threads, 0, st>>>(
-        ws->best, P, out_packed, out_score, out_idx);
+        ws->best, P, cosm ? 1 : 0, out_packed, out_score, out_idx);
     EOSVR_CUDA(cudaGetLastError());
     EOSVR_COUNT_LAUNCH(3);
     return EOSVR_OK;

@@ -12,7 +12,7 @@ import ctypes
 import torch
 
 from eosvr_b200 import _lib
-from eosvr_b200._lib import (METRIC_EUCLID_TEMPORAL, ORIG_REF_QUIRK, SCREEN_F16, check, lib)
+from eosvr_b200._lib import (METRIC_COSINE, METRIC_EUCLID_TEMPORAL, ORIG_REF_QUIRK, SCREEN_F16, check, lib)
 
 LAMDA1, LAMDA2 = 0.1, 1.0     # utils.py:43
 
@@ -139,7 +139,15 @@ class MatchWorkspace:
             pass
 
 
-def _match(fn_name, gallery, ws, probes, rows_per_episode, lam1, lam2, want_packed, stream):
+def _metric_id(metric):
+    if metric in (METRIC_EUCLID_TEMPORAL, "euclidean", "euclid_temporal", None):
+        return METRIC_EUCLID_TEMPORAL
+    if metric in (METRIC_COSINE, "cosine"):
+        return METRIC_COSINE
+    raise ValueError(f"unknown metric {metric!r} (use 'euclidean' or 'cosine')")
+
+
+def _match(fn_name, gallery, ws, probes, rows_per_episode, lam1, lam2, want_packed, stream, metric=METRIC_EUCLID_TEMPORAL):
     probes = _dev_f32(probes, "probes")
     if probes.dim() != 2 or probes.shape[1] != gallery.D:
         raise ValueError(f"probes must be [P, {gallery.D}]")
@@ -149,23 +157,26 @@ def _match(fn_name, gallery, ws, probes, rows_per_episode, lam1, lam2, want_pack
     idx = torch.empty(P, dtype=torch.int64, device=probes.device)
     with torch.cuda.device(probes.device):
         check(getattr(lib(), fn_name)(gallery.handle, ws.handle, _ptr(probes), P, int(rows_per_episode),
-                                      METRIC_EUCLID_TEMPORAL, float(lam1), float(lam2), _ptr(packed), _ptr(score),
+                                      _metric_id(metric), float(lam1), float(lam2), _ptr(packed), _ptr(score),
                                       _ptr(idx), _stream_ptr(stream)), fn_name)
     return (idx, score, packed) if want_packed else (idx, score)
 
 
 def match_segments(gallery: GalleryFeatureCache, ws: MatchWorkspace, probes: torch.Tensor, rows_per_episode: int,
-                   lam1: float = LAMDA1, lam2: float = LAMDA2, want_packed: bool = False, stream=None):
+                   lam1: float = LAMDA1, lam2: float = LAMDA2, want_packed: bool = False, stream=None,
+                   metric="euclidean"):
     """network_test.py:208-212 for a batch of episodes: euclidean cdist -> float32 -> temporal taps
     -> arg-min.  probes [P, D]; returns (idx int64[P] global gallery indices, score float32[P]
-    smoothed distance of the winner[, packed int64[P] shard-merge words])."""
-    return _match("eosvr_match", gallery, ws, probes, rows_per_episode, lam1, lam2, want_packed, stream)
+    smoothed distance of the winner[, packed int64[P] shard-merge words]).
+    metric='cosine': L2-normalise both sides, cosine similarity, arg-max (the reference's other metric,
+    classifier.py:117-120); score is the cosine, the packed word carries -cosine."""
+    return _match("eosvr_match", gallery, ws, probes, rows_per_episode, lam1, lam2, want_packed, stream, metric)
 
 
 def match_segments_exact(gallery, ws, probes, rows_per_episode, lam1=LAMDA1, lam2=LAMDA2, want_packed=False,
-                         stream=None):
+                         stream=None, metric="euclidean"):
     """Same contract through the exhaustive float64 CUDA-core kernel (validation / fallback)."""
-    return _match("eosvr_match_exact", gallery, ws, probes, rows_per_episode, lam1, lam2, want_packed, stream)
+    return _match("eosvr_match_exact", gallery, ws, probes, rows_per_episode, lam1, lam2, want_packed, stream, metric)
 
 
 def merge_top1(gathered_packed: torch.Tensor, stream=None):
@@ -321,8 +332,9 @@ class EpisodePipeline:
 
     def __init__(self, gallery: GalleryFeatureCache, n_way: int, k_shot: int, num_segs: int,
                  max_episodes: int, lam1: float = LAMDA1, lam2: float = LAMDA2, orig_mode: int = ORIG_REF_QUIRK,
-                 group=None, cand_capacity: int = 0):
+                 group=None, cand_capacity: int = 0, metric="euclidean"):
         self.gallery = gallery
+        self.metric = _metric_id(metric)
         self.n, self.S, self.n_way = n_way * k_shot, num_segs, n_way
         self.rpe = self.n * self.S
         self.lam1, self.lam2, self.orig_mode = lam1, lam2, orig_mode
@@ -337,7 +349,8 @@ class EpisodePipeline:
         E = int(probes.shape[0])
         D = self.gallery.D
         flat = probes.reshape(E * self.rpe, D)
-        idx, score, packed = match_segments(self.gallery, self.ws, flat, self.rpe, self.lam1, self.lam2, True, stream)
+        idx, score, packed = match_segments(self.gallery, self.ws, flat, self.rpe, self.lam1, self.lam2, True, stream,
+                                            self.metric)
         rows = None
         if self.group is not None:
             import torch.distributed as dist
@@ -345,6 +358,8 @@ class EpisodePipeline:
             gathered = torch.empty(ws, packed.shape[0], dtype=torch.int64, device=packed.device)
             dist.all_gather_into_tensor(gathered, packed, group=self.group)
             idx, score, packed = merge_top1(gathered, stream)
+            if self.metric == METRIC_COSINE:
+                score = -score                       # the packed word carries -cosine
             rows = gather_winner_rows(self.gallery, idx, stream)
             dist.all_reduce(rows, group=self.group)          # one non-zero contributor per row: exact
         y = support_y.to(torch.float32)

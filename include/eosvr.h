@@ -44,6 +44,13 @@ extern "C" {
 
 /* metric / selection rule of the segment matching */
 #define EOSVR_METRIC_EUCLID_TEMPORAL 0 /* cdist euclidean + [lam1,lam2,lam1] taps + arg-min (network_test.py:208-212) */
+#define EOSVR_METRIC_COSINE          1 /* L2-normalise both sides, cosine similarity, arg-max: the reference's other
+                                        * metric (classifier.py:117-120 idiom: argsort(-cosine_similarity)[:,0]), no
+                                        * temporal taps (lam1, lam2, rows_per_episode are ignored).  The similarity
+                                        * is evaluated in float64 on the ORIGINAL rows (dot / (|a| |b|), 0 for a zero
+                                        * row) and rounded to float32; lowest index on exact ties.  d_out_score holds
+                                        * the cosine; the packed word holds -cosine (so that the shard merge stays an
+                                        * unsigned minimum; eosvr_merge_top1 then reports -cosine as its score). */
 
 /* "original clip feature" row of the augmented support set */
 #define EOSVR_ORIG_REF_QUIRK 0 /* flat segment row i, as written at network_test.py:229 */

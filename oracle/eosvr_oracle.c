@@ -155,6 +155,45 @@ void eo_match_stream(const float *A, int P, const float *B, int64_t G, int D,
 }
 
 /* ---------------------------------------------------------------------------------
+ * Cosine metric of the matcher (the reference's other metric, classifier.py:117-120 idiom
+ * np.argsort(-cosine_similarity(A, B))[:, 0] applied to segment matching; SURVEY App. A
+ * "metric='cosine'"): similarity in float64 on the original rows, dot / (|a| |b|), 0 when
+ * either row is zero (sklearn normalises a zero row to zero), rounded to float32; arg-max
+ * with the lowest index on exact float32 ties (a stable sort of -sim).
+ * sklearn itself evaluates a float32 GEMM of float32-normalised rows whose summation order is
+ * not reproducible; tests/ check this function against it within 1e-5 absolute and require
+ * equal indices wherever sklearn's top-2 margin exceeds that error.
+ * ------------------------------------------------------------------------------- */
+void eo_match_cosine(const float *A, int P, const float *B, int64_t G, int D, int64_t *idx, float *val)
+{
+    double *nb = (double *)malloc(sizeof(double) * (size_t)G);
+#pragma omp parallel for schedule(static)
+    for (int64_t g = 0; g < G; ++g) {
+        const float *b = B + (size_t)g * D;
+        double s = 0.0;
+        for (int k = 0; k < D; ++k) s += (double)b[k] * (double)b[k];
+        nb[g] = s;
+    }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int p = 0; p < P; ++p) {
+        const float *a = A + (size_t)p * D;
+        double na = 0.0;
+        for (int k = 0; k < D; ++k) na += (double)a[k] * (double)a[k];
+        float best = -INFINITY; int64_t bidx = -1;
+        for (int64_t g = 0; g < G; ++g) {
+            const float *b = B + (size_t)g * D;
+            double dot = 0.0;
+            for (int k = 0; k < D; ++k) dot += (double)a[k] * (double)b[k];
+            double den = sqrt(na) * sqrt(nb[g]);
+            float c = den > 0.0 ? (float)(dot / den) : 0.0f;
+            if (bidx < 0 || c > best) { best = c; bidx = g; }
+        }
+        idx[p] = bidx; if (val) val[p] = best;
+    }
+    free(nb);
+}
+
+/* ---------------------------------------------------------------------------------
  * numpy float32 mean over axis 0 of a C-contiguous [R,D] block: rows are accumulated
  * sequentially in float32 (row0 + row1 + ...) and the sum is divided by the row count
  * with a true float32 division ("Bit-level evaluation orders").

@@ -223,6 +223,25 @@ def c_match(A, B, rows_per_episode=None, lam1=LAMDA1, lam2=LAMDA2):
     return idx, val
 
 
+def c_match_cosine(A, B):
+    """Cosine metric of the matcher (float64 dot / (|a||b|) -> float32, arg-max, lowest index on ties)."""
+    A, B = _f32(A), _f32(B)
+    P = A.shape[0]
+    idx = np.empty(P, dtype=np.int64)
+    val = np.empty(P, dtype=np.float32)
+    _lib().eo_match_cosine(_p(A, ctypes.c_float), P, _p(B, ctypes.c_float), ctypes.c_int64(B.shape[0]),
+                           A.shape[1], _p(idx, ctypes.c_int64), _p(val, ctypes.c_float))
+    return idx, val
+
+
+def lib_match_cosine(A, B):
+    """The reference's cosine idiom (classifier.py:117-120) applied to segment matching, through sklearn:
+    returns (ids, sim[P,G] float32)."""
+    from sklearn.metrics.pairwise import cosine_similarity
+    sim = cosine_similarity(_f32(A), _f32(B))
+    return np.argsort(-sim, axis=1, kind="stable")[:, 0].astype(np.int64), sim
+
+
 def c_splice(probe, gallery, ids, orig_mode=ORIG_REF_QUIRK):
     probe, gallery = _f32(probe), _f32(gallery)
     ids = np.ascontiguousarray(ids, dtype=np.int64)

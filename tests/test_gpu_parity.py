@@ -324,6 +324,58 @@ def test_run_host_pipelined_equals_device_run():
         assert torch.equal(h2["pred"], r["pred"].cpu()) and torch.equal(h2["idx"], r["idx"].cpu())
 
 
+@pytest.mark.parametrize("P,D,G,fmt", [(60, 192, 2500, 0), (300, 512, 5000, 0), (40, 100, 257, 1), (1, 64, 17, 0)])
+def test_match_cosine_vs_oracle(P, D, G, fmt):
+    """Cosine metric of the matcher: indices and float32 similarities bit-equal to the oracle (float64
+    dot/(|a||b|) -> float32, lowest index on ties), through the tensor-core screening path and the exhaustive
+    kernel; zero rows, duplicates and a probe parallel to a gallery row included."""
+    A = synth.segment_features(311 + P, P, D)
+    B = synth.segment_features(312 + P, G, D)
+    if P > 8 and G > 2000:
+        A[7] = 0.0; B[11] = 0.0
+        B[2000] = B[5]; B[900] = B[5]
+        A[3] = B[5] * np.float32(0.5)
+    oid, oval = O.c_match_cosine(A, B)
+    cache = ev.GalleryFeatureCache(_cuda(B), screen_fmt=fmt)
+    ws = ev.MatchWorkspace(P, D)
+    idx, score, packed = ev.match_segments(cache, ws, _cuda(A), 1, metric="cosine", want_packed=True)
+    st = ws.stats()
+    i2, s2 = ev.match_segments_exact(cache, ws, _cuda(A), 1, metric="cosine")
+    assert np.array_equal(i2.cpu().numpy(), oid) and np.array_equal(s2.cpu().numpy(), oval)
+    assert np.array_equal(idx.cpu().numpy(), oid), st
+    assert np.array_equal(score.cpu().numpy(), oval)
+    # the packed word carries -cosine: merging two shards is still an element-wise unsigned minimum
+    h = (G // 2) // 128 * 128
+    if h > 0:
+        c0, c1 = ev.GalleryFeatureCache(_cuda(B[:h])), ev.GalleryFeatureCache(_cuda(B[h:]), global_offset=h)
+        _, _, p0 = ev.match_segments(c0, ws, _cuda(A), 1, metric="cosine", want_packed=True)
+        _, _, p1 = ev.match_segments(c1, ws, _cuda(A), 1, metric="cosine", want_packed=True)
+        mi, ms, mp = ev.merge_top1(torch.stack([p0, p1]))
+        assert torch.equal(mi, idx) and torch.equal(mp, packed) and torch.equal(-ms, score)
+    # the Euclidean path on the same handle is unaffected by the lazily built cosine copy
+    eid, _ = O.c_match(A, B, 1, 0.0, 1.0)
+    e_idx, _ = ev.match_segments(cache, ws, _cuda(A), 1, 0.0, 1.0)
+    assert np.array_equal(e_idx.cpu().numpy(), eid)
+
+
+def test_cosine_pipeline_at_scale():
+    """Cosine metric at a tensor-bound size (P = 8960, G = 11200, D = 2048): a sample of rows equals the
+    oracle, the call is idempotent, and no row needs the exhaustive fallback."""
+    P, D, G = 8960, 2048, 11200
+    A = synth.segment_features(331, P, D)
+    B = synth.segment_features(332, G, D)
+    cache = ev.GalleryFeatureCache(_cuda(B))
+    ws = ev.MatchWorkspace(P, D)
+    idx, score = ev.match_segments(cache, ws, _cuda(A), 1, metric="cosine")
+    st = ws.stats()
+    assert st["fallback_rows"] == 0, st
+    sel = np.arange(0, P, 173)
+    oid, oval = O.c_match_cosine(A[sel], B)
+    assert np.array_equal(idx.cpu().numpy()[sel], oid) and np.array_equal(score.cpu().numpy()[sel], oval)
+    i2, s2 = ev.match_segments(cache, ws, _cuda(A), 1, metric="cosine")
+    assert torch.equal(i2, idx) and torch.equal(s2, score)
+
+
 def test_segment_features():
     f = synth.frame_features(5, 64, 96)
     a = ev.segment_features(_cuda(f), 2, True).cpu().numpy()

@@ -140,3 +140,33 @@ def test_segment_features():
     b = O.c_segment_features(f, 2, True)
     np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-8)
     assert np.array_equal(O.lib_segment_features(f, 4, False), O.c_segment_features(f, 4, False))
+
+
+def test_cosine_match_oracle_vs_sklearn():
+    """The matcher's cosine metric (oracle: float64 dot/(|a||b|) -> float32, arg-max, lowest index on ties)
+    against the reference's cosine idiom through sklearn (classifier.py:117-120): similarities within 1e-5
+    absolute (sklearn multiplies float32-normalised rows in a float32 GEMM), indices equal wherever sklearn's
+    top-2 margin exceeds that error; zero rows give similarity 0; exact duplicates resolve to the lowest index."""
+    A = synth.segment_features(301, 60, 192)
+    B = synth.segment_features(302, 2500, 192)
+    A[7] = 0.0                                   # zero probe row: every similarity is 0 -> index 0
+    B[11] = 0.0                                  # zero gallery row
+    B[2000] = B[5]; B[900] = B[5]                # duplicates: lowest index must win
+    A[3] = B[5] * np.float32(0.5)                # probe parallel to the duplicated row -> cosine 1
+    idx, val = O.c_match_cosine(A, B)
+    ids, sim = O.lib_match_cosine(A, B)
+    assert idx[7] == 0 and val[7] == 0.0
+    assert idx[3] == 5 and abs(val[3] - 1.0) < 1e-6
+    rows = np.arange(A.shape[0])
+    assert np.abs(sim[rows, idx] - val).max() < 1e-5
+    top2 = np.sort(sim, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 2e-5
+    assert clear.sum() > 40
+    assert np.array_equal(idx[clear], ids[clear])
+    # on unit-norm rows without smoothing the cosine and the Euclidean metric pick the same segment
+    An = A / np.maximum(np.linalg.norm(A, axis=1, keepdims=True), 1e-12).astype(np.float32)
+    Bn = B / np.maximum(np.linalg.norm(B, axis=1, keepdims=True), 1e-12).astype(np.float32)
+    keep = np.ones(A.shape[0], bool); keep[7] = False
+    Bn[11] = 10.0                                # keep the zero row out of the Euclidean race
+    e_idx, _ = O.c_match(An, Bn, 1, 0.0, 1.0)
+    assert (e_idx[keep & clear] == idx[keep & clear]).all()
