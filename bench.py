@@ -199,9 +199,20 @@ def run_ours(args):
     E = args.episodes
     nb = 2                                   # rotate probe batches so no step re-reads the previous one
     batches = make_inputs(E, nb)
-    d_gal = torch.from_numpy(gal).to(dev)
+    shards, row_exchange = None, "none (single GPU)"
+    if world > 1:
+        try:        # shards in symmetric memory: winner rows are read in place over NVLink by the scoring kernel
+            from eosvr_b200.dist import SymmetricGallery
+            shards = SymmetricGallery(torch.from_numpy(gal), rank * G_PER_GPU, group)
+            d_gal = shards.feats
+            row_exchange = "peer loads over NVLink (symmetric memory), data-parallel scoring"
+        except Exception as exc:                                   # noqa: BLE001
+            shards = None
+            row_exchange = f"dense all_reduce (symmetric memory unavailable: {type(exc).__name__})"
+    if shards is None:
+        d_gal = torch.from_numpy(gal).to(dev)
     cache = ev.GalleryFeatureCache(d_gal, global_offset=rank * G_PER_GPU)
-    pipe = ev.EpisodePipeline(cache, N_WAY, K_SHOT, S, E, group=group)
+    pipe = ev.EpisodePipeline(cache, N_WAY, K_SHOT, S, E, group=group, shards=shards)
     dev_in = [(torch.from_numpy(b["probe"]).to(dev), torch.from_numpy(b["support_y"]).to(dev),
                torch.from_numpy(b["query"]).to(dev)) for b in batches]
     host_in = [(torch.from_numpy(b["probe"]).pin_memory(), torch.from_numpy(b["support_y"]).pin_memory(),
@@ -296,7 +307,7 @@ def run_ours(args):
         "config": {"workload": "cfg-2 UnrealAction-shaped 14-way 1-shot episodes, S=8, D=2048, "
                                "G=11200 segments per GPU (1400 clips), E=256 episodes/step",
                    "episodes_per_step": E, "rows_per_episode": RPE, "probe_rows": E * RPE,
-                   "gallery_rows_total": G_total, "gallery_sharding": f"by segment over {world} GPU(s)",
+                   "gallery_rows_total": G_total, "gallery_sharding": f"by segment over {world} GPU(s)", "winner_row_exchange": row_exchange,
                    "l2": "2 probe batches rotated; per-step working set ~490 MB > 126 MB L2, no explicit flush"},
         "episodes_per_s": E / (ms_step * 1e-3),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

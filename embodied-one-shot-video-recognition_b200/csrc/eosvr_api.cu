@@ -410,8 +410,25 @@ int eosvr_episode_score(const float *d_probes, const float *d_winner_rows, const
     if (!d_winner_rows && g && g->D != D) { set_error("episode_score: gallery D=%d != D=%d", g->D, D); return EOSVR_EINVAL; }
     if (orig_mode != EOSVR_ORIG_REF_QUIRK && orig_mode != EOSVR_ORIG_CLIP_MEAN) { set_error("episode_score: bad orig_mode %d", orig_mode); return EOSVR_EINVAL; }
     return launch_episode_score(d_probes, d_winner_rows, d_winner_rows ? nullptr : g->feats, d_winner_rows ? 0 : g->G,
-                                d_winner_rows ? 0 : g->offset, d_idx, d_support_y, d_query, E, n, S, Q, D, orig_mode,
-                                max_proto, d_dist, d_prob, d_pred, d_nproto, static_cast<cudaStream_t>(stream));
+                                d_winner_rows ? 0 : g->offset, nullptr, nullptr, 0, d_idx, d_support_y, d_query, E, n, S,
+                                Q, D, orig_mode, max_proto, d_dist, d_prob, d_pred, d_nproto,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int eosvr_episode_score_sharded(const float *d_probes, const float *const *d_shard_bases, const int64_t *d_shard_begin,
+                                int32_t nshards, const int64_t *d_idx, const float *d_support_y, const float *d_query,
+                                int64_t E, int32_t n, int32_t S, int32_t Q, int32_t D, int32_t orig_mode,
+                                int32_t max_proto, float *d_dist, float *d_prob, int64_t *d_pred, int32_t *d_nproto,
+                                void *stream)
+{
+    if (E < 0 || D < 1 || nshards < 1 || nshards > 64 || !d_shard_bases || !d_shard_begin ||
+        (E > 0 && (!d_probes || !d_support_y || !d_query || !d_idx))) { set_error("episode_score_sharded: bad arguments"); return EOSVR_EINVAL; }
+    if (orig_mode != EOSVR_ORIG_REF_QUIRK && orig_mode != EOSVR_ORIG_CLIP_MEAN) { set_error("episode_score_sharded: bad orig_mode %d", orig_mode); return EOSVR_EINVAL; }
+    int rc = eosvr_device_check();
+    if (rc) return rc;
+    return launch_episode_score(d_probes, nullptr, nullptr, 0, 0, d_shard_bases, d_shard_begin, nshards, d_idx,
+                                d_support_y, d_query, E, n, S, Q, D, orig_mode, max_proto, d_dist, d_prob, d_pred,
+                                d_nproto, static_cast<cudaStream_t>(stream));
 }
 
 int eosvr_temporal_smooth(const double *d_dist64, int64_t P, int64_t G, int32_t rows_per_episode, float lam1,

@@ -360,10 +360,14 @@ constexpr int kEpThreads = 128;
 template <int S_T>
 __global__ void __launch_bounds__(kEpThreads)
 k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wrows, const float *__restrict__ gal,
-                  int64_t G, int64_t goff, const int64_t *__restrict__ idx, const float *__restrict__ sup_y,
-                  const float *__restrict__ query, int n, int Q, int D, int orig_mode, int max_proto, int nsplit,
-                  double *__restrict__ partial, int32_t *__restrict__ np_out)
+                  int64_t G, int64_t goff, const float *const *__restrict__ shard_bases,
+                  const int64_t *__restrict__ shard_begin, int nshards, const int64_t *__restrict__ idx,
+                  const float *__restrict__ sup_y, const float *__restrict__ query, int n, int Q, int D, int orig_mode,
+                  int max_proto, int nsplit, double *__restrict__ partial, int32_t *__restrict__ np_out)
 {
+    // where each winner row of the episode lives: the exchanged rows, the local gallery, or -- gallery sharded
+    // over the GPUs of the box -- the owning GPU's memory, read in place over NVLink (peer loads)
+    __shared__ const float4 *s_wptr[kMaxClips * S_T];
     __shared__ int16_t s_cls[kMaxClips];
     __shared__ int16_t s_order[kMaxClips];
     __shared__ int16_t s_start[kMaxProto + 1];
@@ -381,6 +385,20 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
     const float4 *wr4 = reinterpret_cast<const float4 *>(wrows);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    for (int t = tid; t < n * S_T; t += kEpThreads) {
+        const int64_t slot = e * n * S_T + t;
+        const float4 *ptr = nullptr;
+        if (wrows) ptr = wr4 + slot * D4;
+        else {
+            const int64_t g = idx[slot];
+            if (nshards > 0) {
+                for (int sh = 0; sh < nshards; ++sh)
+                    if (g >= shard_begin[sh] && g < shard_begin[sh + 1])
+                        ptr = reinterpret_cast<const float4 *>(shard_bases[sh]) + (g - shard_begin[sh]) * D4;
+            } else if (g - goff >= 0 && g - goff < G) ptr = gal4 + (g - goff) * D4;
+        }
+        s_wptr[t] = ptr;
+    }
     if (tid == 0) {
         int np = 0;
         for (int i = 0; i < n; ++i) {                     // classifier.py:21-29 (every row of clip i carries Y[i])
@@ -416,7 +434,6 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
             for (int ii = i0; ii < i1; ++ii) {
                 const int i = s_order[ii];
                 const float4 *pc = Pe + static_cast<int64_t>(i) * S_T * D4 + k;
-                const int64_t wbase = (e * n + i) * S_T;
                 float pr[S_T][4], w[S_T][4];
 #pragma unroll
                 for (int s = 0; s < S_T; ++s) {
@@ -426,11 +443,8 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
 #pragma unroll
                 for (int s = 0; s < S_T; ++s) {
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (wrows) v = wr4[(wbase + s) * D4 + k];
-                    else {
-                        const int64_t g = idx[wbase + s] - goff;
-                        if (g >= 0 && g < G) v = gal4[g * D4 + k];
-                    }
+                    const float4 *wp = s_wptr[i * S_T + s];
+                    if (wp) v = wp[k];
                     w[s][0] = v.x; w[s][1] = v.y; w[s][2] = v.z; w[s][3] = v.w;
                 }
                 float o[4];
@@ -520,11 +534,16 @@ __global__ void k_episode_final(const double *__restrict__ partial, const int32_
 }
 
 int launch_episode_score(const float *probes, const float *wrows, const float *gal, int64_t G, int64_t goff,
+                         const float *const *shard_bases, const int64_t *shard_begin, int32_t nshards,
                          const int64_t *idx, const float *sup_y, const float *query, int64_t E, int32_t n,
                          int32_t S, int32_t Q, int32_t D, int32_t orig_mode, int32_t max_proto, float *dist,
                          float *prob, int64_t *pred, int32_t *nproto, cudaStream_t st)
 {
     if (E == 0) return EOSVR_OK;
+    if (nshards > 0 && !((D & 3) == 0 && (S == 2 || S == 4 || S == 8) && D >= 256)) {
+        set_error("episode_score_sharded: needs D %% 4 == 0, D >= 256 and S in {2,4,8}");
+        return EOSVR_EUNSUPPORTED;
+    }
     if (n < 1 || n > kMaxClips || S < 1 || Q < 1 || Q > kMaxQ || max_proto < 1 || max_proto > kMaxProto) {
         set_error("episode_score: need 1<=n<=%d, S>=1, 1<=Q<=%d, 1<=max_proto<=%d", kMaxClips, kMaxQ, kMaxProto);
         return EOSVR_EINVAL;
@@ -542,8 +561,9 @@ int launch_episode_score(const float *probes, const float *wrows, const float *g
         partial = reinterpret_cast<double *>(scratch + nbytes);
         dim3 pgrid(static_cast<unsigned>(E), static_cast<unsigned>(nsplit));
 #define EOSVR_EPP_LAUNCH(ST)                                                                                      \
-        k_episode_partial<ST><<<pgrid, kEpThreads, 0, st>>>(probes, wrows, gal, G, goff, idx, sup_y, query, n, Q, D,  \
-                                                           orig_mode, max_proto, nsplit, partial, np_buf)
+        k_episode_partial<ST><<<pgrid, kEpThreads, 0, st>>>(probes, wrows, gal, G, goff, shard_bases, shard_begin,     \
+                                                           nshards, idx, sup_y, query, n, Q, D, orig_mode, max_proto, \
+                                                           nsplit, partial, np_buf)
         if (S == 2) EOSVR_EPP_LAUNCH(2); else if (S == 4) EOSVR_EPP_LAUNCH(4); else EOSVR_EPP_LAUNCH(8);
 #undef EOSVR_EPP_LAUNCH
         EOSVR_CUDA(cudaGetLastError());

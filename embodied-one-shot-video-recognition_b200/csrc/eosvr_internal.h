@@ -156,6 +156,7 @@ int launch_gather_rows(const eosvr_gallery *g, const int64_t *idx, int64_t P, fl
 int launch_splice(const float *probes, const float *wrows, int64_t E, int32_t n, int32_t S, int32_t D,
                   int32_t orig_mode, float *out, cudaStream_t st);
 int launch_episode_score(const float *probes, const float *wrows, const float *gal, int64_t G, int64_t goff,
+                         const float *const *shard_bases, const int64_t *shard_begin, int32_t nshards,
                          const int64_t *idx, const float *sup_y, const float *query, int64_t E, int32_t n,
                          int32_t S, int32_t Q, int32_t D, int32_t orig_mode, int32_t max_proto, float *dist,
                          float *prob, int64_t *pred, int32_t *nproto, cudaStream_t st);

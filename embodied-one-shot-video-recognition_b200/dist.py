@@ -43,3 +43,41 @@ def unpack_np(packed: np.ndarray):
 def merge_np(gathered: np.ndarray) -> np.ndarray:
     """Element-wise unsigned minimum over shards ([nshards, P] uint64) -- the merge rule."""
     return np.min(np.asarray(gathered).view(np.uint64), axis=0)
+
+
+class SymmetricGallery:
+    """This rank's gallery shard placed in symmetric (peer-mapped) memory, plus the table of all shards.
+
+    Every rank allocates the same-sized buffer with ``torch.distributed._symmetric_memory`` and the rendezvous
+    maps every peer's buffer into this process, so a kernel on GPU r can read rows of shard s in place over
+    NVLink.  ``feats`` is the local [G_r, D] view (hand it to ``GalleryFeatureCache(..., global_offset=begin)``);
+    ``bases`` (int64 [world], device pointers) and ``begin`` (int64 [world+1], global row offsets) are what
+    ``eosvr_episode_score_sharded`` takes."""
+
+    def __init__(self, shard_feats, begin: int, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = dist.group.WORLD if group is None else group
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        shard_feats = torch.as_tensor(shard_feats)
+        rows, D = int(shard_feats.shape[0]), int(shard_feats.shape[1])
+        meta = torch.tensor([rows, int(begin)], dtype=torch.int64, device=dev)
+        allmeta = torch.empty(world, 2, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allmeta, meta, group=group)
+        allmeta = allmeta.cpu()
+        max_rows = int(allmeta[:, 0].max())
+        begins = [int(allmeta[r, 1]) for r in range(world)]
+        ends = [int(allmeta[r, 1] + allmeta[r, 0]) for r in range(world)]
+        if any(begins[r + 1] != ends[r] for r in range(world - 1)) or begins[0] != 0:
+            raise ValueError("shards must be contiguous, ascending by rank and start at row 0")
+        self.buffer = symm.empty(max_rows, D, dtype=torch.float32, device=dev)
+        self.buffer[:rows].copy_(shard_feats.to(dev, non_blocking=True))
+        self.handle = symm.rendezvous(self.buffer, group)
+        torch.cuda.synchronize()
+        self.handle.barrier()                    # every shard is in place before anybody reads a peer
+        self.feats = self.buffer[:rows]
+        self.begin_row, self.rows, self.world, self.rank = int(begin), rows, world, rank
+        self.bases = torch.tensor([int(self.handle.buffer_ptrs[r]) for r in range(world)], dtype=torch.int64, device=dev)
+        self.begin = torch.tensor(begins + [ends[-1]], dtype=torch.int64, device=dev)

@@ -281,6 +281,36 @@ def episode_score(probes: torch.Tensor, support_y: torch.Tensor, query: torch.Te
     return dict(pred=pred, dist=dist, prob=prob, nproto=nproto)
 
 
+def episode_score_sharded(probes: torch.Tensor, support_y: torch.Tensor, query: torch.Tensor, n: int, S: int,
+                          bases: torch.Tensor, begin: torch.Tensor, idx: torch.Tensor, orig_mode: int = ORIG_REF_QUIRK,
+                          max_proto: int = 0, stream=None):
+    """episode_score with the gallery sharded by segment over the GPUs of the box: winner rows are read in place
+    from the owning GPU (``bases``/``begin`` = eosvr_b200.dist.SymmetricGallery tables)."""
+    D = int(probes.shape[-1])
+    probes = _dev_f32(probes, "probes").reshape(-1, D)
+    support_y, query = _dev_f32(support_y, "support_y"), _dev_f32(query, "query")
+    E = probes.shape[0] // (n * S)
+    Q = int(query.shape[1]) if E else 1
+    idx = idx.contiguous().view(-1)
+    if idx.dtype != torch.int64 or idx.numel() != probes.shape[0]:
+        raise ValueError("idx must be int64 [E*n*S]")
+    nshards = int(bases.numel())
+    if bases.dtype != torch.int64 or begin.dtype != torch.int64 or int(begin.numel()) != nshards + 1:
+        raise ValueError("bases int64 [nshards] and begin int64 [nshards+1] expected")
+    mp = int(max_proto) if max_proto else min(n, 64)
+    dev = probes.device
+    dist = torch.empty(E, Q, mp, dtype=torch.float32, device=dev)
+    prob = torch.empty(E, Q, mp, dtype=torch.float32, device=dev)
+    pred = torch.empty(E, Q, dtype=torch.int64, device=dev)
+    nproto = torch.empty(E, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().eosvr_episode_score_sharded(_ptr(probes), _ptr(bases), _ptr(begin), nshards, _ptr(idx),
+                                                _ptr(support_y), _ptr(query), E, int(n), int(S), Q, D, int(orig_mode),
+                                                mp, _ptr(dist), _ptr(prob), _ptr(pred), _ptr(nproto),
+                                                _stream_ptr(stream)), "eosvr_episode_score_sharded")
+    return dict(pred=pred, dist=dist, prob=prob, nproto=nproto)
+
+
 def temporal_smooth(dist64: torch.Tensor, rows_per_episode: int | None = None, lam1: float = LAMDA1,
                     lam2: float = LAMDA2, stream=None) -> torch.Tensor:
     """network_test.py:103-117 on an explicit float64 [P,G] CUDA distance matrix -> float32 [P,G]."""
@@ -332,9 +362,13 @@ class EpisodePipeline:
 
     def __init__(self, gallery: GalleryFeatureCache, n_way: int, k_shot: int, num_segs: int,
                  max_episodes: int, lam1: float = LAMDA1, lam2: float = LAMDA2, orig_mode: int = ORIG_REF_QUIRK,
-                 group=None, cand_capacity: int = 0, metric="euclidean"):
+                 group=None, cand_capacity: int = 0, metric="euclidean", shards=None):
+        """shards: an eosvr_b200.dist.SymmetricGallery whose ``feats`` back `gallery` -- with it (and `group`) the
+        winner rows are read in place from the owning GPU and scoring is data-parallel over episodes; without it
+        the rows are exchanged with a dense all_reduce and scoring is replicated."""
         self.gallery = gallery
         self.metric = _metric_id(metric)
+        self.shards = shards
         self.n, self.S, self.n_way = n_way * k_shot, num_segs, n_way
         self.rpe = self.n * self.S
         self.lam1, self.lam2, self.orig_mode = lam1, lam2, orig_mode
@@ -360,6 +394,8 @@ class EpisodePipeline:
             idx, score, packed = merge_top1(gathered, stream)
             if self.metric == METRIC_COSINE:
                 score = -score                       # the packed word carries -cosine
+            if self.shards is not None and not return_support and self.S in (2, 4, 8) and D % 4 == 0 and D >= 256:
+                return self._score_sharded(flat, support_y.to(torch.float32), query, idx, score, E, ws, stream)
             rows = gather_winner_rows(self.gallery, idx, stream)
             dist.all_reduce(rows, group=self.group)          # one non-zero contributor per row: exact
         y = support_y.to(torch.float32)
@@ -375,6 +411,31 @@ class EpisodePipeline:
                                 orig_mode=self.orig_mode, max_proto=self.n_way, stream=stream)
         res.update(idx=idx.view(E, self.n, self.S), score=score.view(E, self.n, self.S))
         return res
+
+    def _score_sharded(self, flat, y, query, idx, score, E, world, stream):
+        """Data-parallel scoring: this rank scores its slice of the episodes, reading winner rows from the owning
+        GPUs in place, then ONE all_gather of the (small) per-episode results."""
+        import torch.distributed as dist
+        rank = dist.get_rank(self.group)
+        Q, mp = int(query.shape[1]), self.n_way
+        per = (E + world - 1) // world
+        b, e = min(E, rank * per), min(E, (rank + 1) * per)
+        cols = 2 * mp + 2
+        mine = torch.zeros(per, Q, cols, dtype=torch.float32, device=flat.device)
+        if e > b:
+            r = episode_score_sharded(flat[b * self.rpe:e * self.rpe], y[b:e], query[b:e], self.n, self.S,
+                                      self.shards.bases, self.shards.begin, idx[b * self.rpe:e * self.rpe],
+                                      self.orig_mode, mp, stream)
+            mine[:e - b, :, :mp] = r["dist"]
+            mine[:e - b, :, mp:2 * mp] = r["prob"]
+            mine[:e - b, :, 2 * mp] = r["pred"].to(torch.float32)
+            mine[:e - b, :, 2 * mp + 1] = r["nproto"].to(torch.float32)[:, None]
+        allr = torch.empty(world * per, Q, cols, dtype=torch.float32, device=flat.device)
+        dist.all_gather_into_tensor(allr, mine, group=self.group)
+        allr = allr[:E]
+        return dict(pred=allr[:, :, 2 * mp].to(torch.int64), dist=allr[:, :, :mp].contiguous(),
+                    prob=allr[:, :, mp:2 * mp].contiguous(), nproto=allr[:, 0, 2 * mp + 1].to(torch.int32),
+                    idx=idx.view(E, self.n, self.S), score=score.view(E, self.n, self.S))
 
     def run_host(self, probes_host: torch.Tensor, support_y_host: torch.Tensor, query_host: torch.Tensor,
                  chunks: int = 8) -> dict:

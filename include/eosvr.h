@@ -166,6 +166,17 @@ int eosvr_episode_score(const float *d_probes, const float *d_winner_rows, const
                         int32_t max_proto, float *d_dist, float *d_prob, int64_t *d_pred,
                         int32_t *d_nproto, void *stream);
 
+/* Same, with the gallery SHARDED by segment over the GPUs of one box (new): shard s holds the
+ * global rows [d_shard_begin[s], d_shard_begin[s+1]) at d_shard_bases[s], a float32 [rows, D] array in the memory
+ * of the GPU that owns it, mapped into this process (peer / symmetric memory).  Winner rows are read IN PLACE over
+ * NVLink by the scoring kernel -- no dense row exchange.  d_shard_bases [nshards] and d_shard_begin [nshards+1] are
+ * device arrays.  Needs D % 4 == 0, D >= 256 and S in {2,4,8}. */
+int eosvr_episode_score_sharded(const float *d_probes, const float *const *d_shard_bases,
+                                const int64_t *d_shard_begin, int32_t nshards, const int64_t *d_idx,
+                                const float *d_support_y, const float *d_query, int64_t E, int32_t n, int32_t S,
+                                int32_t Q, int32_t D, int32_t orig_mode, int32_t max_proto, float *d_dist,
+                                float *d_prob, int64_t *d_pred, int32_t *d_nproto, void *stream);
+
 /* ---- reference-shaped helpers ------------------------------------------------------------
  * eosvr_temporal_smooth: TestNetwork.temporal_convolution_flating_layer (network_test.py:103-117,
  * models.py:42-56) on an explicit float64 distance matrix d_dist64 [P,G] -> float32 [P,G]; blocks of

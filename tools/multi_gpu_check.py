@@ -41,11 +41,30 @@ def main():
     out = pipe.run(probes, y, q)
     torch.cuda.synchronize()
     ok = all(torch.equal(ref[k], out[k]) for k in ("idx", "score", "pred", "dist"))
+    # peer-memory path: shards in symmetric memory, winner rows read in place over NVLink, data-parallel scoring
+    from eosvr_b200.dist import SymmetricGallery
+    p2p = "skipped"
+    try:
+        sg = SymmetricGallery(torch.from_numpy(gal[b:e]), b, dist.group.WORLD)
+    except Exception as exc:                                   # noqa: BLE001
+        sg = None
+        p2p = f"unavailable ({type(exc).__name__}: {exc})"
+    if sg is not None:
+        shard2 = ev.GalleryFeatureCache(sg.feats, global_offset=b)
+        pipe2 = ev.EpisodePipeline(shard2, n_way, 1, S, E, group=dist.group.WORLD, shards=sg)
+        out2 = pipe2.run(probes, y, q)
+        torch.cuda.synchronize()
+        ok2 = all(torch.equal(ref[k], out2[k]) for k in ("idx", "score", "pred", "dist"))
+        rc = ev.EpisodePipeline(full, n_way, 1, S, E, metric="cosine").run(probes, y, q)
+        oc = ev.EpisodePipeline(shard2, n_way, 1, S, E, group=dist.group.WORLD, shards=sg, metric="cosine").run(probes, y, q)
+        ok3 = all(torch.equal(rc[k], oc[k]) for k in ("idx", "score", "pred", "dist"))
+        p2p = f"identical={ok2} cosine_identical={ok3}"
+        ok = ok and ok2 and ok3
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"multi_gpu_check world={world} shards={[shard_range(G, r, world) for r in range(world)]} "
-              f"identical_to_single_gpu={bool(flag.item())} acc={float((out['pred'].cpu().numpy() == ep['query_y']).mean()):.3f}",
+              f"identical_to_single_gpu={bool(flag.item())} peer_memory_path[{p2p}] acc={float((out['pred'].cpu().numpy() == ep['query_y']).mean()):.3f}",
               flush=True)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() else 1)
