@@ -181,9 +181,11 @@ def run_ours(args):
     gal = make_gallery(rank)
     # CPU baseline first (rank 0, N = 1 only): its worker processes are forked before CUDA is initialised
     cpu = None
+    if args.profile:
+        args.no_cpu = True
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        n_ep = max(cores, 8)
+        n_ep = 8 * max(cores, 8)                 # ~15-20 s of CPU work on the box's host cores
         v, dt, n = cpu_reference(n_ep, gal, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n} cfg-2 episodes in {dt:.1f}s, oracle restatement through the reference's third-party "
@@ -270,6 +272,11 @@ def run_ours(args):
     value = comps_per_step / (ms_step * 1e-3)
 
     # ---- end to end through the public API with host buffers
+    if args.profile:
+        if world > 1:
+            dist.destroy_process_group()
+        print(json.dumps({"profile_run": True, "ms_per_step": ms_step, "steps": args.steps}), flush=True)
+        return
     ms_e2e = timed(step_host, args.steps, args.warmup) / args.steps
     h2d = sum(int(t.numel() * t.element_size()) for t in host_in[0])
     d2h = int(last["h"]["pred"].numel() * 8 + last["h"]["idx"].numel() * 8)
@@ -303,7 +310,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 tensor-core screening (fp32 accumulate) + f64/f32 exact re-rank", "data": "synthetic",
+        "dtype": "f16 (tensor-core screening, f32 accumulate) + f32/f64 exact re-rank", "data": "synthetic",
         "config": {"workload": "cfg-2 UnrealAction-shaped 14-way 1-shot episodes, S=8, D=2048, "
                                "G=11200 segments per GPU (1400 clips), E=256 episodes/step",
                    "episodes_per_step": E, "rows_per_episode": RPE, "probe_rows": E * RPE,
@@ -332,6 +339,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--episodes", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling run (ncu): device-resident steps only, no cpu_baseline and no e2e leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

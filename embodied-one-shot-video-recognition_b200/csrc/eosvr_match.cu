@@ -345,9 +345,15 @@ struct UnitIter {
     int64_t u, jt, gt0, gt1;    // jt: probe tile GROUP of the unit (pair q of the cluster takes tile jt*NP + q)
 };
 
-// Work units are chunk-major: unit u = chunk * NT + probe_tile.  CTAs running at the same time work on
-// the same few gallery chunks (L2-hot, read from HBM once) and on different probe tiles, so a probe
-// row is rarely screened by two CTAs at once and its running threshold stays tight.
+// Work units (gallery chunk x probe tile), three orders (EOSVR_ORDER):
+//   1 (default) probe-tile-major: unit u = probe_tile * n_chunks + chunk.  The pairs that run at the same time work
+//     on the same few probe tiles against different gallery chunks, so a probe tile's K blocks are fetched from HBM
+//     once (L2 hits for the other pairs) and the whole 16-bit gallery stays L2-resident: DRAM traffic close to the
+//     algorithmic bytes.  ~10 % more candidates than chunk-major (several pairs screen the same probe rows at once
+//     and see each other's thresholds one tile late) and still 1-2 % faster;
+//   0 chunk-major: unit u = chunk * NT + probe_tile.  Tightest thresholds, but every probe tile is re-read from HBM
+//     once per gallery chunk (measured 4.7x the algorithmic bytes at the bench size);
+//   2 diagonal (rotated chunks).
 __device__ __forceinline__ bool decode_unit(const ScreenParams &p, int64_t u, UnitIter &it)
 {
     int64_t chunk;
@@ -943,35 +949,51 @@ __device__ __forceinline__ float o2f(unsigned int b)
 
 // COS = cosine metric: one probe row is staged, the score is s = -cosine (so both metrics minimise), the
 // screening value of a candidate is ~ sqrt(2 + 2 s) and the float32 error is absolute (kF32AbsCos).
+constexpr int kRrRowsPerBlock = 8;   // consecutive probe rows per block: neighbours are staged once (sliding window)
+
 template <bool COS>
 __global__ void __launch_bounds__(kRrThreads)
 k_rerank_rows(const RerankParams p)
 {
-    extern __shared__ float4 s_probe4[];          // [3][D/4]: rows p-1, p, p+1  (COS: [D/4], row p)
+    extern __shared__ float4 s_probe4[];          // ring of 3 probe rows [3][D/4]: row q lives in slot q % 3  (COS: 1 row)
     __shared__ int32_t s_g[kRrThreads], s_g2[kRrThreads];
     __shared__ float s_t[kRrThreads], s_t2[kRrThreads];
     __shared__ int s_warpcnt[kRrThreads / 32];
-    __shared__ unsigned int s_bound, s_best32;    // float bits of positive values: unsigned order == float order
+    __shared__ unsigned int s_bound, s_best32;    // s_bound: float bits of a positive value; s_best32: f2o() order
     __shared__ int s_next, s_n32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = p.D, D4 = p.D >> 2;
     unsigned long long appended = 0, done = 0, unsafe_n = 0;
     const float inv_lam2 = 1.0f / p.lam2;
+    const float4 *probes4 = reinterpret_cast<const float4 *>(p.probes);
+    const int64_t nblk = (p.P + kRrRowsPerBlock - 1) / kRrRowsPerBlock;
 
-    for (int64_t row = blockIdx.x; row < p.P; row += gridDim.x) {
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+      const int64_t r0 = blk * kRrRowsPerBlock, r1 = min(p.P, r0 + kRrRowsPerBlock);
+      if (!COS) {                                   // rows r0-1 and r0 (row r0+1 is staged by the first iteration)
+          __syncthreads();
+          for (int k = tid; k < D4; k += kRrThreads) {
+              if (r0 > 0) s_probe4[static_cast<int>((r0 - 1) % 3) * D4 + k] = probes4[(r0 - 1) * D4 + k];
+              s_probe4[static_cast<int>(r0 % 3) * D4 + k] = probes4[r0 * D4 + k];
+          }
+      }
+      for (int64_t row = r0; row < r1; ++row) {
         const unsigned cnt = p.rowcnt[row];
         const int n = cnt < static_cast<unsigned>(p.cand_cap) ? static_cast<int>(cnt) : p.cand_cap;
         if (tid == 0) appended += cnt;
+        __syncthreads();                            // the previous row is done with the slot about to be refilled
+        if (COS) {
+            if (n != 0) for (int k = tid; k < D4; k += kRrThreads) s_probe4[k] = probes4[row * D4 + k];
+        } else if (row + 1 < p.P) {
+            for (int k = tid; k < D4; k += kRrThreads)
+                s_probe4[static_cast<int>((row + 1) % 3) * D4 + k] = probes4[(row + 1) * D4 + k];
+        }
         if (n == 0) continue;                                           // block-uniform
         const int r = static_cast<int>(row % p.rpe);
         const bool hl = r > 0, hr = (r + 1 < p.rpe) && (row + 1 < p.P);
-        const float4 *a1p = reinterpret_cast<const float4 *>(p.probes + row * D);
-        const float4 *a0p = hl ? a1p - D4 : a1p;
-        const float4 *a2p = hr ? a1p + D4 : a1p;
-        for (int k = tid; k < D4; k += kRrThreads) {
-            if (COS) s_probe4[k] = a1p[k];
-            else { s_probe4[k] = a0p[k]; s_probe4[D4 + k] = a1p[k]; s_probe4[2 * D4 + k] = a2p[k]; }
-        }
+        const float4 *sp1 = s_probe4 + (COS ? 0 : static_cast<int>(row % 3) * D4);
+        const float4 *sp0 = s_probe4 + (COS ? 0 : static_cast<int>((row + 2) % 3) * D4);      // row - 1
+        const float4 *sp2 = s_probe4 + (COS ? 0 : static_cast<int>((row + 1) % 3) * D4);
         const float thr = __uint_as_float(p.gthr[row]);
         // one-sided error bound of this row's screening values (half of the two-sided threshold margin)
         const float eps1 = 0.5f * p.margin[(row / p.planR) * p.planBN + p.planHalo + (row % p.planR)];
@@ -1028,7 +1050,7 @@ k_rerank_rows(const RerankParams p)
 #pragma unroll 4
                     for (int k = lane; k < D4; k += 32) {
                         const float4 b = gp[k];
-                        const float4 q = s_probe4[k];
+                        const float4 q = sp1[k];
                         x0 = fmaf(q.x, b.x, x0); x0 = fmaf(q.y, b.y, x0); x0 = fmaf(q.z, b.z, x0); x0 = fmaf(q.w, b.w, x0);
                         x1 = fmaf(b.x, b.x, x1); x1 = fmaf(b.y, b.y, x1); x1 = fmaf(b.z, b.z, x1); x1 = fmaf(b.w, b.w, x1);
                         x2 = fmaf(q.x, q.x, x2); x2 = fmaf(q.y, q.y, x2); x2 = fmaf(q.z, q.z, x2); x2 = fmaf(q.w, q.w, x2);
@@ -1037,7 +1059,7 @@ k_rerank_rows(const RerankParams p)
 #pragma unroll 4
                     for (int k = lane; k < D4; k += 32) {
                         const float4 b = gp[k];
-                        const float4 q0 = s_probe4[k], q1 = s_probe4[D4 + k], q2 = s_probe4[2 * D4 + k];
+                        const float4 q0 = sp0[k], q1 = sp1[k], q2 = sp2[k];
                         float e;
                         e = q0.x - b.x; x0 = fmaf(e, e, x0); e = q0.y - b.y; x0 = fmaf(e, e, x0);
                         e = q0.z - b.z; x0 = fmaf(e, e, x0); e = q0.w - b.w; x0 = fmaf(e, e, x0);
@@ -1089,7 +1111,7 @@ k_rerank_rows(const RerankParams p)
                 if (COS) {
                     for (int k = lane; k < D4; k += 32) {
                         const float4 b = gp[k];
-                        const float4 q = s_probe4[k];
+                        const float4 q = sp1[k];
                         const double bb[4] = {b.x, b.y, b.z, b.w}, qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) { y0 += qq[e] * bb[e]; y1 += bb[e] * bb[e]; y2 += qq[e] * qq[e]; }
@@ -1097,7 +1119,7 @@ k_rerank_rows(const RerankParams p)
                 } else {
                     for (int k = lane; k < D4; k += 32) {
                         const float4 b = gp[k];
-                        const float4 q0 = s_probe4[k], q1 = s_probe4[D4 + k], q2 = s_probe4[2 * D4 + k];
+                        const float4 q0 = sp0[k], q1 = sp1[k], q2 = sp2[k];
                         const double bb[4] = {b.x, b.y, b.z, b.w};
                         const float qq0[4] = {q0.x, q0.y, q0.z, q0.w}, qq1[4] = {q1.x, q1.y, q1.z, q1.w},
                                     qq2[4] = {q2.x, q2.y, q2.z, q2.w};
@@ -1132,7 +1154,7 @@ k_rerank_rows(const RerankParams p)
             __syncthreads();
         }
         if (lane == 0 && loc != ~0ull) atomicMin(p.best + row, loc);
-        __syncthreads();                                                 // s_probe4 is reused by the next row
+      }
     }
     if (lane == 0) {
         if (appended) atomicAdd(&p.ctr->cand_count, appended);
@@ -1286,7 +1308,7 @@ static int launch_screen(const eosvr_gallery *g, const ScreenView &sv, eosvr_wor
     sp.g_stride = g_stride; sp.seed_mode = seed_mode;
     {
         static int order_env = -1, tpu_env = -1;
-        if (order_env < 0) { const char *e = getenv("EOSVR_ORDER"); order_env = e ? atoi(e) : 0; }
+        if (order_env < 0) { const char *e = getenv("EOSVR_ORDER"); order_env = e ? atoi(e) : 1; }
         if (tpu_env < 0) { const char *e = getenv("EOSVR_TPU"); tpu_env = e ? atoi(e) : 0; }
         sp.order = order_env;
         if (tpu_env > 0 && !seed_mode) {
@@ -1386,15 +1408,18 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
         const int64_t GT = (g->G + kPairM - 1) / kPairM;   // 256-row tiles of the CTA pair
         // seed pass over a strided sample of the gallery: tightens every probe row's threshold before the
         // full pass so that concurrent CTAs do not flood the candidate lists
-        if (g->seed_tiles > 0 && GT > g->seed_tiles) {
-            rc = launch_screen(g, sv, ws, pl, np, true, tmB, g->seed_tiles, g->seed_stride, P, false, st);
+        static int seed_env = -1;                           // EOSVR_SEED=0 skips the seed pass (experiments)
+        if (seed_env < 0) { const char *e = getenv("EOSVR_SEED"); seed_env = e ? atoi(e) : 1; }
+        if (seed_env && g->seed_tiles > 0 && GT > g->seed_tiles) {
+            rc = launch_screen(g, sv, ws, pl, np, true, tmB, seed_env == 1 ? g->seed_tiles : 1, g->seed_stride, P, false, st);
             if (rc) return rc;
         }
         rc = launch_screen(g, sv, ws, pl, np, false, tmB, GT, 1, P, true, st);
         if (rc) return rc;
         ws->last_tiles = pl.NT * GT;
 
-        const unsigned rr_grid = static_cast<unsigned>(P < static_cast<int64_t>(g_num_sms) * 32 ? P : g_num_sms * 32);
+        const int64_t rr_blocks = (P + kRrRowsPerBlock - 1) / kRrRowsPerBlock;
+        const unsigned rr_grid = static_cast<unsigned>(rr_blocks < static_cast<int64_t>(g_num_sms) * 32 ? rr_blocks : g_num_sms * 32);
         const size_t rr_smem = static_cast<size_t>(cosm ? 1 : 3) * g->D * sizeof(float);
         if ((g->D & 3) == 0 && rr_smem <= 96 * 1024) {
             static bool rr_attr = false;

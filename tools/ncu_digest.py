@@ -6,17 +6,25 @@ import sys
 
 
 def raw(path):
+    """Metrics of the LONGEST captured launch (a report may hold several, e.g. seed pass + main pass)."""
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    return dict(zip(rows[0], zip(rows[1], rows[2])))
+    ix = rows[0].index("gpu__time_duration.sum")
+    best = max(rows[2:], key=lambda r: float(r[ix].replace(",", "")))
+    print(f"launches in report: {len(rows) - 2}; digest of launch ID {best[0]} ({best[ix]} {rows[1][ix]})")
+    return dict(zip(rows[0], zip(rows[1], best))), best[0]
 
 
-def source(path, top=18):
+def source(path, top=18, launch_id="0"):
     out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr = rows[1]
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]      # one section per captured launch
+    k = min(int(launch_id), len(starts) - 1)
+    sect = rows[starts[k]:(starts[k + 1] if k + 1 < len(starts) else len(rows))]
+    hi = next(i for i, r in enumerate(sect) if "Source" in r and "# Samples" in r)
+    hdr = sect[hi]
     ix = {h: i for i, h in enumerate(hdr)}
-    data = rows[2:]
+    data = [r for r in sect[hi + 1:] if len(r) >= len(hdr) - 1]
     tot = sum(int(r[ix["# Samples"]]) for r in data)
     res = [f"total samples {tot}"]
     for r in sorted(data, key=lambda r: -int(r[ix["# Samples"]]))[:top]:
@@ -39,8 +47,8 @@ KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]
 
 if __name__ == "__main__":
-    m = raw(sys.argv[1])
+    m, lid = raw(sys.argv[1])
     for k in KEYS:
         if k in m:
             print(f"{k:78s} {m[k][1]:>16s} {m[k][0]}")
-    print(source(sys.argv[1]))
+    print(source(sys.argv[1], launch_id=lid))
