@@ -640,14 +640,14 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const float x = fmaf(-2.f, __uint_as_float(v), nb) + tl->na[cbeg * kChunk - 1];
                     dprev = sqrt_approx(fmaxf(x, 0.f));
                 }
-                for (int ch = cbeg; ch < cend; ++ch) {
+                // One chunk of 16 accumulator columns.  `v` holds the chunk (already loaded); the NEXT chunk (or just its
+                // first column, the right-hand neighbour of column 15) is requested before the arithmetic on `v` starts
+                // and waited for only when the taps need it, so the TMEM read latency overlaps the sqrt chain.
+                auto do_chunk = [&](const int ch, uint32_t (&v)[kChunk], uint32_t (&vnx)[kChunk]) {
                     const int c0 = ch * kChunk;
-                    uint32_t v[kChunk];
-                    tmem_ld_x16(trow + c0, v);
-                    uint32_t vn = 0;
                     const bool hasn = (c0 + kChunk) < BN;
-                    if (hasn) tmem_ld_x1(trow + c0 + kChunk, vn);
-                    tmem_ld_wait();
+                    if (ch + 1 < cend) tmem_ld_x16(trow + c0 + kChunk, vnx);
+                    else if (hasn) tmem_ld_x1(trow + c0 + kChunk, vnx[0]);
 
                     float d[kChunk];
                     float minx = kBig;
@@ -664,9 +664,10 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             d[j] = sqrt_approx(fmaxf(x, 0.f));
                         }
                     }
+                    tmem_ld_wait_x16(vnx);
                     float dn = kBig;
                     if (hasn) {
-                        const float x = fmaf(-2.f, __uint_as_float(vn), nb) + tl->na[c0 + kChunk];
+                        const float x = fmaf(-2.f, __uint_as_float(vnx[0]), nb) + tl->na[c0 + kChunk];
                         dn = sqrt_approx(fmaxf(x, 0.f));
                     }
                     const float dprev_in = dprev;
@@ -771,6 +772,15 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const int32_t rm = tl->row[c0 + j];
                             if (rm >= 0) p.dbg[static_cast<int64_t>(rm) * p.G + g] = t[j];
                         }
+                    }
+                };
+                {
+                    uint32_t va[kChunk], vb[kChunk];
+                    tmem_ld_x16(trow + cbeg * kChunk, va);
+                    tmem_ld_wait();
+                    for (int ch = cbeg; ch < cend; ch += 2) {
+                        do_chunk(ch, va, vb);
+                        if (ch + 1 < cend) do_chunk(ch + 1, vb, va);
                     }
                 }
                 tc_fence_before();

@@ -148,6 +148,16 @@ __device__ __forceinline__ void tmem_ld_wait()
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// Same, for a load whose wait is separated from its issue by other work: the destination registers are listed as
+// read-write operands so the compiler cannot schedule a use of them above the wait.
+__device__ __forceinline__ void tmem_ld_wait_x16(uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+}
 
 // ---- CTA pair (cluster of 2, cta_group::2) -------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank()

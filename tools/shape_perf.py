@@ -51,5 +51,11 @@ for name, P, rpe, D, G in SHAPES:
     print(f"{name}: match {ms:.3f} ms ({fl / ms / 1e9:.0f} TFLOP/s, {P * G / ms / 1e6:.1f} G comparisons/s); "
           f"screen {kms / kn:.3f} ms ({fl / (kms / kn) / 1e9:.0f} TFLOP/s); cand/row {st['candidates'] / P:.1f} "
           f"exact/row {st['exact_evals'] / P:.2f} fallback {st['fallback_rows']} spilled {st['spilled']}", flush=True)
+    if int(os.environ.get("EOSVR_EXP", "0")) & 16:
+        c = ws.debug_cycles()
+        tot = max(c["total"], 1) / 74
+        print("   cycles/pair %.0f: epi_busy %.3f epi_wait %.3f mma_wait_full(/3 issuers) %.3f mma_wait_acc %.3f prod_wait %.3f"
+              % (tot, c["epi_busy"] / (148 * 8) / tot, c["epi_wait"] / (148 * 8) / tot, c["mma_wait_full"] / 74 / 3 / tot,
+                 c["mma_wait_acc"] / 74 / tot, c["prod_wait"] / 148 / tot), flush=True)
     del cache, ws, gal, A
     torch.cuda.empty_cache()
