@@ -278,7 +278,8 @@ def run_ours(args):
         print(json.dumps({"profile_run": True, "ms_per_step": ms_step, "steps": args.steps}), flush=True)
         return
     ms_e2e = timed(step_host, args.steps, args.warmup) / args.steps
-    h2d = sum(int(t.numel() * t.element_size()) for t in host_in[0])
+    h2d = sum(int(t.numel() * t.element_size()) for t in host_in[0]) * (1 if E % world == 0 else world)   # all ranks: the batch
+    # crosses PCIe once (1/world per rank) and is replicated over NVLink
     d2h = int(last["h"]["pred"].numel() * 8 + last["h"]["idx"].numel() * 8)
     e2e_value = comps_per_step / (ms_e2e * 1e-3)
 

@@ -447,8 +447,6 @@ class EpisodePipeline:
         E = int(probes_host.shape[0])
         Q = int(query_host.shape[1])
         chunks = max(1, min(int(chunks), E))
-        if self.group is not None:
-            chunks = 1                      # the collectives are issued once per batch
         key = (E, Q, tuple(probes_host.shape[1:]))
         st = getattr(self, "_host_state", None)
         if st is None or st["key"] != key:
@@ -463,6 +461,25 @@ class EpisodePipeline:
                       copy=torch.cuda.Stream(device=dev))
             self._host_state = st
         compute = torch.cuda.current_stream(dev)
+        if self.group is not None:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+            if E % world == 0 and world > 1:
+                # every rank holds the same host batch: copy 1/world of it over PCIe and replicate it over NVLink
+                # (one all_gather per tensor) instead of pushing the whole batch through every GPU's PCIe link
+                b, e = E * rank // world, E * (rank + 1) // world
+                for key, host in (("p", probes_host), ("y", support_y_host), ("q", query_host)):
+                    part = host[b:e].to(dev, non_blocking=True)
+                    dist.all_gather_into_tensor(st[key].view(-1), part.reshape(-1), group=self.group)
+            else:
+                st["p"].copy_(probes_host, non_blocking=True)
+                st["y"].copy_(support_y_host, non_blocking=True)
+                st["q"].copy_(query_host, non_blocking=True)
+            r = self.run(st["p"], st["y"], st["q"])
+            st["pred_h"].copy_(r["pred"], non_blocking=True)
+            st["idx_h"].copy_(r["idx"], non_blocking=True)
+            compute.synchronize()
+            return dict(pred=st["pred_h"], idx=st["idx_h"])
         copy = st["copy"]
         copy.wait_stream(compute)           # the previous call may still be reading the device buffers
         bounds = [(E * c // chunks, E * (c + 1) // chunks) for c in range(chunks)]

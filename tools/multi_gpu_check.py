@@ -58,8 +58,11 @@ def main():
         rc = ev.EpisodePipeline(full, n_way, 1, S, E, metric="cosine").run(probes, y, q)
         oc = ev.EpisodePipeline(shard2, n_way, 1, S, E, group=dist.group.WORLD, shards=sg, metric="cosine").run(probes, y, q)
         ok3 = all(torch.equal(rc[k], oc[k]) for k in ("idx", "score", "pred", "dist"))
-        p2p = f"identical={ok2} cosine_identical={ok3}"
-        ok = ok and ok2 and ok3
+        host = [torch.from_numpy(ep[k]).pin_memory() for k in ("probe", "support_y", "query")]
+        oh = pipe2.run_host(*host)                     # 1/world of the batch over PCIe per rank + NVLink all_gather
+        ok4 = torch.equal(oh["pred"], ref["pred"].cpu()) and torch.equal(oh["idx"], ref["idx"].cpu())
+        p2p = f"identical={ok2} cosine_identical={ok3} host_entry_identical={ok4}"
+        ok = ok and ok2 and ok3 and ok4
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
