@@ -32,6 +32,8 @@ for _p in (ROOT, os.path.join(ROOT, "oracle")):
 N_WAY, K_SHOT, S, D = 14, 1, 8, 2048
 G_PER_GPU = 11200
 RPE = N_WAY * K_SHOT * S
+WORKLOAD = ("cfg-2 UnrealAction-shaped 14-way 1-shot episodes, S=8, D=2048, G=11200 segments per GPU (1400 clips), "
+            "E=256 episodes/step")
 METRIC = "gallery_segment_comparisons_per_s"
 UNIT = "comparisons/s"
 
@@ -158,8 +160,8 @@ def run_reference(args):
         "steps": len(vals), "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "cfg-2 UnrealAction-shaped 14-way 1-shot, S=8, D=2048, G=11200 (CPU sample)",
-                   "episodes_per_step": per_step, "rows_per_episode": RPE},
+        "config": {"workload": WORKLOAD, "episodes_per_step": per_step, "rows_per_episode": RPE,
+                   "note": "bounded CPU sample of the same workload: per_step episodes per step on all host cores"},
         "episodes_per_s": value / (RPE * G_PER_GPU),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{per_step} episodes/step x {len(vals)} steps, scipy cdist + torch conv2d + "
@@ -312,8 +314,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 (tensor-core screening, f32 accumulate) + f32/f64 exact re-rank", "data": "synthetic",
-        "config": {"workload": "cfg-2 UnrealAction-shaped 14-way 1-shot episodes, S=8, D=2048, "
-                               "G=11200 segments per GPU (1400 clips), E=256 episodes/step",
+        "config": {"workload": WORKLOAD if E == 256 else WORKLOAD.replace("E=256", f"E={E}"),
                    "episodes_per_step": E, "rows_per_episode": RPE, "probe_rows": E * RPE,
                    "gallery_rows_total": G_total, "gallery_sharding": f"by segment over {world} GPU(s)", "winner_row_exchange": row_exchange,
                    "l2": "2 probe batches rotated; per-step working set ~490 MB > 126 MB L2, no explicit flush"},

@@ -10,6 +10,7 @@ from eosvr_b200.matcher import (EpisodePipeline, GalleryFeatureCache, MatchWorks
                                 episode_score, gather_winner_rows, match_segments, match_segments_exact, merge_top1, proto_score,
                                 segment_features, splice_augmented, temporal_smooth, cosine_predict)
 
+from eosvr_b200.augment import load_gallery_cache, save_gallery_cache, trainaug_manifest  # noqa: F401
 
 
 def dropin_path() -> str:
@@ -19,7 +20,7 @@ def dropin_path() -> str:
     return os.path.join(os.path.dirname(lib_path()), "dropin")
 
 
-__all__ = ["dropin_path", "EosvrError", "lib", "lib_path", "load_library", "GalleryFeatureCache", "MatchWorkspace",
+__all__ = ["dropin_path", "load_gallery_cache", "save_gallery_cache", "trainaug_manifest", "EosvrError", "lib", "lib_path", "load_library", "GalleryFeatureCache", "MatchWorkspace",
            "EpisodePipeline", "episode_score", "gather_winner_rows", "match_segments", "match_segments_exact", "merge_top1", "proto_score",
            "segment_features", "splice_augmented", "temporal_smooth", "cosine_predict", "ORIG_REF_QUIRK", "ORIG_CLIP_MEAN", "SCREEN_F16",
            "SCREEN_BF16", "METRIC_COSINE", "METRIC_EUCLID_TEMPORAL"]

@@ -18,7 +18,8 @@ import torch
 
 import synth
 
-NAMES = ["utils", "models", "classifier", "generate_gallery_videos", "episode_novel_dataloader", "network_test"]
+NAMES = ["utils", "models", "classifier", "generate_gallery_videos", "generate_augmented_datasets",
+         "episode_novel_dataloader", "network_test"]
 
 
 @pytest.fixture()
@@ -237,6 +238,23 @@ def test_end_to_end_on_sampled_episodes(dropin, tmp_path):
     finally:
         u.GALLERY_CACHE = None
         u.EPISODE_NUMS["test"] = 20000
+
+
+@pytest.mark.gpu
+def test_trainaug_manifest_through_dropin(dropin, tmp_path):
+    u = dropin.utils
+    u.GALLERY_CACHE = synth.hash_normal(31, (20, 16, 64))
+    try:
+        train = {"a": synth.hash_normal(32, (2, 32, 64)), "b": synth.hash_normal(33, (1, 48, 64))}
+        path = dropin.generate_augmented_datasets.generate_trainAug_datasets(train, str(tmp_path / "aug"))
+        rows = [l.split("\t") for l in open(path).read().splitlines()]
+        # per video: first seg_len (2) frames of every 16-frame window
+        assert [r[0] for r in rows] == ["a/0"] * 4 + ["a/1"] * 4 + ["b/0"] * 6
+        assert [int(r[1]) for r in rows[:4]] == [0, 1, 16, 17]
+        assert all(0 <= int(r[2]) < 20 and 0 <= int(r[3]) < 16 for r in rows)
+        assert all(int(rows[i + 1][3]) == int(rows[i][3]) + 1 for i in range(0, len(rows), 2))
+    finally:
+        u.GALLERY_CACHE = None
 
 
 @pytest.mark.gpu

@@ -376,6 +376,42 @@ def test_cosine_pipeline_at_scale():
     assert torch.equal(i2, idx) and torch.equal(s2, score)
 
 
+def test_gallery_cache_file_and_trainaug_manifest(tmp_path):
+    """the persisted gallery cache (whole and sharded load give the same winners) and
+    the train-set augmentation manifest (generate_augmented_datasets.py:102-178 on the matcher): per video the
+    matched segments equal the oracle with the smoothing over the WHOLE video, and the replacements are the
+    first seg_len frames of every 16-frame window."""
+    D, G, seg_len = 128, 1500, 2
+    gal = synth.segment_features(401, G, D)
+    path = str(tmp_path / "gallery.npy")
+    ev.save_gallery_cache(path, gal, seg_len=seg_len, l2=True, meta={"source": "synthetic"})
+    cache, meta = ev.load_gallery_cache(path)
+    assert meta["G"] == G and meta["D"] == D and meta["source"] == "synthetic" and cache.G == G
+    lens = [48, 35, 48, 16, 1, 64]                    # frames per video (odd lengths are truncated, :121-125)
+    videos = [synth.frame_features(410 + i, n, D, unit=True) for i, n in enumerate(lens)]
+    res = ev.trainaug_manifest(cache, videos, seg_len=seg_len, video_frames=16, l2=False)
+    for v, n, (ids, rep) in zip(videos, lens, res):
+        c = n // seg_len
+        assert ids.shape == (c,)
+        if c == 0:
+            assert rep.shape == (0, 2)
+            continue
+        seg = O.lib_segment_features(v[:c * seg_len], seg_len, False)
+        oid, _ = O.c_match(seg, gal, c)
+        assert np.array_equal(ids, oid)
+        want = [(fr + j, int(oid[fr // seg_len]) * seg_len + j) for fr in range(0, c * seg_len, 16) for j in range(seg_len)]
+        assert rep.tolist() == [list(w) for w in want]
+    # sharded load: two halves matched separately and merged equal the whole
+    A = synth.segment_features(420, 40, D)
+    ws = ev.MatchWorkspace(40, D)
+    _, _, pk = ev.match_segments(cache, ws, _cuda(A), 20, want_packed=True)
+    parts = []
+    for r in range(2):
+        c_r, _ = ev.load_gallery_cache(path, rank=r, world=2)
+        parts.append(ev.match_segments(c_r, ws, _cuda(A), 20, want_packed=True)[2])
+    assert torch.equal(ev.merge_top1(torch.stack(parts))[2], pk)
+
+
 def test_segment_features():
     f = synth.frame_features(5, 64, 96)
     a = ev.segment_features(_cuda(f), 2, True).cpu().numpy()
