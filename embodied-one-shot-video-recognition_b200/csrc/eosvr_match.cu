@@ -850,6 +850,7 @@ struct RerankParams {
     int32_t ovf_cap;
     const float *margin;     // per plan column
     int32_t planR, planBN, planHalo;
+    int32_t prof;            // EOSVR_EXP bit 64: phase timing of k_rerank_rows into the cycle counters
 };
 
 // Cosine metric, exactly: float64 dot / (|a| |b|) on the original rows (0 for a zero row), rounded to
@@ -965,52 +966,71 @@ template <bool COS>
 __global__ void __launch_bounds__(kRrThreads)
 k_rerank_rows(const RerankParams p)
 {
-    extern __shared__ float4 s_probe4[];          // ring of 3 probe rows [3][D/4]: row q lives in slot q % 3  (COS: 1 row)
+    extern __shared__ float4 s_probe4[];          // ring of 4 probe rows [4][D/4]: row q lives in slot q % 4  (COS: 2 rows)
     __shared__ int32_t s_g[kRrThreads], s_g2[kRrThreads];
     __shared__ float s_t[kRrThreads], s_t2[kRrThreads];
     __shared__ int s_warpcnt[kRrThreads / 32];
     __shared__ unsigned int s_bound, s_best32;    // s_bound: float bits of a positive value; s_best32: f2o() order
     __shared__ int s_next, s_n32;
+    __shared__ unsigned int s_cnt[kRrRowsPerBlock];
+    __shared__ float s_thr[kRrRowsPerBlock], s_eps[kRrRowsPerBlock];
+    __shared__ double s_part64[kRrThreads / 32][3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = p.D, D4 = p.D >> 2;
     unsigned long long appended = 0, done = 0, unsafe_n = 0;
     const float inv_lam2 = 1.0f / p.lam2;
     const float4 *probes4 = reinterpret_cast<const float4 *>(p.probes);
     const int64_t nblk = (p.P + kRrRowsPerBlock - 1) / kRrRowsPerBlock;
+    unsigned long long c_setup = 0, c_sort = 0, c_p1 = 0, c_p2 = 0;   // tid 0, p.prof only
+    long long tk = p.prof ? clock64() : 0;
+#define RR_MARK(acc) do { if (p.prof && tid == 0) { const long long now = clock64(); acc += now - tk; tk = now; } } while (0)
+
+    // probe rows live in a shared-memory ring filled with cp.async one or two rows ahead of their use, so a row's
+    // global-memory latency hides behind the previous row's work
+    constexpr int RING = COS ? 2 : 4, PF = COS ? 1 : 2;
+    auto stage_row = [&](int64_t q) {                 // all threads: request probe row q into its ring slot
+        const uint32_t dst = smem_u32(s_probe4 + static_cast<int>(q % RING) * D4);
+        const float4 *src = probes4 + q * D4;
+        for (int k = tid; k < D4; k += kRrThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + k * 16), "l"(src + k) : "memory");
+    };
 
     for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
       const int64_t r0 = blk * kRrRowsPerBlock, r1 = min(p.P, r0 + kRrRowsPerBlock);
-      if (!COS) {                                   // rows r0-1 and r0 (row r0+1 is staged by the first iteration)
-          __syncthreads();
-          for (int k = tid; k < D4; k += kRrThreads) {
-              if (r0 > 0) s_probe4[static_cast<int>((r0 - 1) % 3) * D4 + k] = probes4[(r0 - 1) * D4 + k];
-              s_probe4[static_cast<int>(r0 % 3) * D4 + k] = probes4[r0 * D4 + k];
-          }
+      const int64_t last_needed = COS ? r1 - 1 : min(r1, p.P - 1);      // last probe row this block reads
+      __syncthreads();                                  // the previous block's rows are done with the ring
+      if (tid < r1 - r0) {
+          const int64_t row = r0 + tid;
+          s_cnt[tid] = p.rowcnt[row];
+          s_thr[tid] = __uint_as_float(p.gthr[row]);
+          // one-sided error bound of the row's screening values (half of the two-sided threshold margin)
+          s_eps[tid] = 0.5f * p.margin[(row / p.planR) * p.planBN + p.planHalo + (row % p.planR)];
       }
+      if (!COS && r0 > 0) stage_row(r0 - 1);
+      for (int64_t q = r0; q < r0 + PF && q <= last_needed; ++q) stage_row(q);
+      asm volatile("cp.async.commit_group;" ::: "memory");
       for (int64_t row = r0; row < r1; ++row) {
-        const unsigned cnt = p.rowcnt[row];
+        __syncthreads();                                // the previous row is done with the slot about to be refilled
+        if (row + PF <= last_needed) stage_row(row + PF);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");           // everything but the newest request has landed
+        __syncthreads();
+        const unsigned cnt = s_cnt[row - r0];
         const int n = cnt < static_cast<unsigned>(p.cand_cap) ? static_cast<int>(cnt) : p.cand_cap;
         if (tid == 0) appended += cnt;
-        __syncthreads();                            // the previous row is done with the slot about to be refilled
-        if (COS) {
-            if (n != 0) for (int k = tid; k < D4; k += kRrThreads) s_probe4[k] = probes4[row * D4 + k];
-        } else if (row + 1 < p.P) {
-            for (int k = tid; k < D4; k += kRrThreads)
-                s_probe4[static_cast<int>((row + 1) % 3) * D4 + k] = probes4[(row + 1) * D4 + k];
-        }
         if (n == 0) continue;                                           // block-uniform
         const int r = static_cast<int>(row % p.rpe);
         const bool hl = r > 0, hr = (r + 1 < p.rpe) && (row + 1 < p.P);
-        const float4 *sp1 = s_probe4 + (COS ? 0 : static_cast<int>(row % 3) * D4);
-        const float4 *sp0 = s_probe4 + (COS ? 0 : static_cast<int>((row + 2) % 3) * D4);      // row - 1
-        const float4 *sp2 = s_probe4 + (COS ? 0 : static_cast<int>((row + 1) % 3) * D4);
-        const float thr = __uint_as_float(p.gthr[row]);
-        // one-sided error bound of this row's screening values (half of the two-sided threshold margin)
-        const float eps1 = 0.5f * p.margin[(row / p.planR) * p.planBN + p.planHalo + (row % p.planR)];
+        const float4 *sp1 = s_probe4 + static_cast<int>(row % RING) * D4;
+        const float4 *sp0 = s_probe4 + static_cast<int>((row + RING - 1) % RING) * D4;        // row - 1
+        const float4 *sp2 = s_probe4 + static_cast<int>((row + 1) % RING) * D4;
+        const float thr = s_thr[row - r0];
+        const float eps1 = s_eps[row - r0];
         const Cand *list = p.cand + row * p.cand_cap;
         unsigned long long loc = ~0ull;
         if (tid == 0) { s_bound = __float_as_uint(thr); s_best32 = f2o(INFINITY); }
         __syncthreads();
+        RR_MARK(c_setup);
 
         for (int b0 = 0; b0 < n; b0 += kRrThreads) {
             // ---- keep what can still win; compact; sort ascending by screening value ----
@@ -1044,6 +1064,7 @@ k_rerank_rows(const RerankParams p)
             }
             if (tid == 0) { s_next = 0; s_n32 = 0; }
             __syncthreads();
+            RR_MARK(c_sort);
             // ---- (1) float32 evaluation, one candidate per warp, ascending screening value.  Every candidate that
             //      could tie or beat the best exact value t* has t~ <= t*/lam2 + eps1, and t* <= best32*(1+kF32Rel):
             //      once a warp's next candidate is above the shared bound, so are all later ones. ----
@@ -1109,17 +1130,18 @@ k_rerank_rows(const RerankParams p)
                 }
             }
             __syncthreads();
+            RR_MARK(c_p1);
             // ---- (2) exact evaluation of everything within the float32 error of the best float32 value ----
             const int n32 = s_n32;
             const float best32 = o2f(s_best32);
             const float cut = COS ? best32 + 2.0f * kF32AbsCos : best32 * (1.0f + 2.0f * kF32Rel);
-            for (int j = warp; j < n32; j += kRrThreads / 32) {
-                if (!(s_t[j] <= cut)) continue;                          // warp-uniform
+            for (int j = 0; j < n32; ++j) {                              // normally ONE candidate: the whole block on it
+                if (!(s_t[j] <= cut)) continue;                          // block-uniform
                 const int32_t g = s_g[j];
                 const float4 *gp = reinterpret_cast<const float4 *>(p.gal + static_cast<int64_t>(g) * D);
                 double y0 = 0.0, y1 = 0.0, y2 = 0.0;
                 if (COS) {
-                    for (int k = lane; k < D4; k += 32) {
+                    for (int k = tid; k < D4; k += kRrThreads) {
                         const float4 b = gp[k];
                         const float4 q = sp1[k];
                         const double bb[4] = {b.x, b.y, b.z, b.w}, qq[4] = {q.x, q.y, q.z, q.w};
@@ -1127,7 +1149,7 @@ k_rerank_rows(const RerankParams p)
                         for (int e = 0; e < 4; ++e) { y0 += qq[e] * bb[e]; y1 += bb[e] * bb[e]; y2 += qq[e] * qq[e]; }
                     }
                 } else {
-                    for (int k = lane; k < D4; k += 32) {
+                    for (int k = tid; k < D4; k += kRrThreads) {
                         const float4 b = gp[k];
                         const float4 q0 = sp0[k], q1 = sp1[k], q2 = sp2[k];
                         const double bb[4] = {b.x, b.y, b.z, b.w};
@@ -1143,7 +1165,12 @@ k_rerank_rows(const RerankParams p)
                     }
                 }
                 y0 = warp_sum(y0); y1 = warp_sum(y1); y2 = warp_sum(y2);
-                if (lane == 0) {
+                if (lane == 0) { s_part64[warp][0] = y0; s_part64[warp][1] = y1; s_part64[warp][2] = y2; }
+                __syncthreads();
+                if (tid == 0) {
+                    y0 = y1 = y2 = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kRrThreads / 32; ++w) { y0 += s_part64[w][0]; y1 += s_part64[w][1]; y2 += s_part64[w][2]; }
                     float acc;
                     if (COS) {
                         const double den = sqrt(y2) * sqrt(y1);
@@ -1160,13 +1187,21 @@ k_rerank_rows(const RerankParams p)
                     loc = v < loc ? v : loc;
                     ++done;
                 }
+                __syncthreads();
             }
             __syncthreads();
+            RR_MARK(c_p2);
         }
-        if (lane == 0 && loc != ~0ull) atomicMin(p.best + row, loc);
+        if (tid == 0 && loc != ~0ull) atomicMin(p.best + row, loc);
       }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    if (lane == 0) {
+    if (p.prof && tid == 0) {
+        atomicAdd(&p.ctr->cyc_epi_busy, c_setup); atomicAdd(&p.ctr->cyc_epi_wait, c_sort);
+        atomicAdd(&p.ctr->cyc_mma_wait_full, c_p1); atomicAdd(&p.ctr->cyc_mma_wait_acc, c_p2);
+    }
+#undef RR_MARK
+    if (tid == 0) {
         if (appended) atomicAdd(&p.ctr->cand_count, appended);
         if (done) atomicAdd(&p.ctr->n_exact, done);
     }
@@ -1394,6 +1429,7 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
     rp.best = ws->best; rp.rowflag = ws->rowflag; rp.flaglist = ws->flaglist;
     rp.ovf = ws->ovf; rp.ovf_cap = static_cast<int32_t>(ws->ovf_cap);
     rp.margin = ws->margin; rp.planR = pl.R; rp.planBN = pl.BN; rp.planHalo = pl.halo;
+    { const char *e = getenv("EOSVR_EXP"); rp.prof = (e && (atoi(e) & 64)) ? 1 : 0; }
 
     ws->last_tiles = 0;
     ws->last_bn = pl.BN;
@@ -1430,7 +1466,7 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
 
         const int64_t rr_blocks = (P + kRrRowsPerBlock - 1) / kRrRowsPerBlock;
         const unsigned rr_grid = static_cast<unsigned>(rr_blocks < static_cast<int64_t>(g_num_sms) * 32 ? rr_blocks : g_num_sms * 32);
-        const size_t rr_smem = static_cast<size_t>(cosm ? 1 : 3) * g->D * sizeof(float);
+        const size_t rr_smem = static_cast<size_t>(cosm ? 2 : 4) * g->D * sizeof(float);
         if ((g->D & 3) == 0 && rr_smem <= 96 * 1024) {
             static bool rr_attr = false;
             if (!rr_attr) {

@@ -57,5 +57,10 @@ for name, P, rpe, D, G in SHAPES:
         print("   cycles/pair %.0f: epi_busy %.3f epi_wait %.3f mma_wait_full(/3 issuers) %.3f mma_wait_acc %.3f prod_wait %.3f"
               % (tot, c["epi_busy"] / (148 * 8) / tot, c["epi_wait"] / (148 * 8) / tot, c["mma_wait_full"] / 74 / 3 / tot,
                  c["mma_wait_acc"] / 74 / tot, c["prod_wait"] / 148 / tot), flush=True)
+    if int(os.environ.get("EOSVR_EXP", "0")) & 64:
+        c = ws.debug_cycles()
+        tot = c["epi_busy"] + c["epi_wait"] + c["mma_wait_full"] + c["mma_wait_acc"]
+        print("   rerank block-cycles: setup %.2f sort %.2f phase1 %.2f phase2 %.2f; per row %.0f cycles"
+              % (c["epi_busy"] / tot, c["epi_wait"] / tot, c["mma_wait_full"] / tot, c["mma_wait_acc"] / tot, tot / P), flush=True)
     del cache, ws, gal, A
     torch.cuda.empty_cache()
