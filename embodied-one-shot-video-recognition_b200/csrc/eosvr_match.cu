@@ -738,9 +738,8 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             float thr = __uint_as_float(*reinterpret_cast<volatile unsigned int *>(&tl->thr[c]));
                             bool pass = rowok && !uns && (tj <= thr);
                             if (__ballot_sync(0xffffffffu, pass)) {
-                                float mn = pass ? tj : kBig;
-#pragma unroll
-                                for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                                // warp minimum in one instruction: t >= 0, so float order == unsigned order of the bits
+                                const float mn = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(pass ? tj : kBig)));
                                 const float nt = fmaf(mn, kSlopMul, tl->mg[c]);
                                 if (nt < thr) {
                                     if (lane == 0) {
