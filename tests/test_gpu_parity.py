@@ -412,6 +412,51 @@ def test_gallery_cache_file_and_trainaug_manifest(tmp_path):
     assert torch.equal(ev.merge_top1(torch.stack(parts))[2], pk)
 
 
+def test_cfg3_scale_100k_gallery_fp32_and_bf16():
+    """BASELINE cfg-3: 5-way 1-shot, 4 segments/clip, D = 512, 100k-segment gallery, fp32 vs bf16 features.
+    A batch of 64 episodes; sampled episodes equal the oracle bit for bit; bf16-rounded features (oracle consumes
+    the same rounded values) through the bf16 screening copy; idempotence; no exhaustive fallback."""
+    E, n_way, S, D, G = 64, 5, 4, 512, 100000
+    rpe = n_way * S
+    A = synth.segment_features(501, E * rpe, D)
+    gal = synth.segment_features(502, G, D)
+    for fmt, cast in ((0, False), (1, True)):
+        a, g = A, gal
+        if cast:
+            a = torch.from_numpy(A).to(torch.bfloat16).to(torch.float32).numpy()
+            g = torch.from_numpy(gal).to(torch.bfloat16).to(torch.float32).numpy()
+        cache = ev.GalleryFeatureCache(_cuda(g), screen_fmt=fmt)
+        ws = ev.MatchWorkspace(E * rpe, D)
+        idx, score = ev.match_segments(cache, ws, _cuda(a), rpe)
+        st = ws.stats()
+        assert st["fallback_rows"] == 0, st
+        for e in (0, 31, 63):
+            oid, oval = O.c_match(a[e * rpe:(e + 1) * rpe], g, rpe)
+            assert np.array_equal(idx.cpu().numpy()[e * rpe:(e + 1) * rpe], oid), (fmt, e, st)
+            assert np.array_equal(score.cpu().numpy()[e * rpe:(e + 1) * rpe], oval)
+        i2, s2 = ev.match_segments(cache, ws, _cuda(a), rpe)
+        assert torch.equal(i2, idx) and torch.equal(s2, score)
+        del cache, ws
+
+
+def test_cfg5_shape_5way5shot_8seg_2048d():
+    """BASELINE cfg-5 shape: 5-way 5-shot, 8 segments/clip (200 probe rows per episode), D = 2048, on one shard
+    of the gallery (20k segments): full pipeline against the oracle for every episode of a small batch."""
+    E, n_way, k, S, D, G = 3, 5, 5, 8, 2048, 20000
+    ep = synth.episode_batch(511, E, n_way, k, S, D)
+    gal = synth.gallery(512, G, D, centroid_seed=511)
+    cache = ev.GalleryFeatureCache(_cuda(gal))
+    pipe = ev.EpisodePipeline(cache, n_way, k, S, E)
+    r = pipe.run(_cuda(ep["probe"]), _cuda(ep["support_y"]), _cuda(ep["query"]))
+    assert pipe.ws.stats()["fallback_rows"] == 0
+    for e in range(E):
+        o = O.lib_episode(ep["probe"][e], ep["support_y"][e], ep["query"][e], gal)
+        assert np.array_equal(r["idx"][e].cpu().numpy(), o["ids"])
+        assert np.array_equal(r["score"][e].cpu().numpy(), o["t_win"])
+        assert np.array_equal(r["dist"][e, :, :n_way].cpu().numpy(), o["dist32"])
+        assert np.array_equal(r["pred"][e].cpu().numpy(), o["pred"])
+
+
 def test_segment_features():
     f = synth.frame_features(5, 64, 96)
     a = ev.segment_features(_cuda(f), 2, True).cpu().numpy()
