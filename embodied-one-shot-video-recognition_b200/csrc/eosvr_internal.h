@@ -21,8 +21,10 @@ constexpr int kIssuers = 3;       // MMA issuer warps 1..3 of the pair's leader;
                                   // (tools/bench_micro/mma_rate.cu): one thread sustains only ~1/3 of the MMA rate.
 constexpr int kAccStages = 2;     // TMEM accumulator double buffer (2 x 256 columns)
 constexpr int kTmemCols = 512;
-constexpr int kEpiWarps = 8;      // warps 4..11
-constexpr int kProdBWarp = 4 + kEpiWarps;   // warp 12: second TMA producer (probe operand); warp 0 loads the gallery
+constexpr int kEpiWarps = 8;      // warps 4..11: warp % 4 = TMEM lane quadrant, (warp - 4) / 4 = column group (12 warps at 96
+                                  // registers measured no faster: the epilogue is throughput-, not latency-bound)
+constexpr int kEpiGroups = kEpiWarps / 4;
+constexpr int kProdBWarp = 4 + kEpiWarps;   // second TMA producer (probe operand); warp 0 loads the gallery
 constexpr int kThreads = 128 + 32 * kEpiWarps + 32;
 static_assert(kStages % kIssuers == 0, "every stage barrier must have a single consumer warp");
 constexpr int kChunk = 16;        // TMEM columns per tcgen05.ld

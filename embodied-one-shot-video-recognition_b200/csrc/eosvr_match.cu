@@ -576,15 +576,14 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp >= 4 && warp < 4 + kEpiWarps) {
-        // ===== epilogue: 8 warps, warp%4 selects the TMEM lane quadrant, (warp-4)/4 the column half =====
+        // ===== epilogue: warp%4 selects the TMEM lane quadrant, (warp-4)/4 the group of column chunks =====
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
         const int te = threadIdx.x - 128;
         const int BN = p.BN;
         const int nchunks = BN / kChunk;
-        const int hc = (nchunks + 1) >> 1;
-        const int cbeg = half == 0 ? 0 : hc;
-        const int cend = half == 0 ? hc : nchunks;
+        const int cbeg = nchunks * half / kEpiGroups;
+        const int cend = nchunks * (half + 1) / kEpiGroups;
         const float xfloor = __uint_as_float(p.ctr->xfloor_bits);
         const float dfloor = sqrtf(xfloor) * 1.000001f;
         int acc = 0; uint32_t accphase = 0;
