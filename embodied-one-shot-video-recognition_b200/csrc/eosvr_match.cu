@@ -375,6 +375,17 @@ __device__ __forceinline__ bool decode_unit(const ScreenParams &p, int64_t u, Un
 // gallery tile against two different probe tiles: every CTA fetches half of its 128-row gallery slab and
 // multicasts it to the CTA of equal parity in the other pair, so the gallery operand crosses L2 -> SM once
 // per cluster instead of once per pair (the kernel is bound by operand delivery).
+// t[j] for a warp-uniform j without indexing the register array dynamically.
+__device__ __forceinline__ float pick16(const float (&t)[kChunk], int j)
+{
+    switch (j) {
+        case 0: return t[0];   case 1: return t[1];   case 2: return t[2];   case 3: return t[3];
+        case 4: return t[4];   case 5: return t[5];   case 6: return t[6];   case 7: return t[7];
+        case 8: return t[8];   case 9: return t[9];   case 10: return t[10]; case 11: return t[11];
+        case 12: return t[12]; case 13: return t[13]; case 14: return t[14]; default: return t[15];
+    }
+}
+
 // Store candidate (g, tbits) of probe row rm at list position pos; full lists spill to the shared buffer and only
 // if that is full too is the row handed to the exhaustive exact kernel.
 __device__ __forceinline__ void put_candidate(const ScreenParams &p, int32_t rm, unsigned pos, int32_t g, uint32_t tbits)
@@ -616,12 +627,14 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int32_t rm = tl->row[te];
                     if (rm >= 0) atomicMin(&tl->thr[te], *reinterpret_cast<volatile unsigned int *>(p.gthr + rm));
                 }
+                // this lane's gallery row and its squared norm: requested BEFORE waiting for the accumulator so the
+                // global-load latency hides behind the wait
+                const int64_t g = (gt * kPairM + rank * kBM + q * 32 + lane) * p.g_stride;
+                const float nb = p.gnorm[g];
                 long long t_e0 = 0;
                 if (prof) { const long long t0 = clock64(); mbar_wait(&tl->tfull[acc], accphase); t_e0 = clock64(); e_wait += t_e0 - t0; }
                 else mbar_wait(&tl->tfull[acc], accphase);
                 tc_fence_after();
-                const int64_t g = (gt * kPairM + rank * kBM + q * 32 + lane) * p.g_stride;
-                const float nb = p.gnorm[g];
                 const uint32_t trow = tmem_base + static_cast<uint32_t>(acc) * kMaxBN + (static_cast<uint32_t>(q * 32) << 16);
 
                 float dprev = kBig;
@@ -632,12 +645,16 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
                     continue;
                 }
-                if (cbeg > 0) {
-                    uint32_t v;
-                    tmem_ld_x1(trow + cbeg * kChunk - 1, v);
+                uint32_t va[kChunk], vb[kChunk];
+                {   // first chunk and (column group > 0) the left-hand neighbour of its first column: one wait for both
+                    uint32_t v = 0;
+                    if (cbeg > 0) tmem_ld_x1(trow + cbeg * kChunk - 1, v);
+                    tmem_ld_x16(trow + cbeg * kChunk, va);
                     tmem_ld_wait();
-                    const float x = fmaf(-2.f, __uint_as_float(v), nb) + tl->na[cbeg * kChunk - 1];
-                    dprev = sqrt_approx(fmaxf(x, 0.f));
+                    if (cbeg > 0) {
+                        const float x = fmaf(-2.f, __uint_as_float(v), nb) + tl->na[cbeg * kChunk - 1];
+                        dprev = sqrt_approx(fabsf(x));
+                    }
                 }
                 // One chunk of 16 accumulator columns.  `v` holds the chunk (already loaded); the NEXT chunk (or just its
                 // first column, the right-hand neighbour of column 15) is requested before the arithmetic on `v` starts
@@ -660,14 +677,14 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const int j = j4 * 4 + jj;
                             const float x = fmaf(-2.f, __uint_as_float(v[j]), nb) + aa[jj];
                             minx = fminf(minx, x);
-                            d[j] = sqrt_approx(fmaxf(x, 0.f));
+                            d[j] = sqrt_approx(fabsf(x));
                         }
                     }
                     tmem_ld_wait_x16(vnx);
                     float dn = kBig;
                     if (hasn) {
                         const float x = fmaf(-2.f, __uint_as_float(vnx[0]), nb) + tl->na[c0 + kChunk];
-                        dn = sqrt_approx(fmaxf(x, 0.f));
+                        dn = sqrt_approx(fabsf(x));
                     }
                     const float dprev_in = dprev;
                     dprev = d[kChunk - 1];
@@ -715,25 +732,34 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (guard) cm = 0xFFFFu;
                         cm = __reduce_or_sync(0xffffffffu, cm);
                         const bool rowok = g < p.G;
+                        const bool any_guard = __any_sync(0xffffffffu, guard);
 #pragma unroll 1
                         while (cm) {
                             const int c = c0 + __ffs(cm) - 1;              // warp-uniform
                             cm &= cm - 1;
                             const int32_t rm = tl->row[c];
                             if (rm < 0) continue;                          // warp-uniform
-                            uint32_t vc, vl = 0, vr = 0;
-                            const bool hl = c > 0, hr = c + 1 < BN;
-                            tmem_ld_x1(trow + c, vc);
-                            if (hl) tmem_ld_x1(trow + c - 1, vl);
-                            if (hr) tmem_ld_x1(trow + c + 1, vr);
-                            tmem_ld_wait();
-                            const float dj = sqrt_approx(fmaxf(fmaf(-2.f, __uint_as_float(vc), nb) + tl->na[c], 0.f));
-                            const float dl = hl ? sqrt_approx(fmaxf(fmaf(-2.f, __uint_as_float(vl), nb) + tl->na[c - 1], 0.f)) : kBig;
-                            const float dr = hr ? sqrt_approx(fmaxf(fmaf(-2.f, __uint_as_float(vr), nb) + tl->na[c + 1], 0.f)) : kBig;
-                            const float wlc = tl->wl[c], wrc = tl->wr[c];
-                            const float tj = fmaf(wlc, dl, fmaf(wrc, dr, dj));
-                            const float m3 = fminf(dj, fminf(wlc > 0.f ? dl : kBig, wrc > 0.f ? dr : kBig));
-                            const bool uns = rowok && (m3 < dfloor);
+                            float tj;
+                            bool uns = false;
+                            if (!any_guard) {
+                                tj = pick16(t, c - c0);                    // warp-uniform index: a jump, no local memory
+                            } else {
+                                // some lane is inside the cancellation guard: the column and its neighbours again,
+                                // straight from TMEM (same arithmetic, same bits as the fast path)
+                                uint32_t vc, vl = 0, vr = 0;
+                                const bool hl = c > 0, hr = c + 1 < BN;
+                                tmem_ld_x1(trow + c, vc);
+                                if (hl) tmem_ld_x1(trow + c - 1, vl);
+                                if (hr) tmem_ld_x1(trow + c + 1, vr);
+                                tmem_ld_wait();
+                                const float dj = sqrt_approx(fabsf(fmaf(-2.f, __uint_as_float(vc), nb) + tl->na[c]));
+                                const float dl = hl ? sqrt_approx(fabsf(fmaf(-2.f, __uint_as_float(vl), nb) + tl->na[c - 1])) : kBig;
+                                const float dr = hr ? sqrt_approx(fabsf(fmaf(-2.f, __uint_as_float(vr), nb) + tl->na[c + 1])) : kBig;
+                                const float wlc = tl->wl[c], wrc = tl->wr[c];
+                                tj = fmaf(wlc, dl, fmaf(wrc, dr, dj));
+                                const float m3 = fminf(dj, fminf(wlc > 0.f ? dl : kBig, wrc > 0.f ? dr : kBig));
+                                uns = rowok && (m3 < dfloor);
+                            }
                             float thr = __uint_as_float(*reinterpret_cast<volatile unsigned int *>(&tl->thr[c]));
                             bool pass = rowok && !uns && (tj <= thr);
                             if (__ballot_sync(0xffffffffu, pass)) {
@@ -772,14 +798,9 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 };
-                {
-                    uint32_t va[kChunk], vb[kChunk];
-                    tmem_ld_x16(trow + cbeg * kChunk, va);
-                    tmem_ld_wait();
-                    for (int ch = cbeg; ch < cend; ch += 2) {
-                        do_chunk(ch, va, vb);
-                        if (ch + 1 < cend) do_chunk(ch + 1, vb, va);
-                    }
+                for (int ch = cbeg; ch < cend; ch += 2) {
+                    do_chunk(ch, va, vb);
+                    if (ch + 1 < cend) do_chunk(ch + 1, vb, va);
                 }
                 tc_fence_before();
                 __syncwarp();
