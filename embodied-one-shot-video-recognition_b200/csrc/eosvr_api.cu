@@ -1,5 +1,6 @@
 // eosvr_api.cu -- the extern "C" surface declared in include/eosvr.h.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -163,6 +164,7 @@ int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtyp
     int64_t st_tiles = GT / 24;
     if (st_tiles < 1) st_tiles = 1;
     if (st_tiles > kMaxSeedTiles) st_tiles = kMaxSeedTiles;
+    { const char *e = getenv("EOSVR_SEED_TILES"); if (e && atoi(e) > 0 && atoi(e) <= GT) st_tiles = atoi(e); }   // experiments
     g->seed_tiles = static_cast<int32_t>(st_tiles);
     g->seed_stride = Gpad / (st_tiles * kPairM);
     if (g->seed_stride > 1 && (g->seed_stride & 1) == 0) g->seed_stride -= 1;

@@ -9,13 +9,16 @@
 //      consecutive registers: the temporal 3-tap is register-local.  The epilogue forms
 //      d = sqrt(|a|^2 + |b|^2 - 2 a.b), the taps, and compares against a per-probe running
 //      threshold (min so far + rigorous error margin); the few elements below it are
-//      appended to a candidate list.
-//   2. EXACT RE-RANK (k_rerank): every candidate is re-evaluated on CUDA cores exactly as
-//      the reference does (float64 direct differences, float32 cast, float32 FMA chain) and
-//      merged with a packed 64-bit atomicMin whose low word is the gallery index, which
-//      gives the lowest-index tie rule for free.
-// The error margin guarantees the true winner (and every exact tie) is among the candidates,
-// so indices and scores are bit-equal to the reference, not merely close.
+//      appended to a candidate list.  13 warps per CTA: 2 TMA producers, 3 MMA issuers (one
+//      issuing thread cannot keep the tensor pipe fed), 8 epilogue warps.
+//   2. EXACT RE-RANK (k_rerank_rows): candidates are first evaluated with float32 direct
+//      differences (an error bound orders of magnitude tighter than the 16-bit screening) and
+//      the float32 near-ties -- normally one per row -- exactly as the reference does (float64
+//      direct differences, float32 cast, float32 FMA chain), merged with a packed 64-bit
+//      atomicMin whose low word is the gallery index: the lowest-index tie rule for free.
+// The error margins guarantee the true winner (and every exact tie) is evaluated exactly, so
+// indices and scores are bit-equal to the reference, not merely close.  The cosine metric
+// (EOSVR_METRIC_COSINE) runs the same kernels on L2-normalised screening copies.
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <math.h>
