@@ -873,6 +873,7 @@ struct RerankParams {
     const float *margin;     // per plan column
     int32_t planR, planBN, planHalo;
     int32_t prof;            // EOSVR_EXP bit 64: phase timing of k_rerank_rows into the cycle counters
+    int32_t rows_per_block;  // consecutive probe rows per k_rerank_rows block (1..kRrRowsPerBlock)
 };
 
 // Cosine metric, exactly: float64 dot / (|a| |b|) on the original rows (0 for a zero row), rounded to
@@ -1002,7 +1003,8 @@ k_rerank_rows(const RerankParams p)
     unsigned long long appended = 0, done = 0, unsafe_n = 0;
     const float inv_lam2 = 1.0f / p.lam2;
     const float4 *probes4 = reinterpret_cast<const float4 *>(p.probes);
-    const int64_t nblk = (p.P + kRrRowsPerBlock - 1) / kRrRowsPerBlock;
+    const int rpb = p.rows_per_block;
+    const int64_t nblk = (p.P + rpb - 1) / rpb;
     unsigned long long c_setup = 0, c_sort = 0, c_p1 = 0, c_p2 = 0;   // tid 0, p.prof only
     long long tk = p.prof ? clock64() : 0;
 #define RR_MARK(acc) do { if (p.prof && tid == 0) { const long long now = clock64(); acc += now - tk; tk = now; } } while (0)
@@ -1018,7 +1020,7 @@ k_rerank_rows(const RerankParams p)
     };
 
     for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-      const int64_t r0 = blk * kRrRowsPerBlock, r1 = min(p.P, r0 + kRrRowsPerBlock);
+      const int64_t r0 = blk * rpb, r1 = min(p.P, r0 + rpb);
       const int64_t last_needed = COS ? r1 - 1 : min(r1, p.P - 1);      // last probe row this block reads
       __syncthreads();                                  // the previous block's rows are done with the ring
       if (tid < r1 - r0) {
@@ -1452,6 +1454,7 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
     rp.ovf = ws->ovf; rp.ovf_cap = static_cast<int32_t>(ws->ovf_cap);
     rp.margin = ws->margin; rp.planR = pl.R; rp.planBN = pl.BN; rp.planHalo = pl.halo;
     { const char *e = getenv("EOSVR_EXP"); rp.prof = (e && (atoi(e) & 64)) ? 1 : 0; }
+    rp.rows_per_block = 1;
 
     ws->last_tiles = 0;
     ws->last_bn = pl.BN;
@@ -1486,7 +1489,12 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
         if (rc) return rc;
         ws->last_tiles = pl.NT * GT;
 
-        const int64_t rr_blocks = (P + kRrRowsPerBlock - 1) / kRrRowsPerBlock;
+        // few probe rows (a single episode): one row per block keeps the call's latency low; large batches take 8
+        // consecutive rows per block so that neighbouring probe rows are staged once
+        int64_t rpb = P / (static_cast<int64_t>(g_num_sms) * 8);
+        rpb = rpb < 1 ? 1 : (rpb > kRrRowsPerBlock ? kRrRowsPerBlock : rpb);
+        rp.rows_per_block = static_cast<int32_t>(rpb);
+        const int64_t rr_blocks = (P + rpb - 1) / rpb;
         const unsigned rr_grid = static_cast<unsigned>(rr_blocks < static_cast<int64_t>(g_num_sms) * 32 ? rr_blocks : g_num_sms * 32);
         const size_t rr_smem = static_cast<size_t>(cosm ? 2 : 4) * g->D * sizeof(float);
         if ((g->D & 3) == 0 && rr_smem <= 96 * 1024) {
