@@ -25,7 +25,9 @@ constexpr int kEpiWarps = 8;      // warps 4..11: warp % 4 = TMEM lane quadrant,
                                   // registers measured no faster: the epilogue is throughput-, not latency-bound)
 constexpr int kEpiGroups = kEpiWarps / 4;
 constexpr int kProdBWarp = 4 + kEpiWarps;   // second TMA producer (probe operand); warp 0 loads the gallery
-constexpr int kThreads = 128 + 32 * kEpiWarps + 32;
+constexpr int kTwoProducers = 1;  // 1: warp 4+kEpiWarps issues the probe-operand loads.  0 (one producer thread, 12 warps, 164
+                                  // registers) measured 3-5 % slower at D = 2048 (operand waits) and no faster at D = 512
+constexpr int kThreads = 128 + 32 * kEpiWarps + 32 * kTwoProducers;
 static_assert(kStages % kIssuers == 0, "every stage barrier must have a single consumer warp");
 constexpr int kChunk = 16;        // TMEM columns per tcgen05.ld
 constexpr int kMaxSeedTiles = 2;  // strided gallery tiles screened first to seed the per-probe thresholds
@@ -70,6 +72,7 @@ struct Counters {
     unsigned int ovf_count;          // entries appended to the shared spill-over buffer
     // cycle accounting of the screening kernel (EOSVR_EXP bit 16; measurement only), summed over CTAs
     unsigned long long cyc_epi_busy, cyc_epi_wait, cyc_mma_wait_full, cyc_mma_wait_acc, cyc_prod_wait, cyc_total;
+    unsigned long long cyc_epi_first, cyc_epi_chunks, cyc_epi_tail;   // split of cyc_epi_busy: first TMEM load, chunk loop, release
 };
 
 }  // namespace eosvr

@@ -464,11 +464,11 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool prof = (p.exp_mode & 16) != 0;
 
     // Producer and issuer warps run their loops with the whole warp; lane 0 issues.
-    if (warp == 0 || warp == kProdBWarp) {
+    if (warp == 0 || (kTwoProducers && warp == kProdBWarp)) {
         // ===== TMA producers (every CTA): warp 0 loads the CTA's gallery rows (A), warp 12 its half of the pair's
         //       probe tile (B) -- a UTMALDG occupies its issuing thread for ~150 cycles, so one thread per operand.
         //       Warp 0 also posts the byte count of the whole stage. =====
-        const bool isA = warp == 0;
+        const bool isA = warp == 0, isB = kTwoProducers ? warp == kProdBWarp : true;   // one warp may play both roles
         int stage = 0; uint32_t phase = 0;
         const int32_t bhalf = p.BN >> 1;
         const uint32_t tx_cta = kABytes + static_cast<uint32_t>(bhalf) * kBK * 2;
@@ -499,7 +499,7 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int sb = 0; sb < nsub; ++sb) {
                                 const int32_t kc = (ks * kSub + sb) * kBK;
                                 if (isA) tma_load_2d_2sm(sA + stage * kAStage + sb * kABytes, &tmA, lbar, kc, arow);
-                                else tma_load_2d_2sm(sB + stage * kBStage + sb * kBBytes, &tmB, lbar, kc, brow);
+                                if (isB) tma_load_2d_2sm(sB + stage * kBStage + sb * kBBytes, &tmB, lbar, kc, brow);
                             }
                         } else {
                             if (isA) mbar_arrive_expect_tx(&tl->full[stage], tx_cta * nsub);
@@ -507,7 +507,7 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 const int32_t kc = (ks * kSub + sb) * kBK;
                                 if (isA) tma_load_2d_mc(sA + stage * kAStage + sb * kABytes + pq * (kABytes / NP), &tmA,
                                                         &tl->full[stage], kc, arow, mc_mask);
-                                else tma_load_2d(sB + stage * kBStage + sb * kBBytes, &tmB, &tl->full[stage], kc, brow);
+                                if (isB) tma_load_2d(sB + stage * kBStage + sb * kBBytes, &tmB, &tl->full[stage], kc, brow);
                             }
                         }
                     }
