@@ -358,7 +358,7 @@ int eosvr_match_stats(eosvr_workspace_t *ws, void *stream, int64_t out[8])
     return EOSVR_OK;
 }
 
-int eosvr_workspace_debug_cycles(eosvr_workspace_t *ws, void *stream, int64_t out[9])
+int eosvr_workspace_debug_cycles(eosvr_workspace_t *ws, void *stream, int64_t out[6])
 {
     if (!ws || !out) { set_error("debug_cycles: NULL argument"); return EOSVR_EINVAL; }
     Counters c;
@@ -367,8 +367,6 @@ int eosvr_workspace_debug_cycles(eosvr_workspace_t *ws, void *stream, int64_t ou
     out[0] = static_cast<int64_t>(c.cyc_epi_busy); out[1] = static_cast<int64_t>(c.cyc_epi_wait);
     out[2] = static_cast<int64_t>(c.cyc_mma_wait_full); out[3] = static_cast<int64_t>(c.cyc_mma_wait_acc);
     out[4] = static_cast<int64_t>(c.cyc_prod_wait); out[5] = static_cast<int64_t>(c.cyc_total);
-    out[6] = static_cast<int64_t>(c.cyc_epi_first); out[7] = static_cast<int64_t>(c.cyc_epi_chunks);
-    out[8] = static_cast<int64_t>(c.cyc_epi_tail);
     return EOSVR_OK;
 }
 

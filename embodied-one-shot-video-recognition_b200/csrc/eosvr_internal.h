@@ -72,7 +72,6 @@ struct Counters {
     unsigned int ovf_count;          // entries appended to the shared spill-over buffer
     // cycle accounting of the screening kernel (EOSVR_EXP bit 16; measurement only), summed over CTAs
     unsigned long long cyc_epi_busy, cyc_epi_wait, cyc_mma_wait_full, cyc_mma_wait_acc, cyc_prod_wait, cyc_total;
-    unsigned long long cyc_epi_first, cyc_epi_chunks, cyc_epi_tail;   // split of cyc_epi_busy: first TMEM load, chunk loop, release
 };
 
 }  // namespace eosvr

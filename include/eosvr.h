@@ -215,9 +215,8 @@ int eosvr_workspace_set_debug(eosvr_workspace_t *ws, float *d_dump, int64_t elem
 /* Cycle accounting of the last screening kernel when the environment variable EOSVR_EXP has bit 16 set
  * (measurement only; sums over CTAs): out = {epilogue busy, epilogue waiting for accumulators, MMA issuer
  * waiting for operands, MMA issuer waiting for a free accumulator, TMA producers waiting for a free stage,
- * kernel cycles summed over pair leaders, and the split of "epilogue busy" into first TMEM load / chunk loop /
- * accumulator release}. */
-int eosvr_workspace_debug_cycles(eosvr_workspace_t *ws, void *stream, int64_t out[9]);
+ * kernel cycles summed over pair leaders}. */
+int eosvr_workspace_debug_cycles(eosvr_workspace_t *ws, void *stream, int64_t out[6]);
 
 #ifdef __cplusplus
 }
