@@ -275,7 +275,6 @@ __global__ void k_reset(Counters *ctr, unsigned long long *best, int32_t *rowfla
         ctr->overflow = flag_all ? 1u : 0u; ctr->n_flag_rows = 0; ctr->xfloor_bits = 0; ctr->ovf_count = 0;
         ctr->cyc_epi_busy = ctr->cyc_epi_wait = ctr->cyc_mma_wait_full = ctr->cyc_mma_wait_acc = 0;
         ctr->cyc_prod_wait = ctr->cyc_total = 0;
-        ctr->cyc_epi_first = ctr->cyc_epi_chunks = ctr->cyc_epi_tail = 0;
     }
     if (i < P) { best[i] = ~0ull; rowflag[i] = flag_all; rowcnt[i] = 0; gthr[i] = 0x7f800000u; }
 }
@@ -604,7 +603,7 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int acc = 0; uint32_t accphase = 0;
         const uint32_t tempty_leader0 = mapa(smem_u32(&tl->tempty[0]), leader);
         const uint32_t tempty_leader1 = mapa(smem_u32(&tl->tempty[1]), leader);
-        unsigned long long e_busy = 0, e_wait = 0, e_first = 0, e_chunks = 0, e_tail = 0;
+        unsigned long long e_busy = 0, e_wait = 0;
         StagedCand *wstage = tl->stage[warp - 4];
         int wn = 0;                                       // candidates parked by this warp (warp-uniform)
         for (int64_t u = pair; u < p.n_units; u += npairs) {
@@ -660,8 +659,6 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         dprev = sqrt_approx(fabsf(x));
                     }
                 }
-                long long t_e1 = 0;
-                if (prof) { t_e1 = clock64(); e_first += t_e1 - t_e0; }
                 // One chunk of 16 accumulator columns.  `v` holds the chunk (already loaded); the NEXT chunk (or just its
                 // first column, the right-hand neighbour of column 15) is requested before the arithmetic on `v` starts
                 // and waited for only when the taps need it, so the TMEM read latency overlaps the sqrt chain.
@@ -808,21 +805,15 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     do_chunk(ch, va, vb);
                     if (ch + 1 < cend) do_chunk(ch + 1, vb, va);
                 }
-                long long t_e2 = 0;
-                if (prof) { t_e2 = clock64(); e_chunks += t_e2 - t_e1; }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
                 if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
-                if (prof) { const long long now = clock64(); e_busy += now - t_e0; e_tail += now - t_e2; }
+                if (prof) e_busy += clock64() - t_e0;
             }
         }
         if (wn) flush_staged(p, wstage, wn, lane);
-        if (prof && lane == 0) {
-            atomicAdd(&p.ctr->cyc_epi_busy, e_busy); atomicAdd(&p.ctr->cyc_epi_wait, e_wait);
-            atomicAdd(&p.ctr->cyc_epi_first, e_first); atomicAdd(&p.ctr->cyc_epi_chunks, e_chunks);
-            atomicAdd(&p.ctr->cyc_epi_tail, e_tail);
-        }
+        if (prof && lane == 0) { atomicAdd(&p.ctr->cyc_epi_busy, e_busy); atomicAdd(&p.ctr->cyc_epi_wait, e_wait); }
     }
 
     tc_fence_before();

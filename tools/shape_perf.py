@@ -57,9 +57,6 @@ for name, P, rpe, D, G in SHAPES:
         print("   cycles/pair %.0f: epi_busy %.3f epi_wait %.3f mma_wait_full(/3 issuers) %.3f mma_wait_acc %.3f prod_wait %.3f"
               % (tot, c["epi_busy"] / (148 * 8) / tot, c["epi_wait"] / (148 * 8) / tot, c["mma_wait_full"] / 74 / 3 / tot,
                  c["mma_wait_acc"] / 74 / tot, c["prod_wait"] / 148 / tot), flush=True)
-        eb = max(c["epi_busy"], 1)
-        print("   epilogue busy split: first load %.3f  chunk loop %.3f  release %.3f"
-              % (c["epi_first"] / eb, c["epi_chunks"] / eb, c["epi_tail"] / eb), flush=True)
     if int(os.environ.get("EOSVR_EXP", "0")) & 64:
         c = ws.debug_cycles()
         tot = c["epi_busy"] + c["epi_wait"] + c["mma_wait_full"] + c["mma_wait_acc"]
