@@ -1,0 +1,38 @@
+"""bench.py contract (CPU part): the reference arm prints ONE JSON line with the keys the driver reads, on the
+same metric / unit / workload as the GPU arm; ranks other than 0 print nothing and exit 0."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(env_extra=None):
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                           "--warmup", "0"], capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
+
+
+def test_reference_arm_line():
+    r = _run()
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference"
+    assert d["metric"] == "gallery_segment_comparisons_per_s" and d["unit"] == "comparisons/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["config"]["workload"].startswith("cfg-2 UnrealAction-shaped 14-way 1-shot")
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"]["workload"] == bench.WORKLOAD and d["metric"] == bench.METRIC
+
+
+def test_reference_arm_other_ranks_are_silent():
+    r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
