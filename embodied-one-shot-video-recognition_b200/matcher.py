@@ -325,8 +325,11 @@ def temporal_smooth(dist64: torch.Tensor, rows_per_episode: int | None = None, l
     return out
 
 
-def cosine_predict(support: torch.Tensor, query: torch.Tensor, want_sim: bool = False, stream=None):
-    """classifier.py:117-120 for E episodes: support [E,R,D], query [E,Q,D] -> best support-row index [E,Q]."""
+def cosine_predict(support: torch.Tensor, query: torch.Tensor, want_sim: bool = False, stream=None,
+                   support_y: torch.Tensor | None = None):
+    """classifier.py:117-120 for E episodes: support [E,R,D], query [E,Q,D] -> best support-row index [E,Q]
+    (the reference returns the ROW index, not its label).  With support_y [E,R] the label of
+    that row is returned instead (the label-correct variant)."""
     support, query = _dev_f32(support, "support"), _dev_f32(query, "query")
     E, R, D = (int(x) for x in support.shape)
     Q = int(query.shape[1])
@@ -335,6 +338,8 @@ def cosine_predict(support: torch.Tensor, query: torch.Tensor, want_sim: bool = 
     with torch.cuda.device(support.device):
         check(lib().eosvr_cosine_predict(_ptr(support), _ptr(query), E, R, Q, D, _ptr(sim), _ptr(best),
                                          _stream_ptr(stream)), "eosvr_cosine_predict")
+    if support_y is not None:
+        best = torch.gather(support_y.to(best.device), 1, best)          # row index -> its label (plumbing only)
     return (best, sim) if want_sim else best
 
 

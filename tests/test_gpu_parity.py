@@ -457,6 +457,18 @@ def test_cfg5_shape_5way5shot_8seg_2048d():
         assert np.array_equal(r["pred"][e].cpu().numpy(), o["pred"])
 
 
+def test_cosine_predict_rows_and_labels(golden_dir):
+    """Classifier('cosine'): the reference returns the best SUPPORT ROW index (golden); the label-correct variant
+    maps it to the row's label."""
+    fx = np.load(os.path.join(golden_dir, "golden_classifier.npz"), allow_pickle=False)
+    for c in range(int(fx["n_cases"])):
+        sup, y, q = fx[f"c{c}_sup"], fx[f"c{c}_y"], fx[f"c{c}_q"]
+        rows = ev.cosine_predict(_cuda(sup)[None], _cuda(q)[None])
+        assert np.array_equal(rows[0].cpu().numpy(), fx[f"c{c}_pred_cosine"])
+        lab = ev.cosine_predict(_cuda(sup)[None], _cuda(q)[None], support_y=_cuda(y)[None])
+        assert np.array_equal(lab[0].cpu().numpy(), y[fx[f"c{c}_pred_cosine"]])
+
+
 def test_segment_features():
     f = synth.frame_features(5, 64, 96)
     a = ev.segment_features(_cuda(f), 2, True).cpu().numpy()
