@@ -20,6 +20,9 @@ constexpr int kIssuers = 3;       // MMA issuer warps 1..3 of the pair's leader;
                                   // A tcgen05.commit blocks its thread for ~600 cycles and a UTCHMMA for ~70
                                   // (tools/bench_micro/mma_rate.cu): one thread sustains only ~1/3 of the MMA rate.
 constexpr int kAccStages = 2;     // TMEM accumulator double buffer (2 x 256 columns)
+constexpr bool kZeroAcc = true;   // every MMA accumulates; the epilogue zeroes the accumulator behind itself.  false: the
+                                  // tile's first stage overwrites and the other issuers wait for its completion (a
+                                  // ~600-cycle bubble per tile)
 constexpr int kTmemCols = 512;
 constexpr int kEpiWarps = 8;      // warps 4..11: warp % 4 = TMEM lane quadrant, (warp - 4) / 4 = column group (12 warps at 96
                                   // registers measured no faster: the epilogue is throughput-, not latency-bound)

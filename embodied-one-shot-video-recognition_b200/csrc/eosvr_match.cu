@@ -522,9 +522,10 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp >= 1 && warp <= kIssuers && rank == 0) {
         // ===== MMA issuers: kIssuers warps of the pair's leader drive the tensor cores of both SMs, taking the
-        //       pipeline stages round-robin (stage s -> issuer s % kIssuers) into the same accumulator.  The first
-        //       stage of a tile overwrites the accumulator: its owner commits to tfirst[acc] and the other warps wait
-        //       for that before accumulating on top.  Every issuer observes every phase of tempty / tfirst. =====
+        //       pipeline stages round-robin (stage s -> issuer s % kIssuers) into the same accumulator.  kZeroAcc:
+        //       every MMA accumulates onto an accumulator the epilogue left zeroed.  Otherwise the first stage of a
+        //       tile overwrites the accumulator: its owner commits to tfirst[acc] and the other warps wait for that
+        //       before accumulating on top.  Every issuer observes every phase of tempty / tfirst. =====
         const int w = warp - 1;
         int64_t seq = 0;                                  // running stage number of this pair
         int acc = 0; uint32_t accphase = 0;
@@ -537,9 +538,11 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (!decode_unit(p, u, it)) continue;
             for (int64_t gt = it.gt0; gt < it.gt1; ++gt) {
                 const bool first_owner = static_cast<int>(seq % kIssuers) == w;   // issues the overwriting stage
-                if (prof) { const long long t0 = clock64(); mbar_wait(&tl->tempty[acc], accphase ^ 1); w_acc += clock64() - t0; }
-                else mbar_wait(&tl->tempty[acc], accphase ^ 1);
-                if (!first_owner) mbar_wait(&tl->tfirst[acc], accphase);
+                // kZeroAcc: phase 0 of tempty is the epilogue's initial zeroing, phase k+1 the release after the k-th use
+                const uint32_t epar = kZeroAcc ? accphase : (accphase ^ 1);
+                if (prof) { const long long t0 = clock64(); mbar_wait(&tl->tempty[acc], epar); w_acc += clock64() - t0; }
+                else mbar_wait(&tl->tempty[acc], epar);
+                if (!kZeroAcc && !first_owner) mbar_wait(&tl->tfirst[acc], accphase);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * kMaxBN;
                 for (int ks = 0; ks < KS; ++ks, ++seq) {
@@ -559,15 +562,15 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 for (int k = 0; k < kBK / 16; ++k)
                                     mma_f16_ss_2sm(d_tmem, umma_desc_sw128(a0 + sb * kABytes, k * 32),
                                                    umma_desc_sw128(b0 + sb * kBBytes, k * 32), p.idesc,
-                                                   (ks | sb | k) != 0 ? 1u : 0u);
+                                                   (kZeroAcc || (ks | sb | k) != 0) ? 1u : 0u);
                             }
                         }
                         mma_commit_2sm(&tl->empty[stage], all_mask);    // one of the NP arrivals that free the stage
-                        if (ks == 0) mma_commit_2sm(&tl->tfirst[acc], self_mask);
+                        if (!kZeroAcc && ks == 0) mma_commit_2sm(&tl->tfirst[acc], self_mask);
                     }
                     __syncwarp();
                 }
-                if (first_owner) mbar_wait(&tl->tfirst[acc], accphase);     // long complete; keeps the phase observed
+                if (!kZeroAcc && first_owner) mbar_wait(&tl->tfirst[acc], accphase);   // long complete; keeps the phase observed
                 if (lane == 0) mma_commit_2sm(&tl->tfull[acc], pair_mask);   // this warp's share of the tile is done
                 __syncwarp();
                 if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
@@ -604,6 +607,18 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t tempty_leader0 = mapa(smem_u32(&tl->tempty[0]), leader);
         const uint32_t tempty_leader1 = mapa(smem_u32(&tl->tempty[1]), leader);
         unsigned long long e_busy = 0, e_wait = 0;
+        if (kZeroAcc) {
+            // column group `half` of this lane quadrant zeroes accumulator `half`; every warp then reports both
+            // accumulators (a barrier completes only when all 2*kEpiWarps warps of the pair have arrived)
+            static_assert(!kZeroAcc || kEpiGroups == kAccStages, "initial zeroing: one column group per accumulator");
+            const uint32_t tz = tmem_base + static_cast<uint32_t>(half) * kMaxBN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < kMaxBN; c += kChunk) tmem_st_zero_x16(tz + c);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive_cluster(tempty_leader0); mbar_arrive_cluster(tempty_leader1); }
+        }
         StagedCand *wstage = tl->stage[warp - 4];
         int wn = 0;                                       // candidates parked by this warp (warp-uniform)
         for (int64_t u = pair; u < p.n_units; u += npairs) {
@@ -649,15 +664,18 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     continue;
                 }
                 uint32_t va[kChunk], vb[kChunk];
-                {   // first chunk and (column group > 0) the left-hand neighbour of its first column: one wait for both
-                    uint32_t v = 0;
-                    if (cbeg > 0) tmem_ld_x1(trow + cbeg * kChunk - 1, v);
+                uint32_t vleft = 0, vright = 0;          // the neighbouring column groups' boundary columns
+                {   // first chunk and the boundary columns of the neighbouring column groups: one wait for all
+                    if (cbeg > 0) tmem_ld_x1(trow + cbeg * kChunk - 1, vleft);
+                    if (cend * kChunk < BN) tmem_ld_x1(trow + cend * kChunk, vright);
                     tmem_ld_x16(trow + cbeg * kChunk, va);
                     tmem_ld_wait();
                     if (cbeg > 0) {
-                        const float x = fmaf(-2.f, __uint_as_float(v), nb) + tl->na[cbeg * kChunk - 1];
+                        const float x = fmaf(-2.f, __uint_as_float(vleft), nb) + tl->na[cbeg * kChunk - 1];
                         dprev = sqrt_approx(fabsf(x));
                     }
+                    // kZeroAcc: nobody zeroes a column before every warp of the lane quadrant holds its boundary reads
+                    if (kZeroAcc) named_bar_sync(2 + q, 32 * kEpiGroups);
                 }
                 // One chunk of 16 accumulator columns.  `v` holds the chunk (already loaded); the NEXT chunk (or just its
                 // first column, the right-hand neighbour of column 15) is requested before the arithmetic on `v` starts
@@ -666,7 +684,7 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int c0 = ch * kChunk;
                     const bool hasn = (c0 + kChunk) < BN;
                     if (ch + 1 < cend) tmem_ld_x16(trow + c0 + kChunk, vnx);
-                    else if (hasn) tmem_ld_x1(trow + c0 + kChunk, vnx[0]);
+                    else vnx[0] = vright;
 
                     float d[kChunk];
                     float minx = kBig;
@@ -752,9 +770,11 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 uint32_t vc, vl = 0, vr = 0;
                                 const bool hl = c > 0, hr = c + 1 < BN;
                                 tmem_ld_x1(trow + c, vc);
-                                if (hl) tmem_ld_x1(trow + c - 1, vl);
-                                if (hr) tmem_ld_x1(trow + c + 1, vr);
+                                if (hl && c != cbeg * kChunk) tmem_ld_x1(trow + c - 1, vl);
+                                if (hr && c + 1 != cend * kChunk) tmem_ld_x1(trow + c + 1, vr);
                                 tmem_ld_wait();
+                                if (c == cbeg * kChunk) vl = vleft;                 // other column groups' columns may
+                                if (c + 1 == cend * kChunk) vr = vright;            // already be zeroed: use the early reads
                                 const float dj = sqrt_approx(fabsf(fmaf(-2.f, __uint_as_float(vc), nb) + tl->na[c]));
                                 const float dl = hl ? sqrt_approx(fabsf(fmaf(-2.f, __uint_as_float(vl), nb) + tl->na[c - 1])) : kBig;
                                 const float dr = hr ? sqrt_approx(fabsf(fmaf(-2.f, __uint_as_float(vr), nb) + tl->na[c + 1])) : kBig;
@@ -803,8 +823,15 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 };
                 for (int ch = cbeg; ch < cend; ch += 2) {
                     do_chunk(ch, va, vb);
-                    if (ch + 1 < cend) do_chunk(ch + 1, vb, va);
+                    // zero one chunk behind: the rare path of chunk ch may still read the last column of chunk ch - 1
+                    if (kZeroAcc && ch > cbeg) tmem_st_zero_x16(trow + (ch - 1) * kChunk);
+                    if (ch + 1 < cend) {
+                        do_chunk(ch + 1, vb, va);
+                        if (kZeroAcc) tmem_st_zero_x16(trow + ch * kChunk);
+                    }
                 }
+                if (kZeroAcc && cend > cbeg) { tmem_st_zero_x16(trow + (cend - 1) * kChunk); tmem_st_wait(); }   // (a column
+                                                                          // group is empty when the tile has one chunk)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);

@@ -159,6 +159,21 @@ __device__ __forceinline__ void tmem_ld_wait_x16(uint32_t (&v)[16])
                  : "memory");
 }
 
+// registers -> TMEM: zero this warp's 32 lanes x 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_zero_x16(uint32_t taddr)
+{
+    const uint32_t z = 0;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+        ::"r"(taddr), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait()
+{
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // ---- CTA pair (cluster of 2, cta_group::2) -------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
