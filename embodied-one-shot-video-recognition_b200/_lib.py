@@ -21,7 +21,9 @@ class EosvrError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libeosvr.so")
+    """The in-tree library; EOSVR_LIB_PATH selects another build of it (tools/exp_perf.sh measures with a
+    -DEOSVR_EXPERIMENTS build)."""
+    return os.environ.get("EOSVR_LIB_PATH") or os.path.join(_HERE, "libeosvr.so")
 
 
 _c = ctypes

@@ -3,6 +3,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <new>
 
@@ -11,7 +12,8 @@
 namespace eosvr {
 
 static thread_local char g_err[512] = "";
-unsigned long long g_launches = 0;
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...)
 {
@@ -92,9 +94,7 @@ int build_cosine_copy(eosvr_gallery *g, cudaStream_t st)
     const uint64_t rows = static_cast<uint64_t>(Gpad), cols = static_cast<uint64_t>(g->Dp);
     const uint64_t srows = static_cast<uint64_t>(g->seed_tiles) * kPairM, sstr = static_cast<uint64_t>(g->seed_stride);
     if (!rc) rc = encode_tmap_2d(&c->tmapA, c->h16, g->screen_fmt, rows, cols, kBM, kBK, 1);
-    if (!rc) rc = encode_tmap_2d(&c->tmapAH, c->h16, g->screen_fmt, rows, cols, kBM / 2, kBK, 1);
     if (!rc) rc = encode_tmap_2d(&c->tmapSeed, c->h16, g->screen_fmt, srows, cols, kBM, kBK, sstr);
-    if (!rc) rc = encode_tmap_2d(&c->tmapSeedH, c->h16, g->screen_fmt, srows, cols, kBM / 2, kBK, sstr);
     if (!rc && cudaEventRecord(c->ready, st) != cudaSuccess) { set_error("cudaEventRecord failed"); rc = EOSVR_ECUDA; }
     if (rc) { free_screen_copy(c); return rc; }
     g->cos = c;
@@ -157,7 +157,6 @@ int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtyp
     }
     rc = launch_gallery_prep(g, static_cast<cudaStream_t>(stream));
     if (!rc) rc = encode_tmap_2d(&g->tmapA, g->h16, screen_fmt, static_cast<uint64_t>(Gpad), static_cast<uint64_t>(g->Dp), kBM, kBK, 1);
-    if (!rc) rc = encode_tmap_2d(&g->tmapAH, g->h16, screen_fmt, static_cast<uint64_t>(Gpad), static_cast<uint64_t>(g->Dp), kBM / 2, kBK, 1);
     // strided seed sample: seed_tiles tiles of rows {0, stride, 2*stride, ...}
     // (an ODD stride so that periodic class layouts of the gallery cannot alias with the sample)
     const int64_t GT = Gpad / kPairM;
@@ -170,8 +169,6 @@ int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtyp
     if (g->seed_stride > 1 && (g->seed_stride & 1) == 0) g->seed_stride -= 1;
     if (!rc) rc = encode_tmap_2d(&g->tmapSeed, g->h16, screen_fmt, static_cast<uint64_t>(st_tiles * kPairM),
                                  static_cast<uint64_t>(g->Dp), kBM, kBK, static_cast<uint64_t>(g->seed_stride));
-    if (!rc) rc = encode_tmap_2d(&g->tmapSeedH, g->h16, screen_fmt, static_cast<uint64_t>(st_tiles * kPairM),
-                                 static_cast<uint64_t>(g->Dp), kBM / 2, kBK, static_cast<uint64_t>(g->seed_stride));
     if (rc) { eosvr_gallery_destroy(g); return rc; }
     *out = g;
     return EOSVR_OK;
@@ -219,9 +216,9 @@ int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capac
     auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_q = carve(static_cast<size_t>(ws->cap_rows) * ws->Dp * 2);
     const size_t o_na = carve(ws->cap_rows * 4), o_wl = carve(ws->cap_rows * 4), o_wr = carve(ws->cap_rows * 4);
-    const size_t o_mg = carve(ws->cap_rows * 4), o_ep = carve(ws->cap_rows * 4), o_rm = carve(ws->cap_rows * 4);
+    const size_t o_ep = carve(ws->cap_rows * 4), o_rm = carve(ws->cap_rows * 4);
     const size_t o_thr = carve(ws->maxP * 4), o_best = carve(ws->maxP * 8), o_rf = carve(ws->maxP * 4);
-    const size_t o_fl = carve(ws->maxP * 4), o_rc = carve(ws->maxP * 4);
+    const size_t o_rc = carve(ws->maxP * 4);
     const size_t o_cd = carve(static_cast<size_t>(ws->maxP) * ws->cand_cap * sizeof(Cand)), o_ct = carve(sizeof(Counters));
     ws->ovf_cap = ws->maxP * 16 > (1ll << 16) ? ws->maxP * 16 : (1ll << 16);
     const size_t o_ov = carve(static_cast<size_t>(ws->ovf_cap) * sizeof(OvfCand));
@@ -235,10 +232,10 @@ int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capac
     char *b = static_cast<char *>(ws->slab);
     ws->q16 = b + o_q;
     ws->na = reinterpret_cast<float *>(b + o_na); ws->wl = reinterpret_cast<float *>(b + o_wl);
-    ws->wr = reinterpret_cast<float *>(b + o_wr); ws->margin = reinterpret_cast<float *>(b + o_mg);
+    ws->wr = reinterpret_cast<float *>(b + o_wr);
     ws->epsd = reinterpret_cast<float *>(b + o_ep); ws->rowmap = reinterpret_cast<int32_t *>(b + o_rm);
     ws->gthr = reinterpret_cast<unsigned int *>(b + o_thr); ws->best = reinterpret_cast<unsigned long long *>(b + o_best);
-    ws->rowflag = reinterpret_cast<int32_t *>(b + o_rf); ws->flaglist = reinterpret_cast<int32_t *>(b + o_fl);
+    ws->rowflag = reinterpret_cast<int32_t *>(b + o_rf);
     ws->rowcnt = reinterpret_cast<unsigned int *>(b + o_rc); ws->cand = reinterpret_cast<Cand *>(b + o_cd);
     ws->counters = reinterpret_cast<Counters *>(b + o_ct);
     ws->ovf = reinterpret_cast<OvfCand *>(b + o_ov);
@@ -296,7 +293,7 @@ int eosvr_workspace_screen_ms(eosvr_workspace_t *ws, double *sum_ms, int64_t *ca
     return EOSVR_OK;
 }
 
-uint64_t eosvr_launch_count(void) { return g_launches; }
+uint64_t eosvr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int eosvr_plan(int64_t P, int32_t rows_per_episode, int64_t out[4])
 {
@@ -317,6 +314,13 @@ static int check_match_args(const eosvr_gallery_t *g, eosvr_workspace_t *ws, con
     if (metric != EOSVR_METRIC_EUCLID_TEMPORAL && metric != EOSVR_METRIC_COSINE) { set_error("match: unsupported metric %d", metric); return EOSVR_EINVAL; }
     if (metric == EOSVR_METRIC_EUCLID_TEMPORAL && (!(lam2 > 0.f) || !(lam1 >= 0.f))) { set_error("match: need lam2 > 0 and lam1 >= 0"); return EOSVR_EINVAL; }
     if (P > 0 && !d_out_packed) { set_error("match: d_out_packed is required"); return EOSVR_EINVAL; }
+    int dev = -1;
+    EOSVR_CUDA(cudaGetDevice(&dev));
+    if (dev != g->device || dev != ws->device) {
+        set_error("match: current device %d, gallery on device %d, workspace on device %d -- make the handles' device current",
+                  dev, g->device, ws->device);
+        return EOSVR_EINVAL;
+    }
     return EOSVR_OK;
 }
 
@@ -358,7 +362,7 @@ int eosvr_match_stats(eosvr_workspace_t *ws, void *stream, int64_t out[8])
     return EOSVR_OK;
 }
 
-int eosvr_workspace_debug_cycles(eosvr_workspace_t *ws, void *stream, int64_t out[6])
+int eosvr_workspace_debug_cycles(eosvr_workspace_t *ws, void *stream, int64_t out[8])
 {
     if (!ws || !out) { set_error("debug_cycles: NULL argument"); return EOSVR_EINVAL; }
     Counters c;
@@ -367,6 +371,7 @@ int eosvr_workspace_debug_cycles(eosvr_workspace_t *ws, void *stream, int64_t ou
     out[0] = static_cast<int64_t>(c.cyc_epi_busy); out[1] = static_cast<int64_t>(c.cyc_epi_wait);
     out[2] = static_cast<int64_t>(c.cyc_mma_wait_full); out[3] = static_cast<int64_t>(c.cyc_mma_wait_acc);
     out[4] = static_cast<int64_t>(c.cyc_prod_wait); out[5] = static_cast<int64_t>(c.cyc_total);
+    out[6] = static_cast<int64_t>(c.cyc_epi_pre); out[7] = static_cast<int64_t>(c.cyc_epi_loop);
     return EOSVR_OK;
 }
 
@@ -408,7 +413,8 @@ int eosvr_episode_score(const float *d_probes, const float *d_winner_rows, const
                         float *d_prob, int64_t *d_pred, int32_t *d_nproto, void *stream)
 {
     if (E < 0 || D < 1 || (E > 0 && (!d_probes || !d_support_y || !d_query))) { set_error("episode_score: bad arguments"); return EOSVR_EINVAL; }
-    if (E > 0 && !d_winner_rows && !(g && d_idx)) { set_error("episode_score: need d_winner_rows, or a gallery handle and d_idx"); return EOSVR_EINVAL; }
+    if (E == 0) return EOSVR_OK;
+    if (!d_winner_rows && !(g && d_idx)) { set_error("episode_score: need d_winner_rows, or a gallery handle and d_idx"); return EOSVR_EINVAL; }
     if (!d_winner_rows && g && g->D != D) { set_error("episode_score: gallery D=%d != D=%d", g->D, D); return EOSVR_EINVAL; }
     if (orig_mode != EOSVR_ORIG_REF_QUIRK && orig_mode != EOSVR_ORIG_CLIP_MEAN) { set_error("episode_score: bad orig_mode %d", orig_mode); return EOSVR_EINVAL; }
     return launch_episode_score(d_probes, d_winner_rows, d_winner_rows ? nullptr : g->feats, d_winner_rows ? 0 : g->G,

@@ -542,7 +542,7 @@ int launch_episode_score(const float *probes, const float *wrows, const float *g
     if (E == 0) return EOSVR_OK;
     if (nshards > 0 && !((D & 3) == 0 && (S == 2 || S == 4 || S == 8) && D >= 256)) {
         set_error("episode_score_sharded: needs D %% 4 == 0, D >= 256 and S in {2,4,8}");
-        return EOSVR_EUNSUPPORTED;
+        return EOSVR_ESHAPE;
     }
     if (n < 1 || n > kMaxClips || S < 1 || Q < 1 || Q > kMaxQ || max_proto < 1 || max_proto > kMaxProto) {
         set_error("episode_score: need 1<=n<=%d, S>=1, 1<=Q<=%d, 1<=max_proto<=%d", kMaxClips, kMaxQ, kMaxProto);

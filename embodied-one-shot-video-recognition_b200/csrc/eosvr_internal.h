@@ -24,21 +24,25 @@ constexpr bool kZeroAcc = true;   // every MMA accumulates; the epilogue zeroes 
                                   // tile's first stage overwrites and the other issuers wait for its completion (a
                                   // ~600-cycle bubble per tile)
 constexpr int kTmemCols = 512;
-constexpr int kEpiWarps = 8;      // warps 4..11: warp % 4 = TMEM lane quadrant, (warp - 4) / 4 = column group (12 warps at 96
-                                  // registers measured no faster: the epilogue is throughput-, not latency-bound)
-constexpr int kEpiGroups = kEpiWarps / 4;
-constexpr int kProdBWarp = 4 + kEpiWarps;   // second TMA producer (probe operand); warp 0 loads the gallery
-constexpr int kTwoProducers = 1;  // 1: warp 4+kEpiWarps issues the probe-operand loads.  0 (one producer thread, 12 warps, 164
-                                  // registers) measured 3-5 % slower at D = 2048 (operand waits) and no faster at D = 512
-constexpr int kThreads = 128 + 32 * kEpiWarps + 32 * kTwoProducers;
+// Epilogue warps (template parameter EW of k_match_screen): warps 4 .. 4+EW-1; warp % 4 = TMEM lane quadrant, (warp - 4) / 4 =
+// column group.  8 warps keep up with the tensor pipe when D >= 1024; for shorter rows the epilogue is the critical path and 16
+// warps run it (tools/bench_micro/epi_rate.cu: 3538 -> 2793 cycles per 128 x 240 tile against 3840 cycles of MMA at D = 512).
+constexpr int kMaxEpiWarps = 16;
+// TMA producers: warp 0 loads the gallery operand; with 8 epilogue warps a second producer warp (4+EW) loads the probe
+// operand (a UTMALDG occupies its issuing thread for ~150 cycles; one thread for both measured 3-5 % slower at D = 2048,
+// where a stage lasts 448 cycles, and no different at D = 512).  With 16 epilogue warps warp 0 loads both: 20 warps = 5 per
+// scheduler can start at 96 registers, which is what lets the epilogue warps grow to 104 (setmaxnreg moves registers
+// inside the CTA's own allocation only).
+__host__ __device__ constexpr bool two_producers(int ew) { return ew <= 8; }
+__host__ __device__ constexpr int screen_threads(int ew) { return 128 + 32 * ew + (two_producers(ew) ? 32 : 0); }
 static_assert(kStages % kIssuers == 0, "every stage barrier must have a single consumer warp");
 constexpr int kChunk = 16;        // TMEM columns per tcgen05.ld
-constexpr int kMaxSeedTiles = 2;  // strided gallery tiles screened first to seed the per-probe thresholds
+constexpr int kMaxSeedTiles = 4;   // strided gallery tiles screened first to seed the per-probe thresholds
 constexpr float kPadNorm = 1.0e30f;
 constexpr int kTimingRing = 256;  // event pairs kept for eosvr_workspace_screen_ms
 
-extern unsigned long long g_launches;   // kernels launched by this library (host-side count)
-#define EOSVR_COUNT_LAUNCH(n) (::eosvr::g_launches += (n))
+void count_launches(unsigned n);        // kernels launched by this library (host-side count, atomic)
+#define EOSVR_COUNT_LAUNCH(n) (::eosvr::count_launches(n))
 
 void set_error(const char *fmt, ...);
 
@@ -73,8 +77,11 @@ struct Counters {
     unsigned int n_flag_rows;        // rows sent to the exact fallback
     unsigned int xfloor_bits;        // max over columns of the cancellation guard (x domain)
     unsigned int ovf_count;          // entries appended to the shared spill-over buffer
+    unsigned int done_blocks;        // k_finish: blocks that have finished the exhaustive evaluation (last one unpacks)
+    unsigned int pad0;
     // cycle accounting of the screening kernel (EOSVR_EXP bit 16; measurement only), summed over CTAs
     unsigned long long cyc_epi_busy, cyc_epi_wait, cyc_mma_wait_full, cyc_mma_wait_acc, cyc_prod_wait, cyc_total;
+    unsigned long long cyc_epi_pre, cyc_epi_loop;   // epilogue busy time split: before / inside the chunk loop of a tile
 };
 
 }  // namespace eosvr
@@ -84,7 +91,7 @@ struct eosvr_screen_copy {
     void *h16;               // [Gpad, Dp] fp16/bf16
     float *gnorm;            // [Gpad] squared norm of the screened row (kPadNorm beyond G)
     float *scalars;          // [4] error-bound scalars
-    CUtensorMap tmapA, tmapSeed, tmapAH, tmapSeedH;
+    CUtensorMap tmapA, tmapSeed;
     cudaEvent_t ready;       // recorded after the build kernel (lazily built copies)
 };
 
@@ -94,7 +101,6 @@ struct eosvr_gallery {
     int32_t seed_tiles;      // gallery tiles of the strided seed pass
     int64_t seed_stride;     // row stride of the seed pass
     CUtensorMap tmapSeed;
-    CUtensorMap tmapAH, tmapSeedH;   // same tensors with half-height (64-row) boxes: multicast halves of a slab
     int32_t D, Dp;           // Dp = D rounded up to kBK
     int64_t offset;          // global index of row 0
     int32_t screen_fmt;
@@ -115,12 +121,11 @@ struct eosvr_workspace {
     void *slab;              // single device allocation
     // carved views
     void *q16;               // [cap_rows, Dp] packed probe plan (16-bit)
-    float *na, *wl, *wr, *margin, *epsd;   // [cap_rows]
+    float *na, *wl, *wr, *epsd;   // [cap_rows]
     int32_t *rowmap;         // [cap_rows] emitted probe row or -1
     unsigned int *gthr;      // [maxP] float bits of the running threshold
     unsigned long long *best;  // [maxP] packed winners
     int32_t *rowflag;        // [maxP]
-    int32_t *flaglist;       // [maxP]
     unsigned int *rowcnt;    // [maxP] candidates appended per probe row
     eosvr::Cand *cand;       // [maxP, cand_cap]
     eosvr::OvfCand *ovf;     // [ovf_cap] shared spill-over of full row lists
@@ -150,6 +155,18 @@ struct MatchPlan {
 };
 
 MatchPlan make_plan(int64_t P, int32_t rpe);
+
+// Per-device launch state (the library may drive several GPUs from one process); guarded by one mutex.
+struct DeviceState {
+    int num_sms = 0;
+    int max_clusters[2][2] = {{0, 0}, {0, 0}};   // [DIAG][EW == 16]: co-resident CTA pairs of k_match_screen<EW, DIAG>
+    bool rr_attr = false;
+    int issuers = 0;                              // MMA issuer warps in use; 0 = not decided yet (self-check pending)
+};
+// First screening call on a device: run a small match through the tensor-core path and compare every screening
+// value with a CUDA-core evaluation (eosvr_selfcheck.cu).  Decides ds->issuers (kIssuers, or 1 if several threads
+// issuing tcgen05.mma into one accumulator do not add up on this part) or fails.
+int screening_selfcheck(DeviceState *ds, cudaStream_t st);
 
 int launch_gallery_prep(eosvr_gallery *g, cudaStream_t st);
 int build_cosine_copy(eosvr_gallery *g, cudaStream_t st);      // eosvr_api.cu

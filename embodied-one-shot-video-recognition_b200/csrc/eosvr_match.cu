@@ -25,6 +25,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "eosvr_internal.h"
 #include "eosvr_ptx.cuh"
 
@@ -187,13 +189,32 @@ __device__ __forceinline__ int64_t plan_row_of(const PlanDev &pl, int64_t col, b
     return p;
 }
 
-// One warp per plan column: convert the probe row to the 16-bit screening format, compute the
-// squared norm and the per-column error bound E2 (see DESIGN.md "Error bound").
+// Threshold margin of plan column i: twice the one-sided error bound of its smoothed screening value
+// (DESIGN.md "Error bound"); epsd / wl / wr are the per-column arrays k_probe_prep writes.
+__device__ __forceinline__ float column_margin(const float *__restrict__ epsd, const float *__restrict__ wl,
+                                               const float *__restrict__ wr, int64_t i)
+{
+    const float l = wl[i], r = wr[i];
+    const float el = l > 0.f ? epsd[i - 1] : 0.f, er = r > 0.f ? epsd[i + 1] : 0.f;
+    return 2.02f * (epsd[i] + l * el + r * er) + 1e-7f;
+}
+
+// per-probe-row state of one eosvr_match call
+struct RowState {
+    unsigned long long *best;
+    int32_t *rowflag;
+    unsigned int *rowcnt;
+    unsigned int *gthr;
+};
+
+// One warp per plan column: convert the probe row to the 16-bit screening format, compute the squared norm, the
+// per-column error bound E2 (see DESIGN.md "Error bound") and the tap weights (w = lam1/lam2 towards a neighbour of
+// the same episode, 0 at episode ends), and reset the state of the probe row the column emits.
 template <typename T16, bool NORM>
-__global__ void k_probe_prep(const float *__restrict__ probes, PlanDev pl, int D, int Dp,
+__global__ void k_probe_prep(const float *__restrict__ probes, PlanDev pl, int D, int Dp, float w,
                              const float *__restrict__ gscal, T16 *__restrict__ q16,
-                             float *__restrict__ na, float *__restrict__ epsd, int32_t *__restrict__ rowmap,
-                             Counters *ctr)
+                             float *__restrict__ na, float *__restrict__ epsd, float *__restrict__ wl,
+                             float *__restrict__ wr, int32_t *__restrict__ rowmap, RowState rs, Counters *ctr)
 {
     const int lane = threadIdx.x & 31;
     const int64_t col = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -203,7 +224,7 @@ __global__ void k_probe_prep(const float *__restrict__ probes, PlanDev pl, int D
     T16 *dst = q16 + col * Dp;
     if (!valid) {
         for (int k = lane; k < Dp; k += 32) dst[k] = to16<T16>(0.f);
-        if (lane == 0) { na[col] = kPadNorm; epsd[col] = 0.f; rowmap[col] = -1; }
+        if (lane == 0) { na[col] = kPadNorm; epsd[col] = 0.f; wl[col] = 0.f; wr[col] = 0.f; rowmap[col] = -1; }
         return;
     }
     const float *src = probes + p * D;
@@ -230,9 +251,10 @@ __global__ void k_probe_prep(const float *__restrict__ probes, PlanDev pl, int D
     if (lane == 0) {
         const double B2 = gscal[0], Bl2 = gscal[1], Bh2 = gscal[2];
         const double ulp = 1.0 / 4194304.0;   // 2^-22
-        // |x~ - x| <= 2(|a_lo||b| + |a_hi||b_lo|) + tensor-core accumulation + fp32 rounding
+        // |x~ - x| <= 2(|a_lo||b| + |a_hi||b_lo|) + tensor-core accumulation + fp32 rounding.  The accumulator starts
+        // at -|b|^2/2 (the epilogue's fill value), so the partial sums are bounded by |a_hi||b_hi| + |b|^2/2.
         double e2 = 2.0 * (sqrt(sl * B2) + sqrt(sh * Bl2))
-                  + 2.0 * ulp * (Dp / 16 + 1) * sqrt(sh * Bh2)
+                  + 2.0 * ulp * (Dp / 16 + 1) * (sqrt(sh * Bh2) + 0.5 * B2)
                   + 2.0 * ulp * (s + B2);
         e2 *= 1.01;
         if (e2 < 1e-30) e2 = 1e-30;
@@ -240,43 +262,25 @@ __global__ void k_probe_prep(const float *__restrict__ probes, PlanDev pl, int D
         epsd[col] = __double2float_ru(sqrt(e2) / 16.0);           // E2 / (2 sqrt(64 E2))
         rowmap[col] = emit ? static_cast<int32_t>(p) : -1;
         atomicMax(&ctr->xfloor_bits, __float_as_uint(__double2float_ru(65.0 * e2)));
-    }
-}
-
-// Thread per plan column: tap weights and threshold margin.
-__global__ void k_column_plan(PlanDev pl, float w, const float *__restrict__ epsd,
-                              float *__restrict__ wl, float *__restrict__ wr, float *__restrict__ margin)
-{
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int64_t ncol = pl.NT * pl.BN;
-    if (i >= ncol) return;
-    bool valid, emit;
-    const int64_t p = plan_row_of(pl, i, valid, emit);
-    const int c = static_cast<int>(i % pl.BN);
-    float l = 0.f, r = 0.f, el = 0.f, er = 0.f;
-    if (valid) {
-        if (c > 0 && p > 0 && (p % pl.rpe) != 0) { l = w; el = epsd[i - 1]; }
+        const int c = static_cast<int>(col % pl.BN);
+        float l = 0.f, r = 0.f;
+        if (c > 0 && p > 0 && (p % pl.rpe) != 0) l = w;
         if (c + 1 < pl.BN && p + 1 < pl.P && ((p + 1) % pl.rpe) != 0) {
-            bool v2, e2;
-            plan_row_of(pl, i + 1, v2, e2);
-            if (v2) { r = w; er = epsd[i + 1]; }
+            bool v2, e2n;
+            plan_row_of(pl, col + 1, v2, e2n);
+            if (v2) r = w;
         }
+        wl[col] = l; wr[col] = r;
+        if (emit) { rs.best[p] = ~0ull; rs.rowflag[p] = 0; rs.rowcnt[p] = 0; rs.gthr[p] = 0x7f800000u; }
     }
-    wl[i] = l; wr[i] = r;
-    margin[i] = valid ? 2.02f * (epsd[i] + l * el + r * er) + 1e-7f : 0.f;
 }
 
-__global__ void k_reset(Counters *ctr, unsigned long long *best, int32_t *rowflag, unsigned int *rowcnt,
-                        unsigned int *gthr, int64_t P, int flag_all)
+// eosvr_match_exact only (no screening pass): every row goes to the exhaustive kernel.
+__global__ void k_reset_exact(Counters *ctr, RowState rs, int64_t P)
 {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i == 0) {
-        ctr->cand_count = 0; ctr->n_exact = 0; ctr->n_unsafe = 0;
-        ctr->overflow = flag_all ? 1u : 0u; ctr->n_flag_rows = 0; ctr->xfloor_bits = 0; ctr->ovf_count = 0;
-        ctr->cyc_epi_busy = ctr->cyc_epi_wait = ctr->cyc_mma_wait_full = ctr->cyc_mma_wait_acc = 0;
-        ctr->cyc_prod_wait = ctr->cyc_total = 0;
-    }
-    if (i < P) { best[i] = ~0ull; rowflag[i] = flag_all; rowcnt[i] = 0; gthr[i] = 0x7f800000u; }
+    if (i == 0) ctr->overflow = 2u;                      // 2: all rows
+    if (i < P) { rs.best[i] = ~0ull; rs.rowflag[i] = 1; rs.rowcnt[i] = 0; rs.gthr[i] = 0x7f800000u; }
 }
 
 // -------------------------------------------------------------------------------------------
@@ -287,15 +291,15 @@ struct ScreenParams {
     int64_t G;
     int32_t KB;             // K blocks of 64 elements
     int32_t BN;
-    int64_t NT, GT;
+    int32_t NT, GT;         // probe tiles, gallery tiles (32-bit: unit arithmetic stays cheap in the kernel)
     int32_t TPU;            // gallery tiles per work unit
-    int64_t n_chunks;       // gallery chunks (of TPU tiles)
-    int64_t NTG;            // probe tile groups: NT / (CTA pairs per cluster)
-    int64_t n_units;        // n_chunks * NTG, chunk-major: concurrent clusters share a gallery chunk
+    int32_t n_chunks;       // gallery chunks (of TPU tiles)
+    int32_t n_units;        // n_chunks * NT
     int32_t order;          // unit order: 0 chunk-major, 1 probe-tile-major, 2 diagonal (rotated chunks)
     int64_t g_stride;       // gallery row stride (1; > 1 in the seed pass)
     int32_t seed_mode;      // 1: only tighten the thresholds, append nothing
-    const float *na, *wl, *wr, *margin;
+    int32_t issuers;        // MMA issuer warps in use: kIssuers, or 1 (the documented single-issuer ordering)
+    const float *na, *wl, *wr, *epsd;
     const int32_t *rowmap;
     unsigned int *gthr;
     Cand *cand;
@@ -307,9 +311,17 @@ struct ScreenParams {
     int32_t *rowflag;
     uint32_t idesc;
     float *dbg;             // optional [P,G] dump of the screening values
-    int32_t exp_mode;       // experiments (EOSVR_EXP): 1 = epilogue releases the accumulator untouched,
-                            // 2 = producer skips the TMA loads, 4 = MMA issuer skips the MMAs
+    int32_t exp_mode;       // measurement modes (EOSVR_EXP): 16 = cycle accounting.  Only in builds with
+                            // -DEOSVR_EXPERIMENTS (timing only, WRONG results): 1 = the epilogue releases the accumulator
+                            // untouched, 2 = producers skip the TMA loads, 4 = issuers skip the MMAs, 32 = no rare path,
+                            // 128 = no accumulator refill, 256 = no lane-quadrant barrier, 512 = no square roots
 };
+
+#ifdef EOSVR_EXPERIMENTS
+#define EOSVR_EXP_ON(p, bit) (((p).exp_mode & (bit)) != 0)
+#else
+#define EOSVR_EXP_ON(p, bit) false
+#endif
 
 struct StagedCand {
     int32_t rm;         // probe row
@@ -318,6 +330,7 @@ struct StagedCand {
 };
 constexpr int kWarpStage = 64;
 
+template <int EW>
 struct __align__(16) ScreenSmemTail {
     float na[kMaxBN];
     float wl[kMaxBN];
@@ -325,27 +338,30 @@ struct __align__(16) ScreenSmemTail {
     float mg[kMaxBN];
     unsigned int thr[kMaxBN];
     int32_t row[kMaxBN];
-    uint64_t full[kStages];           // stage s is always consumed by issuer s % kIssuers: a parity wait is only safe
+    uint64_t full[kStages];           // stage s is always consumed by issuer s % issuers: a parity wait is only safe
                                       // on a barrier whose every phase the waiter observes
     uint64_t empty[kStages];
     uint64_t tfull[kAccStages];
     uint64_t tempty[kAccStages];
-    uint64_t tfirst[kAccStages];      // the overwriting first stage of a tile has completed
     uint32_t tmem_base;
+    uint32_t zeros[8];                // zeros the compiler cannot see through (refill-store source registers)
     // candidate staging: every epilogue warp parks its candidates in shared memory and hands them to the
     // per-row lists 32 at a time (one global atomicAdd per lane, all in flight together) instead of stalling on
     // one atomic round trip per column
-    StagedCand stage[kEpiWarps][kWarpStage];
+    StagedCand stage[EW][kWarpStage];
 };
 
 constexpr int kABytes = kBM * kBK * 2;              // 16 KiB: this CTA's 128 gallery rows
 constexpr int kBBytes = (kMaxBN / 2) * kBK * 2;     // 16 KiB: this CTA's half of the probe tile
 constexpr int kAStage = kSub * kABytes;             // one pipeline stage = kSub K blocks of each operand
 constexpr int kBStage = kSub * kBBytes;
-constexpr size_t kScreenSmem = 1024 + static_cast<size_t>(kStages) * (kAStage + kBStage) + sizeof(ScreenSmemTail);
+template <int EW>
+constexpr size_t screen_smem() { return static_cast<size_t>(kStages) * (kAStage + kBStage) + sizeof(ScreenSmemTail<EW>); }
+constexpr int kEpiRegs = 104;     // registers of an epilogue thread when 16 epilogue warps run (setmaxnreg) ...
+constexpr int kLightRegs = 64;    // ... and of the producer / issuer threads: 64 + 4 x 104 = 5 x 96 per scheduler
 
 struct UnitIter {
-    int64_t u, jt, gt0, gt1;    // jt: probe tile GROUP of the unit (pair q of the cluster takes tile jt*NP + q)
+    int32_t u, jt, gt0, gt1;    // jt: probe tile of the unit
 };
 
 // Work units (gallery chunk x probe tile), three orders (EOSVR_ORDER):
@@ -357,16 +373,16 @@ struct UnitIter {
 //   0 chunk-major: unit u = chunk * NT + probe_tile.  Tightest thresholds, but every probe tile is re-read from HBM
 //     once per gallery chunk (measured 4.7x the algorithmic bytes at the bench size);
 //   2 diagonal (rotated chunks).
-__device__ __forceinline__ bool decode_unit(const ScreenParams &p, int64_t u, UnitIter &it)
+__device__ __forceinline__ bool decode_unit(const ScreenParams &p, int32_t u, UnitIter &it)
 {
-    int64_t chunk;
+    int32_t chunk;
     it.u = u;
     if (p.order == 1) {
         it.jt = u / p.n_chunks;
         chunk = u % p.n_chunks;
     } else {
-        chunk = u / p.NTG;
-        it.jt = u % p.NTG;
+        chunk = u / p.NT;
+        it.jt = u % p.NT;
         if (p.order == 2) chunk = (chunk + it.jt) % p.n_chunks;   // every (tile, chunk) still visited once
     }
     it.gt0 = chunk * p.TPU;
@@ -374,10 +390,28 @@ __device__ __forceinline__ bool decode_unit(const ScreenParams &p, int64_t u, Un
     return it.gt0 < it.gt1;
 }
 
-// NP = CTA pairs per cluster (cluster size 2*NP).  With NP = 2 the two pairs of a cluster screen the SAME
-// gallery tile against two different probe tiles: every CTA fetches half of its 128-row gallery slab and
-// multicasts it to the CTA of equal parity in the other pair, so the gallery operand crosses L2 -> SM once
-// per cluster instead of once per pair (the kernel is bound by operand delivery).
+// The sequence of (unit, gallery tile) a CTA pair works through; the epilogue keeps a second cursor two tiles
+// ahead (the next user of the accumulator it is reading).
+struct TileCursor {
+    int32_t u;
+    UnitIter it;
+    int32_t gt;
+    bool valid;
+};
+__device__ __forceinline__ void cursor_seek(const ScreenParams &p, TileCursor &c, int32_t stride)
+{
+    c.valid = false;
+    for (; c.u < p.n_units; c.u += stride)
+        if (decode_unit(p, c.u, c.it)) { c.gt = c.it.gt0; c.valid = true; return; }
+}
+__device__ __forceinline__ void cursor_next(const ScreenParams &p, TileCursor &c, int32_t stride)
+{
+    if (!c.valid) return;
+    if (++c.gt < c.it.gt1) return;
+    c.u += stride;
+    cursor_seek(p, c, stride);
+}
+
 // t[j] for a warp-uniform j without indexing the register array dynamically.
 __device__ __forceinline__ float pick16(const float (&t)[kChunk], int j)
 {
@@ -422,37 +456,47 @@ __device__ __forceinline__ void flush_staged(const ScreenParams &p, const Staged
     __syncwarp();
 }
 
-template <int NP>
-__global__ void __launch_bounds__(kThreads, 1)
+// EW = epilogue warps (8 or 16).  DIAG = diagnostic build of the kernel: cycle accounting (EOSVR_EXP bit 16) and the
+// screening-value dump (eosvr_workspace_set_debug, used by the tests and by the per-device self-check); the
+// production instantiation carries neither (they cost ~25 predicated-off instructions per chunk).
+//
+// The accumulator never starts from zero: the epilogue leaves -|b|^2/2 of the gallery row that will occupy the
+// lane NEXT in every column it has finished with (tcgen05.st, one chunk behind its reads), and every MMA
+// accumulates, so the tensor core delivers a.b - |b|^2/2 and the squared distance is one FFMA per element:
+// x = fma(acc, -2, |a|^2).  The three issuers therefore never order themselves against each other either.
+template <int EW, bool DIAG>
+__global__ void __launch_bounds__(screen_threads(EW), 1)
 k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ScreenParams p)
 {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment (SWIZZLE_128B operand tiles) comes from the declaration, so that every pointer below stays
+    // in the shared address space for the compiler (an integer round trip turns the epilogue's loads into generic
+    // LD.E: +20 % epilogue time, tools/bench_micro/epi_rate.cu); checked once below
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sA = smem;
     uint8_t *sB = smem + kStages * kAStage;
-    ScreenSmemTail *tl = reinterpret_cast<ScreenSmemTail *>(smem + kStages * (kAStage + kBStage));
+    using Tail = ScreenSmemTail<EW>;
+    Tail *tl = reinterpret_cast<Tail *>(smem + kStages * (kAStage + kBStage));
     const int KS = (p.KB + kSub - 1) / kSub;            // pipeline stages per gallery tile
+    constexpr bool kTwoProducers = two_producers(EW);
+    constexpr int kProdBWarp = 4 + EW;                  // second TMA producer (probe operand); warp 0 loads the gallery
+    constexpr int EG = EW / 4;                          // column groups of the epilogue
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank();
     const uint32_t rank = crank & 1u;                   // 0 = leader of its pair (issues the MMAs), 1 = peer
-    const uint32_t pq = crank >> 1;                     // pair within the cluster
-    const uint32_t leader = crank & ~1u;                // cluster rank of this pair's leader
-    const int64_t pair = blockIdx.x / (2 * NP), npairs = gridDim.x / (2 * NP);   // cluster index / count
+    const int32_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;   // cluster (CTA pair) index / count
 
     if (warp == 0 && lane == 0) {
+        if ((smem_u32(smem) & 1023u) != 0u) __trap();
+        for (int i = 0; i < 8; ++i) tl->zeros[i] = 0u;
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
-        // NP > 1: every CTA collects its own bytes on its own full barrier and the peer relays its completion
-        // to the leader (second arrival); the stage is free once the MMAs of ALL pairs have read it.
-        const uint32_t full_count = (NP > 1 && rank == 0) ? 2u : 1u;
-        for (int s = 0; s < kStages; ++s) { mbar_init(&tl->full[s], full_count); mbar_init(&tl->empty[s], NP); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&tl->full[s], 1); mbar_init(&tl->empty[s], 1); }
         for (int s = 0; s < kAccStages; ++s) {
-            mbar_init(&tl->tfull[s], kIssuers);          // one commit per MMA issuer warp
-            mbar_init(&tl->tempty[s], 2 * kEpiWarps);
-            mbar_init(&tl->tfirst[s], 1);
+            mbar_init(&tl->tfull[s], p.issuers);         // one commit per MMA issuer warp
+            mbar_init(&tl->tempty[s], 2 * EW);
         }
         fence_mbar_init();
     }
@@ -461,36 +505,39 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     cluster_sync();
     tc_fence_after();
     const uint32_t tmem_base = tl->tmem_base;
-    const bool prof = (p.exp_mode & 16) != 0;
+    const bool prof = DIAG && (p.exp_mode & 16) != 0;
+    const bool epi_warp = warp >= 4 && warp < 4 + EW;
+    // EW = 16: 20 warps share 64 K registers; every role branch below starts by handing back (setmaxnreg.dec) or
+    // claiming (setmaxnreg.inc, epilogue) registers, and the branches only meet again at the final cluster barrier
+    constexpr bool kRepartition = EW > 8;
 
     // Producer and issuer warps run their loops with the whole warp; lane 0 issues.
     if (warp == 0 || (kTwoProducers && warp == kProdBWarp)) {
-        // ===== TMA producers (every CTA): warp 0 loads the CTA's gallery rows (A), warp 12 its half of the pair's
+        // ===== TMA producers (every CTA): warp 0 loads the CTA's gallery rows (A), warp 4+EW its half of the pair's
         //       probe tile (B) -- a UTMALDG occupies its issuing thread for ~150 cycles, so one thread per operand.
         //       Warp 0 also posts the byte count of the whole stage. =====
+        if (kRepartition) reg_release<kLightRegs>();
         const bool isA = warp == 0, isB = kTwoProducers ? warp == kProdBWarp : true;   // one warp may play both roles
         int stage = 0; uint32_t phase = 0;
         const int32_t bhalf = p.BN >> 1;
         const uint32_t tx_cta = kABytes + static_cast<uint32_t>(bhalf) * kBK * 2;
-        uint16_t mc_mask = 0;
-        for (int k = 0; k < NP; ++k) mc_mask |= static_cast<uint16_t>(1u << (2 * k + rank));
         unsigned long long w_prod = 0;
         const long long t_begin = clock64();
         const uint32_t lbar0 = mapa(smem_u32(&tl->full[0]), 0);
-        for (int64_t u = pair; u < p.n_units; u += npairs) {
+        for (int32_t u = pair; u < p.n_units; u += npairs) {
             UnitIter it;
             if (!decode_unit(p, u, it)) continue;
-            const int32_t brow = static_cast<int32_t>((it.jt * NP + pq) * p.BN + rank * bhalf);
-            for (int64_t gt = it.gt0; gt < it.gt1; ++gt) {
-                const int32_t arow = static_cast<int32_t>(gt * kPairM + rank * kBM + (NP > 1 ? pq * (kBM / NP) : 0));
+            const int32_t brow = static_cast<int32_t>(it.jt * p.BN + rank * bhalf);
+            for (int32_t gt = it.gt0; gt < it.gt1; ++gt) {
+                const int32_t arow = static_cast<int32_t>(gt * kPairM + rank * kBM);
                 for (int ks = 0; ks < KS; ++ks) {
                     const int nsub = min(kSub, p.KB - ks * kSub);
                     if (prof) { const long long t0 = clock64(); mbar_wait(&tl->empty[stage], phase ^ 1); w_prod += clock64() - t0; }
                     else mbar_wait(&tl->empty[stage], phase ^ 1);
                     if (lane == 0) {
-                        if (p.exp_mode & 2) {
-                            if (isA && (NP > 1 || rank == 0)) mbar_arrive(&tl->full[stage]);
-                        } else if (NP == 1) {
+                        if (EOSVR_EXP_ON(p, 2)) {
+                            if (isA && rank == 0) mbar_arrive(&tl->full[stage]);
+                        } else {
                             // the bytes of both CTAs complete on the LEADER's full barrier: only the leader
                             // arrives; the peer cannot run ahead of the phase because its stage is freed by
                             // the leader's MMA commit
@@ -500,14 +547,6 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 const int32_t kc = (ks * kSub + sb) * kBK;
                                 if (isA) tma_load_2d_2sm(sA + stage * kAStage + sb * kABytes, &tmA, lbar, kc, arow);
                                 if (isB) tma_load_2d_2sm(sB + stage * kBStage + sb * kBBytes, &tmB, lbar, kc, brow);
-                            }
-                        } else {
-                            if (isA) mbar_arrive_expect_tx(&tl->full[stage], tx_cta * nsub);
-                            for (int sb = 0; sb < nsub; ++sb) {
-                                const int32_t kc = (ks * kSub + sb) * kBK;
-                                if (isA) tma_load_2d_mc(sA + stage * kAStage + sb * kABytes + pq * (kABytes / NP), &tmA,
-                                                        &tl->full[stage], kc, arow, mc_mask);
-                                if (isB) tma_load_2d(sB + stage * kBStage + sb * kBBytes, &tmB, &tl->full[stage], kc, brow);
                             }
                         }
                     }
@@ -520,33 +559,29 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             atomicAdd(&p.ctr->cyc_prod_wait, w_prod);
             if (rank == 0) atomicAdd(&p.ctr->cyc_total, static_cast<unsigned long long>(clock64() - t_begin));
         }
-    } else if (warp >= 1 && warp <= kIssuers && rank == 0) {
-        // ===== MMA issuers: kIssuers warps of the pair's leader drive the tensor cores of both SMs, taking the
-        //       pipeline stages round-robin (stage s -> issuer s % kIssuers) into the same accumulator.  kZeroAcc:
-        //       every MMA accumulates onto an accumulator the epilogue left zeroed.  Otherwise the first stage of a
-        //       tile overwrites the accumulator: its owner commits to tfirst[acc] and the other warps wait for that
-        //       before accumulating on top.  Every issuer observes every phase of tempty / tfirst. =====
+    } else if (warp >= 1 && warp <= p.issuers && rank == 0) {
+        // ===== MMA issuers: p.issuers warps of the pair's leader drive the tensor cores of both SMs, taking the
+        //       pipeline stages round-robin (stage s -> issuer s % issuers) into the same accumulator.  Every MMA
+        //       accumulates onto the values the epilogue left behind, so the issuers need no ordering among
+        //       themselves.  Every issuer observes every phase of tempty. =====
+        if (kRepartition) reg_release<kLightRegs>();
         const int w = warp - 1;
+        const int nis = p.issuers;
         int64_t seq = 0;                                  // running stage number of this pair
         int acc = 0; uint32_t accphase = 0;
-        const uint16_t all_mask = static_cast<uint16_t>((1u << (2 * NP)) - 1u);
-        const uint16_t pair_mask = static_cast<uint16_t>(3u << leader);
-        const uint16_t self_mask = static_cast<uint16_t>(1u << leader);
+        const uint16_t pair_mask = 3u;
         unsigned long long w_full = 0, w_acc = 0;
-        for (int64_t u = pair; u < p.n_units; u += npairs) {
+        for (int32_t u = pair; u < p.n_units; u += npairs) {
             UnitIter it;
             if (!decode_unit(p, u, it)) continue;
-            for (int64_t gt = it.gt0; gt < it.gt1; ++gt) {
-                const bool first_owner = static_cast<int>(seq % kIssuers) == w;   // issues the overwriting stage
-                // kZeroAcc: phase 0 of tempty is the epilogue's initial zeroing, phase k+1 the release after the k-th use
-                const uint32_t epar = kZeroAcc ? accphase : (accphase ^ 1);
-                if (prof) { const long long t0 = clock64(); mbar_wait(&tl->tempty[acc], epar); w_acc += clock64() - t0; }
-                else mbar_wait(&tl->tempty[acc], epar);
-                if (!kZeroAcc && !first_owner) mbar_wait(&tl->tfirst[acc], accphase);
+            for (int32_t gt = it.gt0; gt < it.gt1; ++gt) {
+                // phase 0 of tempty is the epilogue's initial fill, phase k+1 the release after the k-th use
+                if (prof) { const long long t0 = clock64(); mbar_wait(&tl->tempty[acc], accphase); w_acc += clock64() - t0; }
+                else mbar_wait(&tl->tempty[acc], accphase);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * kMaxBN;
                 for (int ks = 0; ks < KS; ++ks, ++seq) {
-                    if (static_cast<int>(seq % kIssuers) != w) continue;
+                    if (static_cast<int>(seq % nis) != w) continue;
                     const int stage = static_cast<int>(seq % kStages);
                     const uint32_t phase = static_cast<uint32_t>(seq / kStages) & 1u;
                     const int nsub = min(kSub, p.KB - ks * kSub);
@@ -556,21 +591,18 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t a0 = smem_u32(sA + stage * kAStage);
                     const uint32_t b0 = smem_u32(sB + stage * kBStage);
                     if (lane == 0) {
-                        if (!(p.exp_mode & 4)) {
+                        if (!EOSVR_EXP_ON(p, 4)) {
                             for (int sb = 0; sb < nsub; ++sb) {
 #pragma unroll
                                 for (int k = 0; k < kBK / 16; ++k)
                                     mma_f16_ss_2sm(d_tmem, umma_desc_sw128(a0 + sb * kABytes, k * 32),
-                                                   umma_desc_sw128(b0 + sb * kBBytes, k * 32), p.idesc,
-                                                   (kZeroAcc || (ks | sb | k) != 0) ? 1u : 0u);
+                                                   umma_desc_sw128(b0 + sb * kBBytes, k * 32), p.idesc, 1u);
                             }
                         }
-                        mma_commit_2sm(&tl->empty[stage], all_mask);    // one of the NP arrivals that free the stage
-                        if (!kZeroAcc && ks == 0) mma_commit_2sm(&tl->tfirst[acc], self_mask);
+                        mma_commit_2sm(&tl->empty[stage], pair_mask);   // frees the stage in both CTAs
                     }
                     __syncwarp();
                 }
-                if (!kZeroAcc && first_owner) mbar_wait(&tl->tfirst[acc], accphase);   // long complete; keeps the phase observed
                 if (lane == 0) mma_commit_2sm(&tl->tfull[acc], pair_mask);   // this warp's share of the tile is done
                 __syncwarp();
                 if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
@@ -578,209 +610,217 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (prof && lane == 0 && w == 0) atomicAdd(&p.ctr->cyc_mma_wait_acc, w_acc);
         if (prof && lane == 0) atomicAdd(&p.ctr->cyc_mma_wait_full, w_full);
-    } else if (NP > 1 && warp == 1 && rank == 1) {
-        // ===== relay (peer CTA): tell the leader when this CTA's stage has landed =====
-        int stage = 0; uint32_t phase = 0;
-        const uint32_t lfull0 = mapa(smem_u32(&tl->full[0]), leader);
-        for (int64_t u = pair; u < p.n_units; u += npairs) {
-            UnitIter it;
-            if (!decode_unit(p, u, it)) continue;
-            for (int64_t n = (it.gt1 - it.gt0) * KS; n > 0; --n) {
-                mbar_wait(&tl->full[stage], phase);
-                if (lane == 0) mbar_arrive_cluster(lfull0 + stage * static_cast<uint32_t>(sizeof(uint64_t)));
-                __syncwarp();
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
-            }
-        }
-    } else if (warp >= 4 && warp < 4 + kEpiWarps) {
+    } else if (epi_warp) {
         // ===== epilogue: warp%4 selects the TMEM lane quadrant, (warp-4)/4 the group of column chunks =====
+        if (kRepartition) reg_acquire<kEpiRegs>();
         const int q = warp & 3;
-        const int half = (warp - 4) >> 2;
+        const int grp = (warp - 4) >> 2;
         const int te = threadIdx.x - 128;
         const int BN = p.BN;
         const int nchunks = BN / kChunk;
-        const int cbeg = nchunks * half / kEpiGroups;
-        const int cend = nchunks * (half + 1) / kEpiGroups;
+        const int cbeg = nchunks * grp / EG;
+        const int cend = nchunks * (grp + 1) / EG;
         const float xfloor = __uint_as_float(p.ctr->xfloor_bits);
         const float dfloor = sqrtf(xfloor) * 1.000001f;
+        const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+        const int64_t row_in_tile = static_cast<int64_t>(rank) * kBM + q * 32 + lane;
         int acc = 0; uint32_t accphase = 0;
-        const uint32_t tempty_leader0 = mapa(smem_u32(&tl->tempty[0]), leader);
-        const uint32_t tempty_leader1 = mapa(smem_u32(&tl->tempty[1]), leader);
-        unsigned long long e_busy = 0, e_wait = 0;
-        if (kZeroAcc) {
-            // column group `half` of this lane quadrant zeroes accumulator `half`; every warp then reports both
-            // accumulators (a barrier completes only when all 2*kEpiWarps warps of the pair have arrived)
-            static_assert(!kZeroAcc || kEpiGroups == kAccStages, "initial zeroing: one column group per accumulator");
-            const uint32_t tz = tmem_base + static_cast<uint32_t>(half) * kMaxBN + (static_cast<uint32_t>(q * 32) << 16);
+        const uint32_t tempty_leader0 = mapa(smem_u32(&tl->tempty[0]), 0);
+        const uint32_t tempty_leader1 = mapa(smem_u32(&tl->tempty[1]), 0);
+        unsigned long long e_busy = 0, e_wait = 0, e_pre = 0, e_loop = 0;
+
+        // accumulator fill value for tile c: -|b|^2/2 of this lane's gallery row (0 when there is no such tile)
+        auto fill_bits = [&](const TileCursor &c) -> uint32_t {
+            if (!c.valid) return 0u;
+            return __float_as_uint(-0.5f * p.gnorm[(static_cast<int64_t>(c.gt) * kPairM + row_in_tile) * p.g_stride]);
+        };
+        TileCursor cur;
+        cur.u = pair;
+        cursor_seek(p, cur, npairs);
+        TileCursor ahead = cur;
+        cursor_next(p, ahead, npairs);
+        {
+            // initial fill: accumulator 0 for the pair's first tile, accumulator 1 for its second; every column group
+            // takes its share of the 2 x 256 columns and every warp then reports both accumulators (a barrier
+            // completes only when all 2*EW warps of the pair have arrived)
+            const uint32_t f0 = fill_bits(cur), f1 = fill_bits(ahead);
+            constexpr int kShare = kAccStages * kMaxBN / EG;
 #pragma unroll 1
-            for (int c = 0; c < kMaxBN; c += kChunk) tmem_st_zero_x16(tz + c);
+            for (int c = grp * kShare; c < (grp + 1) * kShare; c += kChunk)
+                tmem_st_fill_x16(tmem_base + lane_off + c, c < kMaxBN ? f0 : f1);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive_cluster(tempty_leader0); mbar_arrive_cluster(tempty_leader1); }
         }
+        cursor_next(p, ahead, npairs);                    // from here on: the next tile to use the accumulator `cur` is in
         StagedCand *wstage = tl->stage[warp - 4];
         int wn = 0;                                       // candidates parked by this warp (warp-uniform)
-        for (int64_t u = pair; u < p.n_units; u += npairs) {
-            UnitIter it;
-            if (!decode_unit(p, u, it)) continue;
-            // per-unit column arrays -> smem
-            named_bar_sync(1, 32 * kEpiWarps);
-            if (te < BN) {
-                const int64_t c = (it.jt * NP + pq) * BN + te;
-                tl->na[te] = p.na[c];
-                tl->wl[te] = p.wl[c];
-                tl->wr[te] = p.wr[c];
-                tl->mg[te] = p.margin[c];
-                const int32_t rm = p.rowmap[c];
-                tl->row[te] = rm;
-                tl->thr[te] = rm >= 0 ? *reinterpret_cast<volatile unsigned int *>(p.gthr + rm)
-                                      : __float_as_uint(-1.0f);
-            }
-            named_bar_sync(1, 32 * kEpiWarps);
-
-            for (int64_t gt = it.gt0; gt < it.gt1; ++gt) {
-                // pick up thresholds tightened by other CTAs since the last tile (benign race)
+        int32_t smem_unit = -1;
+        while (cur.valid) {
+            if (cur.it.u != smem_unit) {
+                // per-unit column arrays -> smem
+                smem_unit = cur.it.u;
+                named_bar_sync(1, 32 * EW);
                 if (te < BN) {
-                    const int32_t rm = tl->row[te];
-                    if (rm >= 0) atomicMin(&tl->thr[te], *reinterpret_cast<volatile unsigned int *>(p.gthr + rm));
+                    const int64_t c = static_cast<int64_t>(cur.it.jt) * BN + te;
+                    tl->na[te] = p.na[c];
+                    tl->wl[te] = p.wl[c];
+                    tl->wr[te] = p.wr[c];
+                    tl->mg[te] = column_margin(p.epsd, p.wl, p.wr, c);
+                    const int32_t rm = p.rowmap[c];
+                    tl->row[te] = rm;
+                    tl->thr[te] = rm >= 0 ? ld_volatile_u32(p.gthr + rm) : __float_as_uint(-1.0f);
                 }
-                // this lane's gallery row and its squared norm: requested BEFORE waiting for the accumulator so the
-                // global-load latency hides behind the wait
-                const int64_t g = (gt * kPairM + rank * kBM + q * 32 + lane) * p.g_stride;
-                const float nb = p.gnorm[g];
-                long long t_e0 = 0;
-                if (prof) { const long long t0 = clock64(); mbar_wait(&tl->tfull[acc], accphase); t_e0 = clock64(); e_wait += t_e0 - t0; }
-                else mbar_wait(&tl->tfull[acc], accphase);
-                tc_fence_after();
-                const uint32_t trow = tmem_base + static_cast<uint32_t>(acc) * kMaxBN + (static_cast<uint32_t>(q * 32) << 16);
+                named_bar_sync(1, 32 * EW);
+            }
+            // thresholds tightened by other CTAs since the last tile (benign race): requested now, folded in after
+            // this tile's chunks, so the load's latency hides behind the tile instead of stalling the warp
+            unsigned int pend_thr = 0xFFFFFFFFu;
+            if (te < BN) {
+                const int32_t rm = tl->row[te];
+                if (rm >= 0) pend_thr = ld_volatile_u32(p.gthr + rm);
+            }
+            // this lane's gallery row; the fill value of the accumulator's next tile is requested BEFORE waiting for
+            // the accumulator so the global-load latency hides behind the wait
+            const int64_t g = (static_cast<int64_t>(cur.gt) * kPairM + row_in_tile) * p.g_stride;
+            const uint32_t fill = fill_bits(ahead);
+            long long t_e0 = 0;
+            if (prof) { const long long t0 = clock64(); mbar_wait(&tl->tfull[acc], accphase); t_e0 = clock64(); e_wait += t_e0 - t0; }
+            else mbar_wait(&tl->tfull[acc], accphase);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + static_cast<uint32_t>(acc) * kMaxBN + lane_off;
 
-                float dprev = kBig;
-                if (p.exp_mode & 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
-                    if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
-                    continue;
+            if (!EOSVR_EXP_ON(p, 1) && cend > cbeg) {
+                const bool rowok = g < p.G;
+                // eight registers holding the fill value: the source of the refill stores (a tcgen05.st wants consecutive
+                // registers; or-ing in zeros the compiler cannot see through keeps it from re-copying one register into
+                // fifteen others in front of every store)
+                uint32_t fv[8];
+                {
+                    const volatile unsigned int *zp = tl->zeros;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) fv[i] = fill | zp[i];
                 }
-                uint32_t va[kChunk], vb[kChunk];
+                uint32_t v[kChunk];                      // TMEM landing registers
                 uint32_t vleft = 0, vright = 0;          // the neighbouring column groups' boundary columns
-                {   // first chunk and the boundary columns of the neighbouring column groups: one wait for all
-                    if (cbeg > 0) tmem_ld_x1(trow + cbeg * kChunk - 1, vleft);
-                    if (cend * kChunk < BN) tmem_ld_x1(trow + cend * kChunk, vright);
-                    tmem_ld_x16(trow + cbeg * kChunk, va);
-                    tmem_ld_wait();
-                    if (cbeg > 0) {
-                        const float x = fmaf(-2.f, __uint_as_float(vleft), nb) + tl->na[cbeg * kChunk - 1];
-                        dprev = sqrt_approx(fabsf(x));
-                    }
-                    // kZeroAcc: nobody zeroes a column before every warp of the lane quadrant holds its boundary reads
-                    if (kZeroAcc) named_bar_sync(2 + q, 32 * kEpiGroups);
-                }
-                // One chunk of 16 accumulator columns.  `v` holds the chunk (already loaded); the NEXT chunk (or just its
-                // first column, the right-hand neighbour of column 15) is requested before the arithmetic on `v` starts
-                // and waited for only when the taps need it, so the TMEM read latency overlaps the sqrt chain.
-                auto do_chunk = [&](const int ch, uint32_t (&v)[kChunk], uint32_t (&vnx)[kChunk]) {
-                    const int c0 = ch * kChunk;
-                    const bool hasn = (c0 + kChunk) < BN;
-                    if (ch + 1 < cend) tmem_ld_x16(trow + c0 + kChunk, vnx);
-                    else vnx[0] = vright;
+                float dprev = kBig, dright = kBig;
+                // first chunk and the boundary columns of the neighbouring column groups: one wait for all
+                if (cbeg > 0) tmem_ld_x1(trow + cbeg * kChunk - 1, vleft);
+                if (cend * kChunk < BN) tmem_ld_x1(trow + cend * kChunk, vright);
+                tmem_ld_x16(trow + cbeg * kChunk, v);
+                tmem_ld_wait();
+                if (cbeg > 0) dprev = sqrt_approx(fabsf(fmaf(__uint_as_float(vleft), -2.f, tl->na[cbeg * kChunk - 1])));
+                if (cend * kChunk < BN) dright = sqrt_approx(fabsf(fmaf(__uint_as_float(vright), -2.f, tl->na[cend * kChunk])));
+                // nobody refills a column before every warp of the lane quadrant holds its boundary reads
+                if (!EOSVR_EXP_ON(p, 256)) named_bar_sync(2 + q, 32 * EG);
+                long long t_e1 = 0;
+                if (prof) { t_e1 = clock64(); e_pre += t_e1 - t_e0; }
 
+                // One chunk of 16 accumulator columns per iteration.  x = |a|^2 + |b|^2 - 2 a.b and d = sqrt(x) consume the
+                // landing registers, which are then immediately re-used for the NEXT chunk's TMEM read; that read is
+                // waited for only when the last column's right-hand neighbour is needed, so its latency overlaps the taps.
+#pragma unroll 1
+                for (int ch = cbeg; ch < cend; ++ch) {
+                    const int c0 = ch * kChunk;
                     float d[kChunk];
                     float minx = kBig;
-                    const float4 *na4 = reinterpret_cast<const float4 *>(tl->na + c0);
+                    {
+                        const float4 *na4 = reinterpret_cast<const float4 *>(tl->na + c0);
 #pragma unroll
-                    for (int j4 = 0; j4 < kChunk / 4; ++j4) {
-                        const float4 a = na4[j4];
-                        const float aa[4] = {a.x, a.y, a.z, a.w};
+                        for (int j4 = 0; j4 < kChunk / 4; ++j4) {
+                            const float4 a = na4[j4];
+                            const float aa[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            const int j = j4 * 4 + jj;
-                            const float x = fmaf(-2.f, __uint_as_float(v[j]), nb) + aa[jj];
-                            minx = fminf(minx, x);
-                            d[j] = sqrt_approx(fabsf(x));
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int j = j4 * 4 + jj;
+                                const float x = fmaf(__uint_as_float(v[j]), -2.f, aa[jj]);
+                                minx = fminf(minx, x);
+                                d[j] = EOSVR_EXP_ON(p, 512) ? fabsf(x) : sqrt_approx(fabsf(x));
+                            }
                         }
                     }
-                    tmem_ld_wait_x16(vnx);
-                    float dn = kBig;
-                    if (hasn) {
-                        const float x = fmaf(-2.f, __uint_as_float(vnx[0]), nb) + tl->na[c0 + kChunk];
-                        dn = sqrt_approx(fabsf(x));
-                    }
+                    const bool more = ch + 1 < cend;
+                    if (more) tmem_ld_x16(trow + c0 + kChunk, v);
+                    bool any0 = false, any1 = false, any2 = false, any3 = false;      // four short predicate chains
                     const float dprev_in = dprev;
-                    dprev = d[kChunk - 1];
-
-                    bool any = false;
-                    float t[kChunk];
                     const float4 *wl4 = reinterpret_cast<const float4 *>(tl->wl + c0);
                     const float4 *wr4 = reinterpret_cast<const float4 *>(tl->wr + c0);
                     const float4 *th4 = reinterpret_cast<const float4 *>(tl->thr + c0);
+                    float4 l3, r3, th3;
 #pragma unroll
                     for (int j4 = 0; j4 < kChunk / 4; ++j4) {
                         const float4 l = wl4[j4], r = wr4[j4], th = th4[j4];
-                        const float ll[4] = {l.x, l.y, l.z, l.w};
-                        const float rr[4] = {r.x, r.y, r.z, r.w};
-                        const float tt[4] = {th.x, th.y, th.z, th.w};
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            const int j = j4 * 4 + jj;
-                            const float dl = j ? d[j - 1] : dprev_in;
-                            const float dr = (j < kChunk - 1) ? d[j + 1] : dn;
-                            t[j] = fmaf(ll[jj], dl, fmaf(rr[jj], dr, d[j]));
-                            any |= (t[j] <= tt[jj]);
-                        }
+                        const float dl0 = j4 ? d[j4 * 4 - 1] : dprev_in;
+                        const float t0 = fmaf(l.x, dl0, fmaf(r.x, d[j4 * 4 + 1], d[j4 * 4 + 0]));
+                        const float t1 = fmaf(l.y, d[j4 * 4 + 0], fmaf(r.y, d[j4 * 4 + 2], d[j4 * 4 + 1]));
+                        const float t2 = fmaf(l.z, d[j4 * 4 + 1], fmaf(r.z, d[j4 * 4 + 3], d[j4 * 4 + 2]));
+                        any0 |= (t0 <= th.x); any1 |= (t1 <= th.y); any2 |= (t2 <= th.z);
+                        if (j4 < kChunk / 4 - 1) {
+                            const float t3 = fmaf(l.w, d[j4 * 4 + 2], fmaf(r.w, d[j4 * 4 + 4], d[j4 * 4 + 3]));
+                            any3 |= (t3 <= th.w);
+                        } else { l3 = l; r3 = r; th3 = th; }
                     }
+                    // last column: its right-hand neighbour is the first column of the next chunk (or of the next group)
+                    float dn = dright;
+                    if (more) {
+                        tmem_ld_wait_x16(v);
+                        dn = sqrt_approx(fabsf(fmaf(__uint_as_float(v[0]), -2.f, tl->na[c0 + kChunk])));
+                    }
+                    {
+                        const float t15 = fmaf(l3.w, d[kChunk - 2], fmaf(r3.w, dn, d[kChunk - 1]));
+                        any3 |= (t15 <= th3.w);
+                    }
+                    dprev = d[kChunk - 1];
                     const bool guard = (minx < xfloor) || (fminf(dprev_in, dn) < dfloor);
-                    if (__any_sync(0xffffffffu, any || guard) && !(p.exp_mode & 32)) {
-                        // ---- rare path (whole warp, kept small: one loop body, no unrolling).  Only the columns in
-                        //      which some lane is below its threshold (or, if the cancellation guard fired, all
-                        //      columns) are visited.  The column and its two neighbours are read again from TMEM
-                        //      (same arithmetic, same bits as above) so no register array is indexed dynamically.
-                        //      First tighten the threshold with the warp minimum, then park what is still below it
-                        //      in the warp's staging buffer. ----
+                    const bool hit = (any0 || any1) || (any2 || any3) || guard;
+                    if ((DIAG && p.dbg != nullptr) || (__any_sync(0xffffffffu, hit) && !EOSVR_EXP_ON(p, 32))) {
+                        // ---- slow path (whole warp; ~10 % of the chunks): the taps once more from the distances still in
+                        //      registers (same arithmetic, same bits), now keeping every column's value and a mask of
+                        //      the columns in which some lane is below its threshold (all columns if the cancellation
+                        //      guard fired).  Per such column: tighten the threshold with the warp minimum, then park
+                        //      what is still below it in the warp's staging buffer.  The fast path keeps only d[] alive
+                        //      across the vote, so this block costs it no registers. ----
+                        float t[kChunk];
                         unsigned cm = 0;
-                        {
-                            const float4 *th4b = reinterpret_cast<const float4 *>(tl->thr + c0);
 #pragma unroll
-                            for (int j4 = 0; j4 < kChunk / 4; ++j4) {
-                                const float4 th = th4b[j4];
-                                cm |= (t[j4 * 4 + 0] <= th.x ? 1u : 0u) << (j4 * 4 + 0);
-                                cm |= (t[j4 * 4 + 1] <= th.y ? 1u : 0u) << (j4 * 4 + 1);
-                                cm |= (t[j4 * 4 + 2] <= th.z ? 1u : 0u) << (j4 * 4 + 2);
-                                cm |= (t[j4 * 4 + 3] <= th.w ? 1u : 0u) << (j4 * 4 + 3);
+                        for (int j4 = 0; j4 < kChunk / 4; ++j4) {
+                            const float4 l = wl4[j4], r = wr4[j4], th = th4[j4];
+                            const float ll[4] = {l.x, l.y, l.z, l.w}, rr[4] = {r.x, r.y, r.z, r.w}, tt[4] = {th.x, th.y, th.z, th.w};
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int j = j4 * 4 + jj;
+                                const float dl = j ? d[j - 1] : dprev_in;
+                                const float dr = (j < kChunk - 1) ? d[j + 1] : dn;
+                                t[j] = fmaf(ll[jj], dl, fmaf(rr[jj], dr, d[j]));
+                                cm |= (t[j] <= tt[jj] ? 1u : 0u) << j;
+                            }
+                        }
+                        if (DIAG && p.dbg != nullptr && rowok && !p.seed_mode) {
+#pragma unroll
+                            for (int j = 0; j < kChunk; ++j) {
+                                const int32_t rm = tl->row[c0 + j];
+                                if (rm >= 0) p.dbg[static_cast<int64_t>(rm) * p.G + g] = t[j];
                             }
                         }
                         if (guard) cm = 0xFFFFu;
                         cm = __reduce_or_sync(0xffffffffu, cm);
-                        const bool rowok = g < p.G;
                         const bool any_guard = __any_sync(0xffffffffu, guard);
 #pragma unroll 1
                         while (cm) {
-                            const int c = c0 + __ffs(cm) - 1;              // warp-uniform
+                            const int jc = __ffs(cm) - 1;                  // warp-uniform
                             cm &= cm - 1;
+                            const int c = c0 + jc;
                             const int32_t rm = tl->row[c];
                             if (rm < 0) continue;                          // warp-uniform
-                            float tj;
+                            const float tj = pick16(t, jc);                // warp-uniform index: a jump, no local memory
                             bool uns = false;
-                            if (!any_guard) {
-                                tj = pick16(t, c - c0);                    // warp-uniform index: a jump, no local memory
-                            } else {
-                                // some lane is inside the cancellation guard: the column and its neighbours again,
-                                // straight from TMEM (same arithmetic, same bits as the fast path)
-                                uint32_t vc, vl = 0, vr = 0;
-                                const bool hl = c > 0, hr = c + 1 < BN;
-                                tmem_ld_x1(trow + c, vc);
-                                if (hl && c != cbeg * kChunk) tmem_ld_x1(trow + c - 1, vl);
-                                if (hr && c + 1 != cend * kChunk) tmem_ld_x1(trow + c + 1, vr);
-                                tmem_ld_wait();
-                                if (c == cbeg * kChunk) vl = vleft;                 // other column groups' columns may
-                                if (c + 1 == cend * kChunk) vr = vright;            // already be zeroed: use the early reads
-                                const float dj = sqrt_approx(fabsf(fmaf(-2.f, __uint_as_float(vc), nb) + tl->na[c]));
-                                const float dl = hl ? sqrt_approx(fabsf(fmaf(-2.f, __uint_as_float(vl), nb) + tl->na[c - 1])) : kBig;
-                                const float dr = hr ? sqrt_approx(fabsf(fmaf(-2.f, __uint_as_float(vr), nb) + tl->na[c + 1])) : kBig;
-                                const float wlc = tl->wl[c], wrc = tl->wr[c];
-                                tj = fmaf(wlc, dl, fmaf(wrc, dr, dj));
-                                const float m3 = fminf(dj, fminf(wlc > 0.f ? dl : kBig, wrc > 0.f ? dr : kBig));
+                            if (any_guard) {
+                                // inside the cancellation guard the screening value is not trusted: always a candidate
+                                const float dj = pick16(d, jc);
+                                const float dl = jc ? pick16(d, jc - 1) : dprev_in;
+                                const float dr = (jc < kChunk - 1) ? pick16(d, jc + 1) : dn;
+                                const float m3 = fminf(dj, fminf(tl->wl[c] > 0.f ? dl : kBig, tl->wr[c] > 0.f ? dr : kBig));
                                 uns = rowok && (m3 < dfloor);
                             }
                             float thr = __uint_as_float(*reinterpret_cast<volatile unsigned int *>(&tl->thr[c]));
@@ -813,34 +853,31 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                     }
-                    if (p.dbg != nullptr && g < p.G && !p.seed_mode) {
-#pragma unroll
-                        for (int j = 0; j < kChunk; ++j) {
-                            const int32_t rm = tl->row[c0 + j];
-                            if (rm >= 0) p.dbg[static_cast<int64_t>(rm) * p.G + g] = t[j];
-                        }
-                    }
-                };
-                for (int ch = cbeg; ch < cend; ch += 2) {
-                    do_chunk(ch, va, vb);
-                    // zero one chunk behind: the rare path of chunk ch may still read the last column of chunk ch - 1
-                    if (kZeroAcc && ch > cbeg) tmem_st_zero_x16(trow + (ch - 1) * kChunk);
-                    if (ch + 1 < cend) {
-                        do_chunk(ch + 1, vb, va);
-                        if (kZeroAcc) tmem_st_zero_x16(trow + ch * kChunk);
-                    }
+                    // refill one chunk behind (the next group's boundary reads are protected by the quadrant barrier)
+                    if (ch > cbeg && !EOSVR_EXP_ON(p, 128)) tmem_st_fill8_x16(trow + c0 - kChunk, fv);
                 }
-                if (kZeroAcc && cend > cbeg) { tmem_st_zero_x16(trow + (cend - 1) * kChunk); tmem_st_wait(); }   // (a column
-                                                                          // group is empty when the tile has one chunk)
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
-                if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
-                if (prof) e_busy += clock64() - t_e0;
+                if (prof) e_loop += clock64() - t_e1;
+                if (!EOSVR_EXP_ON(p, 128)) tmem_st_fill8_x16(trow + (cend - 1) * kChunk, fv);
+                tmem_st_wait();
+            } else if (!EOSVR_EXP_ON(p, 256)) {
+                named_bar_sync(2 + q, 32 * EG);           // (a column group is empty when the tile has fewer chunks than groups)
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
+            if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
+            if (pend_thr != 0xFFFFFFFFu) atomicMin(&tl->thr[te], pend_thr);
+            if (prof) e_busy += clock64() - t_e0;
+            cursor_next(p, cur, npairs);
+            cursor_next(p, ahead, npairs);
         }
         if (wn) flush_staged(p, wstage, wn, lane);
-        if (prof && lane == 0) { atomicAdd(&p.ctr->cyc_epi_busy, e_busy); atomicAdd(&p.ctr->cyc_epi_wait, e_wait); }
+        if (prof && lane == 0) {
+            atomicAdd(&p.ctr->cyc_epi_busy, e_busy); atomicAdd(&p.ctr->cyc_epi_wait, e_wait);
+            atomicAdd(&p.ctr->cyc_epi_pre, e_pre); atomicAdd(&p.ctr->cyc_epi_loop, e_loop);
+        }
+    } else {
+        if (kRepartition) reg_release<kLightRegs>();             // idle warps (issuer slots of the peer CTA)
     }
 
     tc_fence_before();
@@ -894,10 +931,9 @@ struct RerankParams {
     const unsigned int *gthr;
     unsigned long long *best;
     int32_t *rowflag;
-    int32_t *flaglist;
     const OvfCand *ovf;
     int32_t ovf_cap;
-    const float *margin;     // per plan column
+    const float *epsd, *wl, *wr;   // per plan column (column_margin)
     int32_t planR, planBN, planHalo;
     int32_t prof;            // EOSVR_EXP bit 64: phase timing of k_rerank_rows into the cycle counters
     int32_t rows_per_block;  // consecutive probe rows per k_rerank_rows block (1..kRrRowsPerBlock)
@@ -923,16 +959,15 @@ __device__ __forceinline__ float exact_score(const RerankParams &p, int64_t row,
     return exact_t(p.probes, p.P, p.D, p.rpe, row, p.gal + g * p.D, p.lam1, p.lam2, lane);
 }
 
-// Spill-over candidates (row lists that filled up): one warp per entry.  Exits at once when empty.
-__global__ void k_rerank_ovf(const RerankParams p)
+// Spill-over candidates (row lists that filled up): one warp per entry, grid-strided over the warps of the
+// calling kernel.  Nothing to do when the buffer is empty (the normal case).
+__device__ __forceinline__ void rerank_spilled(const RerankParams &p, int64_t warp_id, int64_t n_warps, int lane)
 {
     const unsigned cnt = p.ctr->ovf_count;
     if (cnt == 0) return;
     const int64_t n = cnt < static_cast<unsigned>(p.ovf_cap) ? cnt : p.ovf_cap;
-    const int lane = threadIdx.x & 31;
-    const int64_t nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     unsigned long long done = 0;
-    for (int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < n; w += nw) {
+    for (int64_t w = warp_id; w < n; w += n_warps) {
         const OvfCand c = p.ovf[w];
         if (c.tbits != kCandUnsafe && __uint_as_float(c.tbits) > __uint_as_float(p.gthr[c.p])) continue;
         const float t = exact_score(p, c.p, c.g, lane);
@@ -980,6 +1015,7 @@ __global__ void k_rerank(const RerankParams p)
         if (done) atomicAdd(&p.ctr->n_exact, done);
         if (uns) atomicAdd(&p.ctr->n_unsafe, uns);
     }
+    rerank_spilled(p, (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, nw, lane);
 }
 
 // Block-per-row re-rank, warp-per-candidate.  The three probe rows the taps need are staged in shared memory
@@ -1055,7 +1091,7 @@ k_rerank_rows(const RerankParams p)
           s_cnt[tid] = p.rowcnt[row];
           s_thr[tid] = __uint_as_float(p.gthr[row]);
           // one-sided error bound of the row's screening values (half of the two-sided threshold margin)
-          s_eps[tid] = 0.5f * p.margin[(row / p.planR) * p.planBN + p.planHalo + (row % p.planR)];
+          s_eps[tid] = 0.5f * column_margin(p.epsd, p.wl, p.wr, (row / p.planR) * p.planBN + p.planHalo + (row % p.planR));
       }
       if (!COS && r0 > 0) stage_row(r0 - 1);
       for (int64_t q = r0; q < r0 + PF && q <= last_needed; ++q) stage_row(q);
@@ -1258,34 +1294,69 @@ k_rerank_rows(const RerankParams p)
     }
     unsafe_n = static_cast<unsigned long long>(warp_sum(static_cast<double>(unsafe_n)));
     if (lane == 0 && unsafe_n) atomicAdd(&p.ctr->n_unsafe, unsafe_n);
+    rerank_spilled(p, static_cast<int64_t>(blockIdx.x) * (kRrThreads / 32) + warp,
+                   static_cast<int64_t>(gridDim.x) * (kRrThreads / 32), lane);
 }
 
-// Rows whose candidates overflowed the list (or all rows, for eosvr_match_exact) are resolved by
-// exhaustive exact evaluation.  Early exit when nothing overflowed.
-__global__ void k_compact_flags(const RerankParams p)
+__device__ __forceinline__ void finalize_row(const unsigned long long *best, int64_t i, int negate,
+                                             uint64_t *out_packed, float *out_score, int64_t *out_idx)
 {
-    if (p.ctr->overflow == 0) return;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.P;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        if (p.rowflag[i]) {
-            const unsigned int pos = atomicAdd(&p.ctr->n_flag_rows, 1u);
-            p.flaglist[pos] = static_cast<int32_t>(i);
-        }
+    const unsigned long long v = __ldcg(best + i);       // L2: other blocks' atomicMin results
+    if (out_packed) out_packed[i] = v;
+    if (out_score) out_score[i] = (v == ~0ull) ? __int_as_float(0x7fc00000) : (negate ? -unpack_score(v) : unpack_score(v));
+    if (out_idx) out_idx[i] = (v == ~0ull) ? -1 : static_cast<int64_t>(v & 0xFFFFFFFFull);
+}
+
+// Last kernel of a match call.  Normal case (no row list overflowed beyond the shared spill buffer): unpack the
+// winners, grid-strided.  Otherwise the flagged rows (ctr->overflow == 1), or all rows (== 2, eosvr_match_exact),
+// are first resolved by exhaustive exact evaluation: every block derives the same ordered list of flagged rows,
+// the grid shares the (row, strip of gallery rows) work items, and the LAST block to finish unpacks the winners
+// (its atomic ticket orders it after every other block's atomicMin).
+constexpr int kStrip = 8;          // gallery rows per warp work item in the exhaustive evaluation
+constexpr int kFinThreads = 256;
+constexpr int kMaxFlagList = 2048;
+
+__global__ void __launch_bounds__(kFinThreads)
+k_finish(const RerankParams p, int negate, uint64_t *out_packed, float *out_score, int64_t *out_idx)
+{
+    const unsigned mode = p.ctr->overflow;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (mode == 0) {
+        for (int64_t i = static_cast<int64_t>(blockIdx.x) * kFinThreads + tid; i < p.P; i += static_cast<int64_t>(gridDim.x) * kFinThreads)
+            finalize_row(p.best, i, negate, out_packed, out_score, out_idx);
+        return;
     }
-}
-
-constexpr int kStrip = 8;    // gallery rows per warp work item in the exhaustive kernel
-
-__global__ void k_exact_fallback(const RerankParams p)
-{
-    if (p.ctr->overflow == 0) return;
-    const int lane = threadIdx.x & 31;
-    const int64_t nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-    int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nrows = p.ctr->n_flag_rows;
+    __shared__ int32_t s_list[kMaxFlagList];
+    __shared__ int s_wcnt[kFinThreads / 32];
+    __shared__ int s_n;
+    __shared__ unsigned int s_ticket;
+    int64_t nrows = p.P;                                 // mode 2, or too many flagged rows: every row is a candidate row
+    bool listed = false;
+    if (mode == 1) {
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        for (int64_t i0 = 0; i0 < p.P; i0 += kFinThreads) {          // ordered compaction, identical in every block
+            const int64_t i = i0 + tid;
+            const bool f = i < p.P && p.rowflag[i] != 0;
+            const unsigned m = __ballot_sync(0xffffffffu, f);
+            if (lane == 0) s_wcnt[warp] = __popc(m);
+            __syncthreads();
+            int base = s_n;
+            for (int w = 0; w < warp; ++w) base += s_wcnt[w];
+            const int pos = base + __popc(m & ((1u << lane) - 1u));
+            if (f && pos < kMaxFlagList) s_list[pos] = static_cast<int32_t>(i);
+            __syncthreads();
+            if (tid == 0) { int t = 0; for (int w = 0; w < kFinThreads / 32; ++w) t += s_wcnt[w]; s_n += t; }
+            __syncthreads();
+        }
+        if (s_n <= kMaxFlagList) { nrows = s_n; listed = true; }
+        if (blockIdx.x == 0 && tid == 0) p.ctr->n_flag_rows = static_cast<unsigned>(s_n);
+    } else if (blockIdx.x == 0 && tid == 0) p.ctr->n_flag_rows = static_cast<unsigned>(p.P);
     const int64_t nstrips = (p.G + kStrip - 1) / kStrip;
-    for (; w < nrows * nstrips; w += nw) {
-        const int64_t row = p.flaglist[w / nstrips];
+    const int64_t nw = static_cast<int64_t>(gridDim.x) * (kFinThreads / 32);
+    for (int64_t w = static_cast<int64_t>(blockIdx.x) * (kFinThreads / 32) + warp; w < nrows * nstrips; w += nw) {
+        const int64_t row = listed ? s_list[w / nstrips] : w / nstrips;
+        if (!listed && mode == 1 && p.rowflag[row] == 0) continue;
         const int64_t g0 = (w % nstrips) * kStrip, g1 = min(g0 + kStrip, p.G);
         unsigned long long loc = ~0ull;
         for (int64_t g = g0; g < g1; ++g) {
@@ -1295,17 +1366,14 @@ __global__ void k_exact_fallback(const RerankParams p)
         }
         if (lane == 0) atomicMin(p.best + row, loc);
     }
-}
-
-__global__ void k_finalize(const unsigned long long *__restrict__ best, int64_t P, int negate,
-                           uint64_t *out_packed, float *out_score, int64_t *out_idx)
-{
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    const unsigned long long v = best[i];
-    if (out_packed) out_packed[i] = v;
-    if (out_score) out_score[i] = (v == ~0ull) ? __int_as_float(0x7fc00000) : (negate ? -unpack_score(v) : unpack_score(v));
-    if (out_idx) out_idx[i] = (v == ~0ull) ? -1 : static_cast<int64_t>(v & 0xFFFFFFFFull);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(&p.ctr->done_blocks, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    for (int64_t i = tid; i < p.P; i += kFinThreads)
+        finalize_row(p.best, i, negate, out_packed, out_score, out_idx);
 }
 
 __global__ void k_merge_top1(const unsigned long long *__restrict__ gathered, int nshards, int64_t P,
@@ -1338,99 +1406,137 @@ int launch_merge(const uint64_t *gathered, int32_t nshards, int64_t P, uint64_t 
 // -------------------------------------------------------------------------------------------
 // Host orchestration of one eosvr_match call (all asynchronous on `st`).
 // -------------------------------------------------------------------------------------------
-static int g_num_sms = 0;
-
-static int g_max_clusters[3] = {0, 0, 0};   // co-resident clusters of k_match_screen<NP>, NP = 1, 2
-
-template <int NP>
-static int launch_screen_np(const CUtensorMap &tmA, const CUtensorMap &tmB, const ScreenParams &sp, cudaStream_t st)
+// Experiment knobs, read from the environment ONCE per process.  None of them changes results: unit order, gallery
+// tiles per unit, seed pass, epilogue warps, issuer warps, and the EOSVR_EXP measurement bits
+// 16 (cycle accounting of the screening kernel) and 64 (phase timing of the re-rank).  The result-destroying
+// timing modes (EOSVR_EXP bits 1, 2, 4, 32) exist only in builds with -DEOSVR_EXPERIMENTS (tools/exp_perf.sh).
+struct Tunables {
+    int order, tpu, seed, ew, issuers, exp;
+};
+static int env_int(const char *name, int dflt)
 {
-    auto kern = k_match_screen<NP>;
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+const Tunables &tunables()
+{
+    static const Tunables t = [] {
+        Tunables v;
+        v.order = env_int("EOSVR_ORDER", 1);
+        v.tpu = env_int("EOSVR_TPU", 0);
+        v.seed = env_int("EOSVR_SEED", 1);
+        v.ew = env_int("EOSVR_EW", 0);
+        v.issuers = env_int("EOSVR_ISSUERS", 0);
+        v.exp = env_int("EOSVR_EXP", 0);
+#ifndef EOSVR_EXPERIMENTS
+        v.exp &= (16 | 64);
+#endif
+        return v;
+    }();
+    return t;
+}
+
+static std::mutex g_dev_mu;
+static DeviceState g_dev[64];
+
+static int device_state(DeviceState **out)
+{
+    int dev = 0;
+    EOSVR_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return EOSVR_EINVAL; }
+    std::lock_guard<std::mutex> lock(g_dev_mu);
+    DeviceState &d = g_dev[dev];
+    if (d.num_sms == 0) EOSVR_CUDA(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    *out = &d;
+    return EOSVR_OK;
+}
+
+template <int EW, bool DIAG>
+static int launch_screen_t(DeviceState *ds, const CUtensorMap &tmA, const CUtensorMap &tmB, const ScreenParams &sp, cudaStream_t st)
+{
+    auto kern = k_match_screen<EW, DIAG>;
+    constexpr size_t smem = screen_smem<EW>();
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2 * NP; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cfg.blockDim = dim3(kThreads, 1, 1);
-    cfg.dynamicSmemBytes = kScreenSmem;
+    cfg.blockDim = dim3(screen_threads(EW), 1, 1);
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    if (g_max_clusters[NP] == 0) {
-        EOSVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kScreenSmem)));
-        cfg.gridDim = dim3(static_cast<unsigned>(g_num_sms / (2 * NP) * (2 * NP)), 1, 1);
-        int n = 0;
-        EOSVR_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-        if (n < 1) { set_error("k_match_screen<%d>: no cluster of %d CTAs can be resident", NP, 2 * NP); return EOSVR_ECUDA; }
-        g_max_clusters[NP] = n;
+    int &maxcl = ds->max_clusters[DIAG ? 1 : 0][EW == 16 ? 1 : 0];
+    {
+        std::lock_guard<std::mutex> lock(g_dev_mu);
+        if (maxcl == 0) {
+            EOSVR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            cfg.gridDim = dim3(static_cast<unsigned>(ds->num_sms / 2 * 2), 1, 1);
+            int n = 0;
+            EOSVR_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+            if (n < 1) { set_error("k_match_screen<%d>: no CTA pair can be resident", EW); return EOSVR_ECUDA; }
+            maxcl = n;
+        }
     }
-    const int64_t ncl = sp.n_units < g_max_clusters[NP] ? sp.n_units : g_max_clusters[NP];
-    cfg.gridDim = dim3(static_cast<unsigned>(ncl * 2 * NP), 1, 1);
+    const int64_t ncl = sp.n_units < maxcl ? sp.n_units : maxcl;
+    cfg.gridDim = dim3(static_cast<unsigned>(ncl * 2), 1, 1);
     EOSVR_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, sp));
     return EOSVR_OK;
 }
 
-// pairs per cluster of the next screening launches.  Two pairs sharing (multicasting) the gallery slab halve its
-// L2 reads but measured 3-6 % SLOWER on B200 (the kernel is not L2-bound), so the default is
-// one pair; EOSVR_NP=2 selects the 2-pair cluster for experiments when there are at least two probe tiles.
-static int choose_np(int64_t NT)
+// Epilogue warps: 16 when the rows are short (the epilogue, not the tensor pipe, bounds a tile below ~1024
+// dimensions), 8 otherwise.
+static int choose_ew(int32_t Dp)
 {
-    static int np_env = -1;
-    if (np_env < 0) { const char *e = getenv("EOSVR_NP"); np_env = e ? atoi(e) : 0; }
-    return (np_env == 2 && NT >= 2) ? 2 : 1;
+    const int e = tunables().ew;
+    if (e == 8 || e == 16) return e;
+    return Dp <= 1024 ? 16 : 8;
 }
 
 struct ScreenView {          // the screening copy of the gallery a launch reads (one per metric)
     const float *gnorm;
-    const CUtensorMap *tmapA, *tmapSeed, *tmapAH, *tmapSeedH;
+    const CUtensorMap *tmapA, *tmapSeed;
 };
 
-static int launch_screen(const eosvr_gallery *g, const ScreenView &sv, eosvr_workspace *ws, const MatchPlan &pl, int np,
+static int launch_screen(DeviceState *ds, const eosvr_gallery *g, const ScreenView &sv, eosvr_workspace *ws, const MatchPlan &pl,
                          bool seed, const CUtensorMap &tmB, int64_t gallery_tiles, int64_t g_stride, int64_t P,
                          bool timed, cudaStream_t st)
 {
+    const Tunables &tn = tunables();
     ScreenParams sp;
-    sp.gnorm = sv.gnorm; sp.G = g->G; sp.KB = g->Dp / kBK; sp.BN = pl.BN; sp.NT = pl.NT;
-    sp.NTG = pl.NT / np;
-    sp.GT = gallery_tiles;
+    sp.gnorm = sv.gnorm; sp.G = g->G; sp.KB = g->Dp / kBK; sp.BN = pl.BN; sp.NT = static_cast<int32_t>(pl.NT);
+    sp.GT = static_cast<int32_t>(gallery_tiles);
     const int seed_mode = seed ? 1 : 0;
-    const int64_t total_tiles = sp.NT * sp.GT;
-    int64_t tpu = total_tiles / (static_cast<int64_t>(g_num_sms / 2) * 6);
+    const int64_t total_tiles = static_cast<int64_t>(sp.NT) * sp.GT;
+    int64_t tpu = total_tiles / (static_cast<int64_t>(ds->num_sms / 2) * 6);
     if (tpu < 1) tpu = 1;
     if (tpu > 16) tpu = 16;
     if (tpu > sp.GT) tpu = sp.GT;
+    if (tn.tpu > 0 && !seed_mode) tpu = tn.tpu < sp.GT ? tn.tpu : sp.GT;
     sp.TPU = static_cast<int32_t>(tpu);
-    sp.n_chunks = (sp.GT + tpu - 1) / tpu;
-    sp.n_units = sp.n_chunks * sp.NTG;
+    sp.n_chunks = static_cast<int32_t>((sp.GT + tpu - 1) / tpu);
+    if (static_cast<int64_t>(sp.n_chunks) * sp.NT > 0x7FFFFFFFll) { set_error("match: too many work units"); return EOSVR_EINVAL; }
+    sp.n_units = sp.n_chunks * sp.NT;
+    sp.order = tn.order;
     sp.g_stride = g_stride; sp.seed_mode = seed_mode;
-    {
-        static int order_env = -1, tpu_env = -1;
-        if (order_env < 0) { const char *e = getenv("EOSVR_ORDER"); order_env = e ? atoi(e) : 1; }
-        if (tpu_env < 0) { const char *e = getenv("EOSVR_TPU"); tpu_env = e ? atoi(e) : 0; }
-        sp.order = order_env;
-        if (tpu_env > 0 && !seed_mode) {
-            sp.TPU = static_cast<int32_t>(tpu_env < sp.GT ? tpu_env : sp.GT);
-            sp.n_chunks = (sp.GT + sp.TPU - 1) / sp.TPU;
-            sp.n_units = sp.n_chunks * sp.NTG;
-        }
-    }
-    sp.na = ws->na; sp.wl = ws->wl; sp.wr = ws->wr; sp.margin = ws->margin; sp.rowmap = ws->rowmap;
+    sp.issuers = ds->issuers > 0 ? ds->issuers : kIssuers;
+    sp.na = ws->na; sp.wl = ws->wl; sp.wr = ws->wr; sp.epsd = ws->epsd; sp.rowmap = ws->rowmap;
     sp.gthr = ws->gthr; sp.cand = ws->cand; sp.rowcnt = ws->rowcnt; sp.cand_cap = static_cast<int32_t>(ws->cand_cap);
     sp.ovf = ws->ovf; sp.ovf_cap = static_cast<int32_t>(ws->ovf_cap);
     sp.ctr = ws->counters; sp.rowflag = ws->rowflag;
     sp.idesc = umma_idesc_f16(g->screen_fmt == EOSVR_SCREEN_F16 ? 0 : 1, kPairM, pl.BN);
     sp.dbg = (!seed_mode && ws->dbg && ws->dbg_elems >= P * g->G) ? ws->dbg : nullptr;
-    {
-        static int exp_env = -1;
-        if (exp_env < 0) { const char *e = getenv("EOSVR_EXP"); exp_env = e ? atoi(e) : 0; }
-        sp.exp_mode = exp_env;
-    }
-    const bool rec = timed && ws->timing_on && ws->timing_calls < kTimingRing;
-    if (rec) EOSVR_CUDA(cudaEventRecord(ws->ev0[ws->timing_calls], st));
+    sp.exp_mode = tn.exp;
+    const bool rec = timed && ws->timing_on;
+    const int slot = static_cast<int>(ws->timing_calls % kTimingRing);
+    if (rec) EOSVR_CUDA(cudaEventRecord(ws->ev0[slot], st));
+    const int ew = choose_ew(g->Dp);
+    const bool diag = sp.dbg != nullptr || (tn.exp & 16) != 0;
+    const CUtensorMap &tmA = seed ? *sv.tmapSeed : *sv.tmapA;
     int rc;
-    if (np == 2) rc = launch_screen_np<2>(seed ? *sv.tmapSeedH : *sv.tmapAH, tmB, sp, st);
-    else rc = launch_screen_np<1>(seed ? *sv.tmapSeed : *sv.tmapA, tmB, sp, st);
+    if (ew == 16) rc = diag ? launch_screen_t<16, true>(ds, tmA, tmB, sp, st) : launch_screen_t<16, false>(ds, tmA, tmB, sp, st);
+    else rc = diag ? launch_screen_t<8, true>(ds, tmA, tmB, sp, st) : launch_screen_t<8, false>(ds, tmA, tmB, sp, st);
     if (rc) return rc;
-    if (rec) { EOSVR_CUDA(cudaEventRecord(ws->ev1[ws->timing_calls], st)); ++ws->timing_calls; }
+    if (rec) { EOSVR_CUDA(cudaEventRecord(ws->ev1[slot], st)); ++ws->timing_calls; }
     EOSVR_COUNT_LAUNCH(1);
     return EOSVR_OK;
 }
@@ -1442,23 +1548,24 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
     if (P == 0) return EOSVR_OK;
     const bool cosm = metric == EOSVR_METRIC_COSINE;
     if (cosm) { lam1 = 0.f; lam2 = 1.f; rpe = 1; }          // no temporal taps: every probe row stands alone
-    ScreenView sv{g->gnorm, &g->tmapA, &g->tmapSeed, &g->tmapAH, &g->tmapSeedH};
+    DeviceState *ds = nullptr;
+    int rc = device_state(&ds);
+    if (rc) return rc;
+    if (!exact_only && ds->issuers == 0) {                   // first screening call on this device: self-check
+        rc = screening_selfcheck(ds, st);
+        if (rc) return rc;
+    }
+    ScreenView sv{g->gnorm, &g->tmapA, &g->tmapSeed};
     const float *scalars = g->scalars;
     if (cosm && !exact_only) {
-        int rc = build_cosine_copy(g, st);                  // first cosine call builds the normalised copy
+        rc = build_cosine_copy(g, st);                      // first cosine call builds the normalised copy
         if (rc) return rc;
         EOSVR_CUDA(cudaStreamWaitEvent(st, g->cos->ready, 0));
-        sv = ScreenView{g->cos->gnorm, &g->cos->tmapA, &g->cos->tmapSeed, &g->cos->tmapAH, &g->cos->tmapSeedH};
+        sv = ScreenView{g->cos->gnorm, &g->cos->tmapA, &g->cos->tmapSeed};
         scalars = g->cos->scalars;
     }
-    if (g_num_sms == 0) {
-        int dev = 0;
-        EOSVR_CUDA(cudaGetDevice(&dev));
-        EOSVR_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const Tunables &tn = tunables();
     MatchPlan pl = make_plan(P, rpe);
-    const int np = exact_only ? 1 : choose_np(pl.NT);
-    pl.NT = (pl.NT + np - 1) / np * np;           // pad with empty probe tiles: every pair of a cluster has one
     const int64_t ncol = pl.NT * pl.BN;
     if (ncol > ws->cap_rows) {
         set_error("workspace too small: plan needs %lld rows, capacity %lld", (long long)ncol, (long long)ws->cap_rows);
@@ -1466,88 +1573,80 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
     }
     PlanDev pd{pl.P, pl.rpe, pl.R, pl.halo, pl.BN, pl.NT};
     const int threads = 256;
-
-    k_reset<<<static_cast<unsigned>((P + threads - 1) / threads), threads, 0, st>>>(
-        ws->counters, ws->best, ws->rowflag, ws->rowcnt, ws->gthr, P, exact_only ? 1 : 0);
-    EOSVR_CUDA(cudaGetLastError());
-    EOSVR_COUNT_LAUNCH(1);
+    const int num_sms = ds->num_sms;
+    RowState rs{ws->best, ws->rowflag, ws->rowcnt, ws->gthr};
 
     RerankParams rp;
     rp.probes = probes; rp.gal = g->feats; rp.P = P; rp.G = g->G; rp.offset = g->offset;
     rp.D = g->D; rp.rpe = rpe; rp.metric = metric; rp.lam1 = lam1; rp.lam2 = lam2;
     rp.cand = ws->cand; rp.rowcnt = ws->rowcnt; rp.cand_cap = static_cast<int32_t>(ws->cand_cap);
     rp.ctr = ws->counters; rp.gthr = ws->gthr;
-    rp.best = ws->best; rp.rowflag = ws->rowflag; rp.flaglist = ws->flaglist;
+    rp.best = ws->best; rp.rowflag = ws->rowflag;
     rp.ovf = ws->ovf; rp.ovf_cap = static_cast<int32_t>(ws->ovf_cap);
-    rp.margin = ws->margin; rp.planR = pl.R; rp.planBN = pl.BN; rp.planHalo = pl.halo;
-    { const char *e = getenv("EOSVR_EXP"); rp.prof = (e && (atoi(e) & 64)) ? 1 : 0; }
+    rp.epsd = ws->epsd; rp.wl = ws->wl; rp.wr = ws->wr; rp.planR = pl.R; rp.planBN = pl.BN; rp.planHalo = pl.halo;
+    rp.prof = (tn.exp & 64) ? 1 : 0;
     rp.rows_per_block = 1;
 
     ws->last_tiles = 0;
     ws->last_bn = pl.BN;
-    if (!exact_only) {
+    EOSVR_CUDA(cudaMemsetAsync(ws->counters, 0, sizeof(Counters), st));
+    if (exact_only) {
+        k_reset_exact<<<static_cast<unsigned>((P + threads - 1) / threads), threads, 0, st>>>(ws->counters, rs, P);
+        EOSVR_CUDA(cudaGetLastError());
+        EOSVR_COUNT_LAUNCH(1);
+    } else {
         const unsigned pblocks = static_cast<unsigned>((ncol * 32 + threads - 1) / threads);
 #define EOSVR_PROBE_PREP(T16, NORM)                                                                              \
-        k_probe_prep<T16, NORM><<<pblocks, threads, 0, st>>>(probes, pd, g->D, g->Dp, scalars,                     \
-            static_cast<T16 *>(ws->q16), ws->na, ws->epsd, ws->rowmap, ws->counters)
+        k_probe_prep<T16, NORM><<<pblocks, threads, 0, st>>>(probes, pd, g->D, g->Dp, lam1 / lam2, scalars,         \
+            static_cast<T16 *>(ws->q16), ws->na, ws->epsd, ws->wl, ws->wr, ws->rowmap, rs, ws->counters)
         if (g->screen_fmt == EOSVR_SCREEN_F16) { if (cosm) EOSVR_PROBE_PREP(__half, true); else EOSVR_PROBE_PREP(__half, false); }
         else { if (cosm) EOSVR_PROBE_PREP(__nv_bfloat16, true); else EOSVR_PROBE_PREP(__nv_bfloat16, false); }
 #undef EOSVR_PROBE_PREP
         EOSVR_CUDA(cudaGetLastError());
-        k_column_plan<<<static_cast<unsigned>((ncol + threads - 1) / threads), threads, 0, st>>>(
-            pd, lam1 / lam2, ws->epsd, ws->wl, ws->wr, ws->margin);
-        EOSVR_CUDA(cudaGetLastError());
-        EOSVR_COUNT_LAUNCH(2);
+        EOSVR_COUNT_LAUNCH(1);
 
         CUtensorMap tmB;
-        int rc = encode_tmap_2d(&tmB, ws->q16, g->screen_fmt, static_cast<uint64_t>(ncol),
-                                static_cast<uint64_t>(g->Dp), static_cast<uint32_t>(pl.BN / 2), kBK);
+        rc = encode_tmap_2d(&tmB, ws->q16, g->screen_fmt, static_cast<uint64_t>(ncol),
+                            static_cast<uint64_t>(g->Dp), static_cast<uint32_t>(pl.BN / 2), kBK);
         if (rc) return rc;
         const int64_t GT = (g->G + kPairM - 1) / kPairM;   // 256-row tiles of the CTA pair
         // seed pass over a strided sample of the gallery: tightens every probe row's threshold before the
-        // full pass so that concurrent CTAs do not flood the candidate lists
-        static int seed_env = -1;                           // EOSVR_SEED=0 skips the seed pass (experiments)
-        if (seed_env < 0) { const char *e = getenv("EOSVR_SEED"); seed_env = e ? atoi(e) : 1; }
-        if (seed_env && g->seed_tiles > 0 && GT > g->seed_tiles) {
-            rc = launch_screen(g, sv, ws, pl, np, true, tmB, seed_env == 1 ? g->seed_tiles : 1, g->seed_stride, P, false, st);
+        // full pass so that concurrent CTAs do not flood the candidate lists (EOSVR_SEED=0 skips it: experiments)
+        if (tn.seed && g->seed_tiles > 0 && GT > g->seed_tiles) {
+            rc = launch_screen(ds, g, sv, ws, pl, true, tmB, tn.seed == 1 ? g->seed_tiles : 1, g->seed_stride, P, false, st);
             if (rc) return rc;
         }
-        rc = launch_screen(g, sv, ws, pl, np, false, tmB, GT, 1, P, true, st);
+        rc = launch_screen(ds, g, sv, ws, pl, false, tmB, GT, 1, P, true, st);
         if (rc) return rc;
         ws->last_tiles = pl.NT * GT;
 
         // few probe rows (a single episode): one row per block keeps the call's latency low; large batches take 8
         // consecutive rows per block so that neighbouring probe rows are staged once
-        int64_t rpb = P / (static_cast<int64_t>(g_num_sms) * 8);
+        int64_t rpb = P / (static_cast<int64_t>(num_sms) * 8);
         rpb = rpb < 1 ? 1 : (rpb > kRrRowsPerBlock ? kRrRowsPerBlock : rpb);
         rp.rows_per_block = static_cast<int32_t>(rpb);
         const int64_t rr_blocks = (P + rpb - 1) / rpb;
-        const unsigned rr_grid = static_cast<unsigned>(rr_blocks < static_cast<int64_t>(g_num_sms) * 32 ? rr_blocks : g_num_sms * 32);
+        const unsigned rr_grid = static_cast<unsigned>(rr_blocks < static_cast<int64_t>(num_sms) * 32 ? rr_blocks : num_sms * 32);
         const size_t rr_smem = static_cast<size_t>(cosm ? 2 : 4) * g->D * sizeof(float);
         if ((g->D & 3) == 0 && rr_smem <= 96 * 1024) {
-            static bool rr_attr = false;
-            if (!rr_attr) {
-                EOSVR_CUDA(cudaFuncSetAttribute(k_rerank_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-                EOSVR_CUDA(cudaFuncSetAttribute(k_rerank_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-                rr_attr = true;
+            {
+                std::lock_guard<std::mutex> lock(g_dev_mu);
+                if (!ds->rr_attr) {
+                    EOSVR_CUDA(cudaFuncSetAttribute(k_rerank_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                    EOSVR_CUDA(cudaFuncSetAttribute(k_rerank_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                    ds->rr_attr = true;
+                }
             }
             if (cosm) k_rerank_rows<true><<<rr_grid, kRrThreads, rr_smem, st>>>(rp);
             else k_rerank_rows<false><<<rr_grid, kRrThreads, rr_smem, st>>>(rp);
         }
-        else k_rerank<<<g_num_sms * 8, 256, 0, st>>>(rp);
+        else k_rerank<<<num_sms * 8, 256, 0, st>>>(rp);
         EOSVR_CUDA(cudaGetLastError());
-        k_rerank_ovf<<<g_num_sms * 4, 256, 0, st>>>(rp);
-        EOSVR_CUDA(cudaGetLastError());
-        EOSVR_COUNT_LAUNCH(2);
+        EOSVR_COUNT_LAUNCH(1);
     }
-    k_compact_flags<<<64, 256, 0, st>>>(rp);
+    k_finish<<<num_sms * 4, kFinThreads, 0, st>>>(rp, cosm ? 1 : 0, out_packed, out_score, out_idx);
     EOSVR_CUDA(cudaGetLastError());
-    k_exact_fallback<<<g_num_sms * 8, 256, 0, st>>>(rp);
-    EOSVR_CUDA(cudaGetLastError());
-    k_finalize<<<static_cast<unsigned>((P + threads - 1) / threads), threads, 0, st>>>(
-        ws->best, P, cosm ? 1 : 0, out_packed, out_score, out_idx);
-    EOSVR_CUDA(cudaGetLastError());
-    EOSVR_COUNT_LAUNCH(3);
+    EOSVR_COUNT_LAUNCH(1);
     return EOSVR_OK;
 }
 

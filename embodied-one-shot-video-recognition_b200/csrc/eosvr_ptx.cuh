@@ -169,6 +169,33 @@ __device__ __forceinline__ void tmem_st_zero_x16(uint32_t taddr)
         ::"r"(taddr), "r"(z)
         : "memory");
 }
+// registers -> TMEM: the same 32-bit value into this warp's 32 lanes x 16 consecutive columns (lane i writes ITS value)
+__device__ __forceinline__ void tmem_st_fill_x16(uint32_t taddr, uint32_t bits)
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+        ::"r"(taddr), "r"(bits)
+        : "memory");
+}
+// Same for 16 columns from EIGHT caller-held registers (two tcgen05.st.x8).  A tcgen05.st needs its source values in
+// consecutive registers: the single-operand form above makes the compiler copy the value into 15 more registers before
+// EVERY store (15 moves per 16-column chunk in the screening epilogue); holding 8 copies for a whole tile costs 7 moves
+// per tile.  `opaque_copy` keeps the compiler from folding the copies back into one register.
+__device__ __forceinline__ uint32_t opaque_copy(uint32_t x)
+{
+    uint32_t y;
+    asm volatile("mov.b32 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+__device__ __forceinline__ void tmem_st_fill8_x16(uint32_t taddr, const uint32_t (&v)[8])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n\t"
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0 + 8], {%1, %2, %3, %4, %5, %6, %7, %8};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait()
 {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -241,7 +268,25 @@ __device__ __forceinline__ void mma_commit_2sm(uint64_t *bar, uint16_t cta_mask)
         : "memory");
 }
 
+// ---- register re-partitioning between warp roles (whole warp executes) -----------------------
+template <int N>
+__device__ __forceinline__ void reg_release()
+{
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_acquire()
+{
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // ---- misc ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ float sqrt_approx(float x)
 {
     float r;

@@ -122,9 +122,9 @@ class MatchWorkspace:
 
     def debug_cycles(self, stream=None) -> dict:
         """Cycle accounting of the last screening kernel (needs EOSVR_EXP bit 16 in the environment)."""
-        out = (ctypes.c_int64 * 6)()
+        out = (ctypes.c_int64 * 8)()
         check(lib().eosvr_workspace_debug_cycles(self._h, _stream_ptr(stream), out), "eosvr_workspace_debug_cycles")
-        keys = ["epi_busy", "epi_wait", "mma_wait_full", "mma_wait_acc", "prod_wait", "total"]
+        keys = ["epi_busy", "epi_wait", "mma_wait_full", "mma_wait_acc", "prod_wait", "total", "epi_pre", "epi_loop"]
         return dict(zip(keys, [int(v) for v in out]))
 
     def close(self):

@@ -54,9 +54,16 @@ for name, P, rpe, D, G in SHAPES:
     if int(os.environ.get("EOSVR_EXP", "0")) & 16:
         c = ws.debug_cycles()
         tot = max(c["total"], 1) / 74
-        print("   cycles/pair %.0f: epi_busy %.3f epi_wait %.3f mma_wait_full(/3 issuers) %.3f mma_wait_acc %.3f prod_wait %.3f"
-              % (tot, c["epi_busy"] / (148 * 8) / tot, c["epi_wait"] / (148 * 8) / tot, c["mma_wait_full"] / 74 / 3 / tot,
-                 c["mma_wait_acc"] / 74 / tot, c["prod_wait"] / 148 / tot), flush=True)
+        ew = int(os.environ.get("EOSVR_EW", "0")) or (16 if D <= 1024 else 8)
+        tiles = st["tiles"] / 74
+        print("   cycles/pair %.0f (%.0f per tile; MMA needs %d): epi_busy %.3f epi_wait %.3f mma_wait_full(/3 issuers) %.3f "
+              "mma_wait_acc %.3f prod_wait %.3f  [fractions of the kernel, per warp of the role; %d epilogue warps]"
+              % (tot, tot / tiles, (D + 63) // 64 * 4 * st["mma_n"] // 2, c["epi_busy"] / (148 * ew) / tot,
+                 c["epi_wait"] / (148 * ew) / tot, c["mma_wait_full"] / 74 / 3 / tot, c["mma_wait_acc"] / 74 / tot,
+                 c["prod_wait"] / 148 / tot, ew), flush=True)
+        print("   epilogue busy split: before the chunk loop %.3f, chunk loop %.3f, after %.3f (of busy)"
+              % (c["epi_pre"] / max(c["epi_busy"], 1), c["epi_loop"] / max(c["epi_busy"], 1),
+                 1.0 - (c["epi_pre"] + c["epi_loop"]) / max(c["epi_busy"], 1)), flush=True)
     if int(os.environ.get("EOSVR_EXP", "0")) & 64:
         c = ws.debug_cycles()
         tot = c["epi_busy"] + c["epi_wait"] + c["mma_wait_full"] + c["mma_wait_acc"]
