@@ -10,7 +10,9 @@ import os
 
 ORIG_REF_QUIRK, ORIG_CLIP_MEAN = 0, 1
 SCREEN_F16, SCREEN_BF16 = 0, 1
+DTYPE_F32, DTYPE_BF16 = 0, 1
 METRIC_EUCLID_TEMPORAL, METRIC_COSINE = 0, 1
+KERNELS = {"probe_prep": 0, "seed": 1, "screen": 2, "rerank": 3, "finish": 4, "episode": 5}   # EOSVR_KERNEL_* ids
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -36,12 +38,15 @@ SIGNATURES = {
     "eosvr_device_check": (_c.c_int, []),
     "eosvr_gallery_create": (_c.c_int, [_vp, _i64, _i32, _i32, _i64, _i32, _vp, _c.POINTER(_vp)]),
     "eosvr_gallery_destroy": (_c.c_int, [_vp]),
+    "eosvr_gallery_info": (_c.c_int, [_vp, _c.POINTER(_i32), _c.POINTER(_i32)]),
+    "eosvr_upcast_bf16": (_c.c_int, [_vp, _i64, _vp, _vp]),
     "eosvr_gallery_rows": (_c.c_int, [_vp, _c.POINTER(_i64), _c.POINTER(_i32), _c.POINTER(_i64)]),
     "eosvr_workspace_create": (_c.c_int, [_i64, _i32, _i64, _c.POINTER(_vp)]),
     "eosvr_workspace_destroy": (_c.c_int, [_vp]),
     "eosvr_workspace_set_debug": (_c.c_int, [_vp, _vp, _i64]),
     "eosvr_workspace_set_timing": (_c.c_int, [_vp, _i32]),
     "eosvr_workspace_screen_ms": (_c.c_int, [_vp, _c.POINTER(_c.c_double), _c.POINTER(_i64)]),
+    "eosvr_workspace_kernel_ms": (_c.c_int, [_vp, _i32, _c.POINTER(_c.c_double), _c.POINTER(_i64)]),
     "eosvr_launch_count": (_c.c_uint64, []),
     "eosvr_plan": (_c.c_int, [_i64, _i32, _c.POINTER(_i64)]),
     "eosvr_match": (_c.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _vp]),
@@ -54,7 +59,9 @@ SIGNATURES = {
     "eosvr_proto_score": (_c.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "eosvr_episode_score": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32,
                                        _vp, _vp, _vp, _vp, _vp]),
-    "eosvr_episode_score_sharded": (_c.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32,
+    "eosvr_episode_batch": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _f32, _f32, _i32, _i32,
+                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "eosvr_episode_score_sharded": (_c.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32,
                                                _i32, _vp, _vp, _vp, _vp, _vp]),
     "eosvr_temporal_smooth": (_c.c_int, [_vp, _i64, _i64, _i32, _f32, _f32, _vp, _vp]),
     "eosvr_cosine_predict": (_c.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),

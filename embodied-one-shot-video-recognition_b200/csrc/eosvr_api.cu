@@ -61,6 +61,20 @@ int encode_tmap_2d(CUtensorMap *m, const void *base, int fmt, uint64_t rows, uin
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+int timing_begin(eosvr_workspace *ws, int kernel, cudaStream_t st)
+{
+    if (!ws || !ws->timing_on) return EOSVR_OK;
+    EOSVR_CUDA(cudaEventRecord(ws->ev0[kernel][ws->timing_calls[kernel] % kTimingRing], st));
+    return EOSVR_OK;
+}
+int timing_end(eosvr_workspace *ws, int kernel, cudaStream_t st)
+{
+    if (!ws || !ws->timing_on) return EOSVR_OK;
+    EOSVR_CUDA(cudaEventRecord(ws->ev1[kernel][ws->timing_calls[kernel] % kTimingRing], st));
+    ++ws->timing_calls[kernel];
+    return EOSVR_OK;
+}
+
 static void free_screen_copy(eosvr_screen_copy *c)
 {
     if (!c) return;
@@ -131,7 +145,7 @@ int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtyp
     if (!out) { set_error("gallery_create: out is NULL"); return EOSVR_EINVAL; }
     *out = nullptr;
     if (!d_feats || G < 1 || D < 1) { set_error("gallery_create: need d_feats != NULL, G >= 1, D >= 1"); return EOSVR_EINVAL; }
-    if (dtype != EOSVR_F32) { set_error("gallery_create: unsupported dtype %d", dtype); return EOSVR_EINVAL; }
+    if (dtype != EOSVR_F32 && dtype != EOSVR_BF16) { set_error("gallery_create: unsupported dtype %d", dtype); return EOSVR_EINVAL; }
     if (screen_fmt != EOSVR_SCREEN_F16 && screen_fmt != EOSVR_SCREEN_BF16) { set_error("gallery_create: bad screen_fmt %d", screen_fmt); return EOSVR_EINVAL; }
     if (global_offset < 0 || global_offset + G > 0xFFFFFFFFll) { set_error("gallery_create: global indices must fit 32 bits"); return EOSVR_EINVAL; }
     if (G > 0x7FFFFF00ll) { set_error("gallery_create: shard too large"); return EOSVR_EINVAL; }
@@ -140,14 +154,20 @@ int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtyp
     eosvr_gallery *g = new (std::nothrow) eosvr_gallery();
     if (!g) { set_error("out of host memory"); return EOSVR_ENOMEM; }
     memset(g, 0, sizeof(*g));
-    g->feats = static_cast<const float *>(d_feats);
+    g->feats = d_feats;
+    g->dtype = dtype;
     g->G = G; g->D = D; g->Dp = (D + kBK - 1) / kBK * kBK;
+    // bfloat16 rows screened as bfloat16: the TMA maps read the caller's rows in place (out-of-bounds rows / columns
+    // of a box are zero-filled by the hardware), no second copy of the gallery.  Needs 16-byte row pitch.
+    g->owns_h16 = !(dtype == EOSVR_BF16 && screen_fmt == EOSVR_SCREEN_BF16 && (D % 8) == 0 &&
+                    (reinterpret_cast<uintptr_t>(d_feats) & 15) == 0);
     g->offset = global_offset; g->screen_fmt = screen_fmt;
     cudaGetDevice(&g->device);
     g->cos_mutex = new (std::nothrow) std::mutex();
     if (!g->cos_mutex) { delete g; set_error("out of host memory"); return EOSVR_ENOMEM; }
     const int64_t Gpad = (G + kPairM - 1) / kPairM * kPairM;
-    if (cudaMalloc(&g->h16, static_cast<size_t>(Gpad) * g->Dp * 2) != cudaSuccess ||
+    if (!g->owns_h16) g->h16 = const_cast<void *>(d_feats);
+    if ((g->owns_h16 && cudaMalloc(&g->h16, static_cast<size_t>(Gpad) * g->Dp * 2) != cudaSuccess) ||
         cudaMalloc(&g->gnorm, static_cast<size_t>(Gpad) * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&g->scalars, 4 * sizeof(float)) != cudaSuccess) {
         cudaGetLastError();
@@ -156,7 +176,10 @@ int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtyp
         return EOSVR_ENOMEM;
     }
     rc = launch_gallery_prep(g, static_cast<cudaStream_t>(stream));
-    if (!rc) rc = encode_tmap_2d(&g->tmapA, g->h16, screen_fmt, static_cast<uint64_t>(Gpad), static_cast<uint64_t>(g->Dp), kBM, kBK, 1);
+    // (in place: the map covers exactly the caller's [G, D] rows; boxes reaching beyond read zeros)
+    const uint64_t map_rows = g->owns_h16 ? static_cast<uint64_t>(Gpad) : static_cast<uint64_t>(G);
+    const uint64_t map_cols = g->owns_h16 ? static_cast<uint64_t>(g->Dp) : static_cast<uint64_t>(D);
+    if (!rc) rc = encode_tmap_2d(&g->tmapA, g->h16, screen_fmt, map_rows, map_cols, kBM, kBK, 1);
     // strided seed sample: seed_tiles tiles of rows {0, stride, 2*stride, ...}
     // (an ODD stride so that periodic class layouts of the gallery cannot alias with the sample)
     const int64_t GT = Gpad / kPairM;
@@ -167,8 +190,12 @@ int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtyp
     g->seed_tiles = static_cast<int32_t>(st_tiles);
     g->seed_stride = Gpad / (st_tiles * kPairM);
     if (g->seed_stride > 1 && (g->seed_stride & 1) == 0) g->seed_stride -= 1;
-    if (!rc) rc = encode_tmap_2d(&g->tmapSeed, g->h16, screen_fmt, static_cast<uint64_t>(st_tiles * kPairM),
-                                 static_cast<uint64_t>(g->Dp), kBM, kBK, static_cast<uint64_t>(g->seed_stride));
+    {
+        // strided view: row r of the map = gallery row r * seed_stride (rows beyond G must not be addressed: clamp)
+        uint64_t srows = static_cast<uint64_t>(st_tiles * kPairM);
+        if (!g->owns_h16) { const uint64_t fit = (static_cast<uint64_t>(G) - 1) / static_cast<uint64_t>(g->seed_stride) + 1; if (srows > fit) srows = fit; }
+        if (!rc) rc = encode_tmap_2d(&g->tmapSeed, g->h16, screen_fmt, srows, map_cols, kBM, kBK, static_cast<uint64_t>(g->seed_stride));
+    }
     if (rc) { eosvr_gallery_destroy(g); return rc; }
     *out = g;
     return EOSVR_OK;
@@ -177,7 +204,7 @@ int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtyp
 int eosvr_gallery_destroy(eosvr_gallery_t *g)
 {
     if (!g) return EOSVR_OK;
-    if (g->h16) cudaFree(g->h16);
+    if (g->h16 && g->owns_h16) cudaFree(g->h16);
     if (g->gnorm) cudaFree(g->gnorm);
     if (g->scalars) cudaFree(g->scalars);
     free_screen_copy(g->cos);
@@ -193,6 +220,21 @@ int eosvr_gallery_rows(const eosvr_gallery_t *g, int64_t *G, int32_t *D, int64_t
     if (D) *D = g->D;
     if (global_offset) *global_offset = g->offset;
     return EOSVR_OK;
+}
+
+int eosvr_gallery_info(const eosvr_gallery_t *g, int32_t *dtype, int32_t *owns_screen_copy)
+{
+    if (!g) { set_error("gallery_info: NULL handle"); return EOSVR_EINVAL; }
+    if (dtype) *dtype = g->dtype;
+    if (owns_screen_copy) *owns_screen_copy = g->owns_h16;
+    return EOSVR_OK;
+}
+
+int eosvr_upcast_bf16(const void *d_in, int64_t n, float *d_out, void *stream)
+{
+    if (n < 0 || (n > 0 && (!d_in || !d_out))) { set_error("upcast_bf16: bad arguments"); return EOSVR_EINVAL; }
+    if ((reinterpret_cast<uintptr_t>(d_in) & 7) || (reinterpret_cast<uintptr_t>(d_out) & 15)) { set_error("upcast_bf16: d_in must be 8-byte and d_out 16-byte aligned"); return EOSVR_EINVAL; }
+    return launch_upcast_bf16(d_in, n, d_out, static_cast<cudaStream_t>(stream));
 }
 
 int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capacity, eosvr_workspace_t **out)
@@ -218,7 +260,7 @@ int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capac
     const size_t o_na = carve(ws->cap_rows * 4), o_wl = carve(ws->cap_rows * 4), o_wr = carve(ws->cap_rows * 4);
     const size_t o_ep = carve(ws->cap_rows * 4), o_rm = carve(ws->cap_rows * 4);
     const size_t o_thr = carve(ws->maxP * 4), o_best = carve(ws->maxP * 8), o_rf = carve(ws->maxP * 4);
-    const size_t o_rc = carve(ws->maxP * 4);
+    const size_t o_rc = carve(ws->maxP * 4), o_ix = carve(ws->maxP * 8);
     const size_t o_cd = carve(static_cast<size_t>(ws->maxP) * ws->cand_cap * sizeof(Cand)), o_ct = carve(sizeof(Counters));
     ws->ovf_cap = ws->maxP * 16 > (1ll << 16) ? ws->maxP * 16 : (1ll << 16);
     const size_t o_ov = carve(static_cast<size_t>(ws->ovf_cap) * sizeof(OvfCand));
@@ -238,6 +280,7 @@ int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capac
     ws->rowflag = reinterpret_cast<int32_t *>(b + o_rf);
     ws->rowcnt = reinterpret_cast<unsigned int *>(b + o_rc); ws->cand = reinterpret_cast<Cand *>(b + o_cd);
     ws->counters = reinterpret_cast<Counters *>(b + o_ct);
+    ws->idx_scratch = reinterpret_cast<int64_t *>(b + o_ix);
     ws->ovf = reinterpret_cast<OvfCand *>(b + o_ov);
     *out = ws;
     return EOSVR_OK;
@@ -246,10 +289,11 @@ int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capac
 int eosvr_workspace_destroy(eosvr_workspace_t *ws)
 {
     if (!ws) return EOSVR_OK;
-    for (int i = 0; i < kTimingRing; ++i) {
-        if (ws->ev0[i]) cudaEventDestroy(ws->ev0[i]);
-        if (ws->ev1[i]) cudaEventDestroy(ws->ev1[i]);
-    }
+    for (int k = 0; k < EOSVR_KERNEL_COUNT; ++k)
+        for (int i = 0; i < kTimingRing; ++i) {
+            if (ws->ev0[k][i]) cudaEventDestroy(ws->ev0[k][i]);
+            if (ws->ev1[k][i]) cudaEventDestroy(ws->ev1[k][i]);
+        }
     if (ws->slab) cudaFree(ws->slab);
     delete ws;
     return EOSVR_OK;
@@ -267,30 +311,36 @@ int eosvr_workspace_set_debug(eosvr_workspace_t *ws, float *d_dump, int64_t elem
 int eosvr_workspace_set_timing(eosvr_workspace_t *ws, int32_t on)
 {
     if (!ws) { set_error("set_timing: NULL workspace"); return EOSVR_EINVAL; }
-    if (on && !ws->ev0[0]) {
-        for (int i = 0; i < kTimingRing; ++i) {
-            EOSVR_CUDA(cudaEventCreate(&ws->ev0[i]));
-            EOSVR_CUDA(cudaEventCreate(&ws->ev1[i]));
-        }
+    if (on && !ws->ev0[0][0]) {
+        for (int k = 0; k < EOSVR_KERNEL_COUNT; ++k)
+            for (int i = 0; i < kTimingRing; ++i) {
+                EOSVR_CUDA(cudaEventCreate(&ws->ev0[k][i]));
+                EOSVR_CUDA(cudaEventCreate(&ws->ev1[k][i]));
+            }
     }
     ws->timing_on = on ? 1 : 0;
-    ws->timing_calls = 0;
+    for (int k = 0; k < EOSVR_KERNEL_COUNT; ++k) ws->timing_calls[k] = 0;
+    return EOSVR_OK;
+}
+
+int eosvr_workspace_kernel_ms(eosvr_workspace_t *ws, int32_t kernel, double *sum_ms, int64_t *calls)
+{
+    if (!ws || !sum_ms || !calls || kernel < 0 || kernel >= EOSVR_KERNEL_COUNT) { set_error("kernel_ms: bad argument"); return EOSVR_EINVAL; }
+    const int64_t n = ws->timing_calls[kernel] < kTimingRing ? ws->timing_calls[kernel] : kTimingRing;
+    double tot = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        float ms = 0.f;
+        EOSVR_CUDA(cudaEventSynchronize(ws->ev1[kernel][i]));
+        EOSVR_CUDA(cudaEventElapsedTime(&ms, ws->ev0[kernel][i], ws->ev1[kernel][i]));
+        tot += ms;
+    }
+    *sum_ms = tot; *calls = n;
     return EOSVR_OK;
 }
 
 int eosvr_workspace_screen_ms(eosvr_workspace_t *ws, double *sum_ms, int64_t *calls)
 {
-    if (!ws || !sum_ms || !calls) { set_error("screen_ms: NULL argument"); return EOSVR_EINVAL; }
-    const int64_t n = ws->timing_calls < kTimingRing ? ws->timing_calls : kTimingRing;
-    double tot = 0.0;
-    for (int64_t i = 0; i < n; ++i) {
-        float ms = 0.f;
-        EOSVR_CUDA(cudaEventSynchronize(ws->ev1[i]));
-        EOSVR_CUDA(cudaEventElapsedTime(&ms, ws->ev0[i], ws->ev1[i]));
-        tot += ms;
-    }
-    *sum_ms = tot; *calls = n;
-    return EOSVR_OK;
+    return eosvr_workspace_kernel_ms(ws, EOSVR_KERNEL_SCREEN, sum_ms, calls);
 }
 
 uint64_t eosvr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
@@ -417,14 +467,36 @@ int eosvr_episode_score(const float *d_probes, const float *d_winner_rows, const
     if (!d_winner_rows && !(g && d_idx)) { set_error("episode_score: need d_winner_rows, or a gallery handle and d_idx"); return EOSVR_EINVAL; }
     if (!d_winner_rows && g && g->D != D) { set_error("episode_score: gallery D=%d != D=%d", g->D, D); return EOSVR_EINVAL; }
     if (orig_mode != EOSVR_ORIG_REF_QUIRK && orig_mode != EOSVR_ORIG_CLIP_MEAN) { set_error("episode_score: bad orig_mode %d", orig_mode); return EOSVR_EINVAL; }
-    return launch_episode_score(d_probes, d_winner_rows, d_winner_rows ? nullptr : g->feats, d_winner_rows ? 0 : g->G,
+    return launch_episode_score(d_probes, d_winner_rows, d_winner_rows ? nullptr : g->feats, d_winner_rows ? 0 : g->dtype, d_winner_rows ? 0 : g->G,
                                 d_winner_rows ? 0 : g->offset, nullptr, nullptr, 0, d_idx, d_support_y, d_query, E, n, S,
                                 Q, D, orig_mode, max_proto, d_dist, d_prob, d_pred, d_nproto,
                                 static_cast<cudaStream_t>(stream));
 }
 
-int eosvr_episode_score_sharded(const float *d_probes, const float *const *d_shard_bases, const int64_t *d_shard_begin,
-                                int32_t nshards, const int64_t *d_idx, const float *d_support_y, const float *d_query,
+int eosvr_episode_batch(const eosvr_gallery_t *g, eosvr_workspace_t *ws, const float *d_probes,
+                        const float *d_support_y, const float *d_query, int64_t E, int32_t n, int32_t S,
+                        int32_t Q, int32_t metric, float lam1, float lam2, int32_t orig_mode, int32_t max_proto,
+                        uint64_t *d_out_packed, float *d_out_score, int64_t *d_out_idx, float *d_dist,
+                        float *d_prob, int64_t *d_pred, int32_t *d_nproto, void *stream)
+{
+    if (E < 0 || n < 1 || S < 1) { set_error("episode_batch: bad shape"); return EOSVR_EINVAL; }
+    const int64_t P = E * n * S;
+    int rc = check_match_args(g, ws, d_probes, P, n * S, metric, lam1, lam2, d_out_packed);
+    if (rc) return rc;
+    if (E == 0) return EOSVR_OK;
+    if (!d_support_y || !d_query) { set_error("episode_batch: d_support_y and d_query are required"); return EOSVR_EINVAL; }
+    if (orig_mode != EOSVR_ORIG_REF_QUIRK && orig_mode != EOSVR_ORIG_CLIP_MEAN) { set_error("episode_batch: bad orig_mode %d", orig_mode); return EOSVR_EINVAL; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int64_t *idx = d_out_idx ? d_out_idx : ws->idx_scratch;
+    rc = launch_match(const_cast<eosvr_gallery_t *>(g), ws, d_probes, P, n * S, metric, lam1, lam2, false, d_out_packed,
+                      d_out_score, idx, st);
+    if (rc) return rc;
+    return launch_episode_score(d_probes, nullptr, g->feats, g->dtype, g->G, g->offset, nullptr, nullptr, 0, idx, d_support_y, d_query, E,
+                                n, S, Q, g->D, orig_mode, max_proto, d_dist, d_prob, d_pred, d_nproto, st, ws);
+}
+
+int eosvr_episode_score_sharded(const float *d_probes, const void *const *d_shard_bases, int32_t shard_dtype,
+                                const int64_t *d_shard_begin, int32_t nshards, const int64_t *d_idx, const float *d_support_y, const float *d_query,
                                 int64_t E, int32_t n, int32_t S, int32_t Q, int32_t D, int32_t orig_mode,
                                 int32_t max_proto, float *d_dist, float *d_prob, int64_t *d_pred, int32_t *d_nproto,
                                 void *stream)
@@ -434,7 +506,8 @@ int eosvr_episode_score_sharded(const float *d_probes, const float *const *d_sha
     if (orig_mode != EOSVR_ORIG_REF_QUIRK && orig_mode != EOSVR_ORIG_CLIP_MEAN) { set_error("episode_score_sharded: bad orig_mode %d", orig_mode); return EOSVR_EINVAL; }
     int rc = eosvr_device_check();
     if (rc) return rc;
-    return launch_episode_score(d_probes, nullptr, nullptr, 0, 0, d_shard_bases, d_shard_begin, nshards, d_idx,
+    if (shard_dtype != EOSVR_F32 && shard_dtype != EOSVR_BF16) { set_error("episode_score_sharded: bad shard_dtype %d", shard_dtype); return EOSVR_EINVAL; }
+    return launch_episode_score(d_probes, nullptr, nullptr, shard_dtype, 0, 0, d_shard_bases, d_shard_begin, nshards, d_idx,
                                 d_support_y, d_query, E, n, S, Q, D, orig_mode, max_proto, d_dist, d_prob, d_pred,
                                 d_nproto, static_cast<cudaStream_t>(stream));
 }

@@ -203,8 +203,8 @@ constexpr int kMaxClips = 256;
 
 template <int S_T>
 __global__ void __launch_bounds__(kProtoThreads)
-k_episode_score(const float *__restrict__ probes, const float *__restrict__ wrows, const float *__restrict__ gal,
-                int64_t G, int64_t goff, const int64_t *__restrict__ idx, const float *__restrict__ sup_y,
+k_episode_score(const float *__restrict__ probes, const float *__restrict__ wrows, const void *__restrict__ gal,
+                int gdt, int64_t G, int64_t goff, const int64_t *__restrict__ idx, const float *__restrict__ sup_y,
                 const float *__restrict__ query, int n, int S_rt, int Q, int D, int orig_mode, int max_proto,
                 float *__restrict__ dist, float *__restrict__ prob, int64_t *__restrict__ pred,
                 int32_t *__restrict__ nproto_out)
@@ -266,7 +266,7 @@ k_episode_score(const float *__restrict__ probes, const float *__restrict__ wrow
                         if (wrows) w[s] = wrows[(wbase + s) * D + k];
                         else {
                             const int64_t g = idx[wbase + s] - goff;
-                            w[s] = (g >= 0 && g < G) ? gal[g * D + k] : 0.f;
+                            w[s] = (g >= 0 && g < G) ? ld_feat(gal, gdt, g * D + k) : 0.f;
                         }
                     }
                     float o;
@@ -299,7 +299,7 @@ k_episode_score(const float *__restrict__ probes, const float *__restrict__ wrow
                         if (wrows) wv = wrows[(wbase + s) * D + k];
                         else {
                             const int64_t g = idx[wbase + s] - goff;
-                            wv = (g >= 0 && g < G) ? gal[g * D + k] : 0.f;
+                            wv = (g >= 0 && g < G) ? ld_feat(gal, gdt, g * D + k) : 0.f;
                         }
                         float a = (s == 0) ? wv : pc[0];
                         for (int s2 = 1; s2 < S; ++s2) a = __fadd_rn(a, (s2 == s) ? wv : pc[static_cast<int64_t>(s2) * D]);
@@ -359,21 +359,25 @@ constexpr int kEpThreads = 128;
 
 template <int S_T>
 __global__ void __launch_bounds__(kEpThreads)
-k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wrows, const float *__restrict__ gal,
-                  int64_t G, int64_t goff, const float *const *__restrict__ shard_bases,
+k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wrows, const void *__restrict__ gal,
+                  int gdt, int64_t G, int64_t goff, const void *const *__restrict__ shard_bases,
                   const int64_t *__restrict__ shard_begin, int nshards, const int64_t *__restrict__ idx,
                   const float *__restrict__ sup_y, const float *__restrict__ query, int n, int Q, int D, int orig_mode,
-                  int max_proto, int nsplit, double *__restrict__ partial, int32_t *__restrict__ np_out)
+                  int max_proto, int nsplit, double *partial, unsigned int *done, float *__restrict__ dist,
+                  float *__restrict__ prob, int64_t *__restrict__ pred, int32_t *__restrict__ nproto_out)
 {
     // where each winner row of the episode lives: the exchanged rows, the local gallery, or -- gallery sharded
     // over the GPUs of the box -- the owning GPU's memory, read in place over NVLink (peer loads)
-    __shared__ const float4 *s_wptr[kMaxClips * S_T];
+    // (winner rows given explicitly are float32; gallery / shard rows are float32 or bfloat16, gdt)
+    __shared__ const void *s_wbase[kMaxClips * S_T];
+    __shared__ int64_t s_wrow4[kMaxClips * S_T];      // index of the row's first float4 group in its array
     __shared__ int16_t s_cls[kMaxClips];
     __shared__ int16_t s_order[kMaxClips];
     __shared__ int16_t s_start[kMaxProto + 1];
     __shared__ float s_pid[kMaxProto];
     __shared__ int s_np;
     __shared__ double s_red[kEpThreads / 32][kMaxQ];
+    __shared__ int s_last;
 
     const int64_t e = blockIdx.x;
     const int sp = blockIdx.y;
@@ -381,24 +385,24 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
     const float4 *Pe = reinterpret_cast<const float4 *>(probes + e * n * S_T * D);
     const float *Y = sup_y + e * n;
     const float4 *Qp = reinterpret_cast<const float4 *>(query + e * Q * D);
-    const float4 *gal4 = reinterpret_cast<const float4 *>(gal);
-    const float4 *wr4 = reinterpret_cast<const float4 *>(wrows);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int t = tid; t < n * S_T; t += kEpThreads) {
         const int64_t slot = e * n * S_T + t;
-        const float4 *ptr = nullptr;
-        if (wrows) ptr = wr4 + slot * D4;
+        const void *base = nullptr;
+        int64_t row4 = 0;
+        if (wrows) { base = wrows; row4 = slot * D4; }
         else {
             const int64_t g = idx[slot];
             if (nshards > 0) {
                 for (int sh = 0; sh < nshards; ++sh)
-                    if (g >= shard_begin[sh] && g < shard_begin[sh + 1])
-                        ptr = reinterpret_cast<const float4 *>(shard_bases[sh]) + (g - shard_begin[sh]) * D4;
-            } else if (g - goff >= 0 && g - goff < G) ptr = gal4 + (g - goff) * D4;
+                    if (g >= shard_begin[sh] && g < shard_begin[sh + 1]) { base = shard_bases[sh]; row4 = (g - shard_begin[sh]) * D4; }
+            } else if (g - goff >= 0 && g - goff < G) { base = gal; row4 = (g - goff) * D4; }
         }
-        s_wptr[t] = ptr;
+        s_wbase[t] = base;
+        s_wrow4[t] = row4;
     }
+    const int wdt = wrows ? EOSVR_F32 : gdt;
     if (tid == 0) {
         int np = 0;
         for (int i = 0; i < n; ++i) {                     // classifier.py:21-29 (every row of clip i carries Y[i])
@@ -415,7 +419,6 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
         }
         s_start[np] = static_cast<int16_t>(pos);
         s_np = np;
-        if (sp == 0) np_out[e] = np;
     }
     __syncthreads();
     const int np = s_np;
@@ -443,8 +446,8 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
 #pragma unroll
                 for (int s = 0; s < S_T; ++s) {
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 *wp = s_wptr[i * S_T + s];
-                    if (wp) v = wp[k];
+                    const void *wb = s_wbase[i * S_T + s];
+                    if (wb) v = ld_feat4(wb, wdt, s_wrow4[i * S_T + s] + k);
                     w[s][0] = v.x; w[s][1] = v.y; w[s][2] = v.z; w[s][3] = v.w;
                 }
                 float o[4];
@@ -503,22 +506,26 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
         }
         __syncthreads();
     }
-}
-
-__global__ void k_episode_final(const double *__restrict__ partial, const int32_t *__restrict__ np_in, int Q,
-                                int max_proto, int nsplit, float *__restrict__ dist, float *__restrict__ prob,
-                                int64_t *__restrict__ pred, int32_t *__restrict__ nproto_out)
-{
-    const int64_t e = blockIdx.x;
-    const int q = threadIdx.x;
-    const int np = np_in[e];
-    if (q == 0 && nproto_out) nproto_out[e] = np;
-    if (q >= Q) return;
+    // The last block of the episode to get here adds the slices in a FIXED order (deterministic) and finishes
+    // sqrt / softmax / arg-max (classifier.py:63-67,:85); its ticket orders it after the other blocks' partial sums.
+    if (nsplit > 1) {
+        __threadfence();
+        if (tid == 0) {
+            const unsigned int ticket = atomicAdd(done + e, 1u);
+            s_last = ticket == static_cast<unsigned int>(nsplit - 1);
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+    }
+    if (tid == 0 && nproto_out) nproto_out[e] = np;
+    if (tid >= Q) return;
+    const int q = tid;
     float d[kMaxProto];
     float mx = 0.f; int best = 0;
     for (int c = 0; c < np; ++c) {
         double v = 0.0;
-        for (int sp = 0; sp < nsplit; ++sp) v += partial[((e * nsplit + sp) * max_proto + c) * kMaxQ + q];
+        for (int s2 = 0; s2 < nsplit; ++s2) v += __ldcg(partial + ((e * nsplit + s2) * max_proto + c) * kMaxQ + q);
         d[c] = static_cast<float>(sqrt(v));                  // classifier.py:66 float32 cast
         if (c == 0) mx = -d[0];
         else { if (-d[c] > mx) mx = -d[c]; if (d[c] < d[best]) best = c; }
@@ -533,11 +540,11 @@ __global__ void k_episode_final(const double *__restrict__ partial, const int32_
     if (pred) pred[e * Q + q] = best;
 }
 
-int launch_episode_score(const float *probes, const float *wrows, const float *gal, int64_t G, int64_t goff,
-                         const float *const *shard_bases, const int64_t *shard_begin, int32_t nshards,
+int launch_episode_score(const float *probes, const float *wrows, const void *gal, int32_t gal_dtype, int64_t G, int64_t goff,
+                         const void *const *shard_bases, const int64_t *shard_begin, int32_t nshards,
                          const int64_t *idx, const float *sup_y, const float *query, int64_t E, int32_t n,
                          int32_t S, int32_t Q, int32_t D, int32_t orig_mode, int32_t max_proto, float *dist,
-                         float *prob, int64_t *pred, int32_t *nproto, cudaStream_t st)
+                         float *prob, int64_t *pred, int32_t *nproto, cudaStream_t st, eosvr_workspace *timing_ws)
 {
     if (E == 0) return EOSVR_OK;
     if (nshards > 0 && !((D & 3) == 0 && (S == 2 || S == 4 || S == 8) && D >= 256)) {
@@ -552,29 +559,30 @@ int launch_episode_score(const float *probes, const float *wrows, const float *g
         int nsplit = D / 512;                 // >= 128 float4 columns per block
         if (nsplit < 1) nsplit = 1;
         if (nsplit > 8) nsplit = 8;
-        double *partial = nullptr;
+        // scratch: [ticket counters E x u32] [partial sums]
         const size_t pbytes = static_cast<size_t>(E) * nsplit * max_proto * kMaxQ * sizeof(double);
-        const size_t nbytes = (static_cast<size_t>(E) * sizeof(int32_t) + 255) / 256 * 256;
+        const size_t nbytes = (static_cast<size_t>(E) * sizeof(unsigned int) + 255) / 256 * 256;
         char *scratch = static_cast<char *>(stream_scratch(st, nbytes + pbytes));
         if (!scratch) { set_error("episode_score: scratch allocation of %zu bytes failed", nbytes + pbytes); return EOSVR_ENOMEM; }
-        int32_t *np_buf = reinterpret_cast<int32_t *>(scratch);
-        partial = reinterpret_cast<double *>(scratch + nbytes);
+        unsigned int *done = reinterpret_cast<unsigned int *>(scratch);
+        if (nsplit > 1) EOSVR_CUDA(cudaMemsetAsync(done, 0, static_cast<size_t>(E) * sizeof(unsigned int), st));   // ticket counters
+        double *partial = reinterpret_cast<double *>(scratch + nbytes);
         dim3 pgrid(static_cast<unsigned>(E), static_cast<unsigned>(nsplit));
 #define EOSVR_EPP_LAUNCH(ST)                                                                                      \
-        k_episode_partial<ST><<<pgrid, kEpThreads, 0, st>>>(probes, wrows, gal, G, goff, shard_bases, shard_begin,     \
+        k_episode_partial<ST><<<pgrid, kEpThreads, 0, st>>>(probes, wrows, gal, gal_dtype, G, goff, shard_bases, shard_begin,     \
                                                            nshards, idx, sup_y, query, n, Q, D, orig_mode, max_proto, \
-                                                           nsplit, partial, np_buf)
+                                                           nsplit, partial, done, dist, prob, pred, nproto)
+        { int trc = timing_begin(timing_ws, EOSVR_KERNEL_EPISODE, st); if (trc) return trc; }
         if (S == 2) EOSVR_EPP_LAUNCH(2); else if (S == 4) EOSVR_EPP_LAUNCH(4); else EOSVR_EPP_LAUNCH(8);
 #undef EOSVR_EPP_LAUNCH
         EOSVR_CUDA(cudaGetLastError());
-        k_episode_final<<<static_cast<unsigned>(E), 32, 0, st>>>(partial, np_buf, Q, max_proto, nsplit, dist, prob, pred, nproto);
-        EOSVR_CUDA(cudaGetLastError());
-        EOSVR_COUNT_LAUNCH(2);
+        { int trc = timing_end(timing_ws, EOSVR_KERNEL_EPISODE, st); if (trc) return trc; }
+        EOSVR_COUNT_LAUNCH(1);
         return EOSVR_OK;
     }
     const unsigned grid = static_cast<unsigned>(E);
 #define EOSVR_EP_LAUNCH(ST)                                                                                    \
-    k_episode_score<ST><<<grid, kProtoThreads, 0, st>>>(probes, wrows, gal, G, goff, idx, sup_y, query, n, S, Q, D, \
+    k_episode_score<ST><<<grid, kProtoThreads, 0, st>>>(probes, wrows, gal, gal_dtype, G, goff, idx, sup_y, query, n, S, Q, D, \
                                                         orig_mode, max_proto, dist, prob, pred, nproto)
     switch (S) {
         case 2: EOSVR_EP_LAUNCH(2); break;

@@ -39,12 +39,29 @@ static_assert(kStages % kIssuers == 0, "every stage barrier must have a single c
 constexpr int kChunk = 16;        // TMEM columns per tcgen05.ld
 constexpr int kMaxSeedTiles = 4;   // strided gallery tiles screened first to seed the per-probe thresholds
 constexpr float kPadNorm = 1.0e30f;
-constexpr int kTimingRing = 256;  // event pairs kept for eosvr_workspace_screen_ms
+constexpr int kTimingRing = 128;  // event pairs kept per kernel class for eosvr_workspace_kernel_ms (the last 128 launches)
 
 void count_launches(unsigned n);        // kernels launched by this library (host-side count, atomic)
 #define EOSVR_COUNT_LAUNCH(n) (::eosvr::count_launches(n))
 
 void set_error(const char *fmt, ...);
+
+#ifdef __CUDACC__
+// Gallery feature rows are float32 or bfloat16 (eosvr_gallery_create dtype); bfloat16 -> float32 is exact (a shift).
+// i4 / i index groups of 4 elements / single elements from the start of the array.
+__device__ __forceinline__ float4 ld_feat4(const void *base, int dtype, int64_t i4)
+{
+    if (dtype == EOSVR_F32) return reinterpret_cast<const float4 *>(base)[i4];
+    const uint2 u = reinterpret_cast<const uint2 *>(base)[i4];
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u),
+                       __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+}
+__device__ __forceinline__ float ld_feat(const void *base, int dtype, int64_t i)
+{
+    if (dtype == EOSVR_F32) return reinterpret_cast<const float *>(base)[i];
+    return __uint_as_float(static_cast<uint32_t>(reinterpret_cast<const unsigned short *>(base)[i]) << 16);
+}
+#endif
 
 #define EOSVR_CUDA(call)                                                                     \
     do {                                                                                     \
@@ -96,7 +113,9 @@ struct eosvr_screen_copy {
 };
 
 struct eosvr_gallery {
-    const float *feats;      // [G,D] float32, caller-owned
+    const void *feats;       // [G,D] float32 or bfloat16 (dtype), caller-owned
+    int32_t dtype;           // EOSVR_F32 / EOSVR_BF16 storage of feats
+    int32_t owns_h16;        // 0: the screening copy IS the caller's bfloat16 rows (no second copy in HBM)
     int64_t G;
     int32_t seed_tiles;      // gallery tiles of the strided seed pass
     int64_t seed_stride;     // row stride of the seed pass
@@ -137,10 +156,11 @@ struct eosvr_workspace {
     int64_t last_tiles;
     int32_t last_bn;
     int device;
-    // optional CUDA-event timing of the screening kernel (bench.py roofline)
+    // optional CUDA-event timing of every kernel class of the path (bench.py rooflines); EOSVR_KERNEL_* ids
     int timing_on;
-    int64_t timing_calls;
-    cudaEvent_t ev0[eosvr::kTimingRing], ev1[eosvr::kTimingRing];
+    int64_t timing_calls[EOSVR_KERNEL_COUNT];
+    cudaEvent_t ev0[EOSVR_KERNEL_COUNT][eosvr::kTimingRing], ev1[EOSVR_KERNEL_COUNT][eosvr::kTimingRing];
+    int64_t *idx_scratch;    // [maxP] winner indices for eosvr_episode_batch when the caller does not want them
 };
 
 namespace eosvr {
@@ -177,13 +197,17 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
 int launch_merge(const uint64_t *gathered, int32_t nshards, int64_t P, uint64_t *out_packed,
                  float *out_score, int64_t *out_idx, cudaStream_t st);
 int launch_gather_rows(const eosvr_gallery *g, const int64_t *idx, int64_t P, float *out, cudaStream_t st);
+int launch_upcast_bf16(const void *in, int64_t n, float *out, cudaStream_t st);
 int launch_splice(const float *probes, const float *wrows, int64_t E, int32_t n, int32_t S, int32_t D,
                   int32_t orig_mode, float *out, cudaStream_t st);
-int launch_episode_score(const float *probes, const float *wrows, const float *gal, int64_t G, int64_t goff,
-                         const float *const *shard_bases, const int64_t *shard_begin, int32_t nshards,
+int launch_episode_score(const float *probes, const float *wrows, const void *gal, int32_t gal_dtype, int64_t G, int64_t goff,
+                         const void *const *shard_bases, const int64_t *shard_begin, int32_t nshards,
                          const int64_t *idx, const float *sup_y, const float *query, int64_t E, int32_t n,
                          int32_t S, int32_t Q, int32_t D, int32_t orig_mode, int32_t max_proto, float *dist,
-                         float *prob, int64_t *pred, int32_t *nproto, cudaStream_t st);
+                         float *prob, int64_t *pred, int32_t *nproto, cudaStream_t st, eosvr_workspace *timing_ws = nullptr);
+// CUDA-event brackets around a kernel class when ws->timing_on (no-ops otherwise); eosvr_api.cu
+int timing_begin(eosvr_workspace *ws, int kernel, cudaStream_t st);
+int timing_end(eosvr_workspace *ws, int kernel, cudaStream_t st);
 int launch_proto_score(const float *sup, const float *sup_y, const float *query, int64_t E, int32_t R,
                        int32_t Q, int32_t D, int32_t max_proto, float *dist, float *prob, int64_t *pred,
                        int32_t *nproto, cudaStream_t st);

@@ -79,32 +79,32 @@ __device__ __forceinline__ void atomic_max_posf(float *addr, float v)
 // normalised row (float64), the stored copy is the 16-bit rounding of the float32 product x * (1/|x|); a zero
 // row stays zero and gets squared norm 1 so that |a' - 0|^2 = 2 - 2*0, consistent with cosine 0.
 template <typename T16, bool NORM>
-__global__ void k_gallery_prep(const float *__restrict__ feats, int64_t G, int64_t Gpad, int D, int Dp,
-                               T16 *__restrict__ h16, float *__restrict__ gnorm, float *__restrict__ scalars)
+__global__ void k_gallery_prep(const void *__restrict__ feats, int src_dtype, int64_t G, int64_t Gpad, int D, int Dp,
+                               T16 *__restrict__ h16, int write_h16, float *__restrict__ gnorm, float *__restrict__ scalars)
 {
     const int lane = threadIdx.x & 31;
     const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (row >= Gpad) return;
     T16 *dst = h16 + row * Dp;
     if (row >= G) {
-        for (int k = lane; k < Dp; k += 32) dst[k] = to16<T16>(0.f);
+        if (write_h16) for (int k = lane; k < Dp; k += 32) dst[k] = to16<T16>(0.f);
         if (lane == 0) gnorm[row] = kPadNorm;
         return;
     }
-    const float *src = feats + row * D;
+    const int64_t src0 = row * D;
     double rn = 1.0; float rnf = 1.f;
     if (NORM) {
         double q = 0.0;
-        for (int k = lane; k < D; k += 32) q += static_cast<double>(src[k]) * static_cast<double>(src[k]);
+        for (int k = lane; k < D; k += 32) { const double x = ld_feat(feats, src_dtype, src0 + k); q += x * x; }
         q = warp_sum(q);
         rn = q > 0.0 ? 1.0 / sqrt(q) : 0.0;
         rnf = static_cast<float>(rn);
     }
     double s = 0.0, sh = 0.0, sl = 0.0;
     for (int k = lane; k < Dp; k += 32) {
-        float x = k < D ? src[k] : 0.f;
+        float x = k < D ? ld_feat(feats, src_dtype, src0 + k) : 0.f;
         T16 h = to16<T16>(NORM ? __fmul_rn(x, rnf) : x);
-        dst[k] = h;
+        if (write_h16) dst[k] = h;
         double xd = NORM ? static_cast<double>(x) * rn : static_cast<double>(x), hd = from16(h);
         s += xd * xd;
         sh += hd * hd;
@@ -121,7 +121,7 @@ __global__ void k_gallery_prep(const float *__restrict__ feats, int64_t G, int64
 }
 
 template <bool NORM>
-static int launch_gallery_prep_t(const eosvr_gallery *g, void *h16, float *gnorm, float *scalars, cudaStream_t st)
+static int launch_gallery_prep_t(const eosvr_gallery *g, void *h16, int write_h16, float *gnorm, float *scalars, cudaStream_t st)
 {
     const int64_t Gpad = (g->G + kPairM - 1) / kPairM * kPairM;
     EOSVR_CUDA(cudaMemsetAsync(scalars, 0, 4 * sizeof(float), st));
@@ -129,22 +129,22 @@ static int launch_gallery_prep_t(const eosvr_gallery *g, void *h16, float *gnorm
     const int64_t blocks = (Gpad * 32 + threads - 1) / threads;
     if (g->screen_fmt == EOSVR_SCREEN_F16)
         k_gallery_prep<__half, NORM><<<static_cast<unsigned>(blocks), threads, 0, st>>>(
-            g->feats, g->G, Gpad, g->D, g->Dp, static_cast<__half *>(h16), gnorm, scalars);
+            g->feats, g->dtype, g->G, Gpad, g->D, g->Dp, static_cast<__half *>(h16), write_h16, gnorm, scalars);
     else
         k_gallery_prep<__nv_bfloat16, NORM><<<static_cast<unsigned>(blocks), threads, 0, st>>>(
-            g->feats, g->G, Gpad, g->D, g->Dp, static_cast<__nv_bfloat16 *>(h16), gnorm, scalars);
+            g->feats, g->dtype, g->G, Gpad, g->D, g->Dp, static_cast<__nv_bfloat16 *>(h16), write_h16, gnorm, scalars);
     EOSVR_CUDA(cudaGetLastError());
     return EOSVR_OK;
 }
 
 int launch_gallery_prep(eosvr_gallery *g, cudaStream_t st)
 {
-    return launch_gallery_prep_t<false>(g, g->h16, g->gnorm, g->scalars, st);
+    return launch_gallery_prep_t<false>(g, g->h16, g->owns_h16, g->gnorm, g->scalars, st);
 }
 
 int launch_gallery_prep_cos(const eosvr_gallery *g, eosvr_screen_copy *c, cudaStream_t st)
 {
-    return launch_gallery_prep_t<true>(g, c->h16, c->gnorm, c->scalars, st);
+    return launch_gallery_prep_t<true>(g, c->h16, 1, c->gnorm, c->scalars, st);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -365,7 +365,7 @@ struct UnitIter {
 };
 
 // Work units (gallery chunk x probe tile), three orders (EOSVR_ORDER):
-//   1 (default) probe-tile-major: unit u = probe_tile * n_chunks + chunk.  The pairs that run at the same time work
+//   1 probe-tile-major: unit u = probe_tile * n_chunks + chunk.  The pairs that run at the same time work
 //     on the same few probe tiles against different gallery chunks, so a probe tile's K blocks are fetched from HBM
 //     once (L2 hits for the other pairs) and the whole 16-bit gallery stays L2-resident: DRAM traffic close to the
 //     algorithmic bytes.  ~10 % more candidates than chunk-major (several pairs screen the same probe rows at once
@@ -892,7 +892,7 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // with zero padding at episode ends.  Warp-cooperative; all lanes return the value.
 // -------------------------------------------------------------------------------------------
 __device__ __forceinline__ float exact_t(const float *__restrict__ probes, int64_t P, int D, int rpe,
-                                         int64_t p, const float *__restrict__ b, float lam1, float lam2, int lane)
+                                         int64_t p, const void *__restrict__ gal, int gdt, int64_t b0, float lam1, float lam2, int lane)
 {
     const int r = static_cast<int>(p % rpe);
     const bool hl = r > 0, hr = (r + 1 < rpe) && (p + 1 < P);
@@ -901,7 +901,7 @@ __device__ __forceinline__ float exact_t(const float *__restrict__ probes, int64
     const float *a2 = hr ? a1 + D : a1;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     for (int k = lane; k < D; k += 32) {
-        const double bv = b[k];
+        const double bv = ld_feat(gal, gdt, b0 + k);
         const double e0 = static_cast<double>(a0[k]) - bv;
         const double e1 = static_cast<double>(a1[k]) - bv;
         const double e2 = static_cast<double>(a2[k]) - bv;
@@ -919,7 +919,8 @@ __device__ __forceinline__ float exact_t(const float *__restrict__ probes, int64
 
 struct RerankParams {
     const float *probes;
-    const float *gal;
+    const void *gal;         // gallery rows, float32 or bfloat16 (gal_dtype)
+    int32_t gal_dtype;
     int64_t P, G, offset;
     int32_t D, rpe;
     int32_t metric;          // EOSVR_METRIC_*; the cosine metric works in the score domain s = -cosine (a minimum)
@@ -941,11 +942,12 @@ struct RerankParams {
 
 // Cosine metric, exactly: float64 dot / (|a| |b|) on the original rows (0 for a zero row), rounded to
 // float32; returned negated (score domain).  Warp-cooperative; all lanes return the value.
-__device__ __forceinline__ float exact_negcos(const float *__restrict__ a, const float *__restrict__ b, int D, int lane)
+__device__ __forceinline__ float exact_negcos(const float *__restrict__ a, const void *__restrict__ gal, int gdt, int64_t b0,
+                                              int D, int lane)
 {
     double dot = 0.0, na = 0.0, nb = 0.0;
     for (int k = lane; k < D; k += 32) {
-        const double x = a[k], y = b[k];
+        const double x = a[k], y = ld_feat(gal, gdt, b0 + k);
         dot += x * y; na += x * x; nb += y * y;
     }
     dot = warp_sum(dot); na = warp_sum(na); nb = warp_sum(nb);
@@ -955,8 +957,8 @@ __device__ __forceinline__ float exact_negcos(const float *__restrict__ a, const
 
 __device__ __forceinline__ float exact_score(const RerankParams &p, int64_t row, int64_t g, int lane)
 {
-    if (p.metric == EOSVR_METRIC_COSINE) return exact_negcos(p.probes + row * p.D, p.gal + g * p.D, p.D, lane);
-    return exact_t(p.probes, p.P, p.D, p.rpe, row, p.gal + g * p.D, p.lam1, p.lam2, lane);
+    if (p.metric == EOSVR_METRIC_COSINE) return exact_negcos(p.probes + row * p.D, p.gal, p.gal_dtype, g * p.D, p.D, lane);
+    return exact_t(p.probes, p.P, p.D, p.rpe, row, p.gal, p.gal_dtype, g * p.D, p.lam1, p.lam2, lane);
 }
 
 // Spill-over candidates (row lists that filled up): one warp per entry, grid-strided over the warps of the
@@ -1162,12 +1164,13 @@ k_rerank_rows(const RerankParams p)
                 if (j >= ns) break;
                 if (s_t2[j] > __uint_as_float(*reinterpret_cast<volatile unsigned int *>(&s_bound))) break;
                 const int32_t g = s_g2[j];
-                const float4 *gp = reinterpret_cast<const float4 *>(p.gal + static_cast<int64_t>(g) * D);
+                const int64_t gp = static_cast<int64_t>(g) * D4;          // float4 index of the gallery row
+                const int gdt = p.gal_dtype;
                 float x0 = 0.f, x1 = 0.f, x2 = 0.f;
                 if (COS) {
 #pragma unroll 4
                     for (int k = lane; k < D4; k += 32) {
-                        const float4 b = gp[k];
+                        const float4 b = ld_feat4(p.gal, gdt, gp + k);
                         const float4 q = sp1[k];
                         x0 = fmaf(q.x, b.x, x0); x0 = fmaf(q.y, b.y, x0); x0 = fmaf(q.z, b.z, x0); x0 = fmaf(q.w, b.w, x0);
                         x1 = fmaf(b.x, b.x, x1); x1 = fmaf(b.y, b.y, x1); x1 = fmaf(b.z, b.z, x1); x1 = fmaf(b.w, b.w, x1);
@@ -1176,7 +1179,7 @@ k_rerank_rows(const RerankParams p)
                 } else {
 #pragma unroll 4
                     for (int k = lane; k < D4; k += 32) {
-                        const float4 b = gp[k];
+                        const float4 b = ld_feat4(p.gal, gdt, gp + k);
                         const float4 q0 = sp0[k], q1 = sp1[k], q2 = sp2[k];
                         float e;
                         e = q0.x - b.x; x0 = fmaf(e, e, x0); e = q0.y - b.y; x0 = fmaf(e, e, x0);
@@ -1225,11 +1228,12 @@ k_rerank_rows(const RerankParams p)
             for (int j = 0; j < n32; ++j) {                              // normally ONE candidate: the whole block on it
                 if (!(s_t[j] <= cut)) continue;                          // block-uniform
                 const int32_t g = s_g[j];
-                const float4 *gp = reinterpret_cast<const float4 *>(p.gal + static_cast<int64_t>(g) * D);
+                const int64_t gp = static_cast<int64_t>(g) * D4;
+                const int gdt = p.gal_dtype;
                 double y0 = 0.0, y1 = 0.0, y2 = 0.0;
                 if (COS) {
                     for (int k = tid; k < D4; k += kRrThreads) {
-                        const float4 b = gp[k];
+                        const float4 b = ld_feat4(p.gal, gdt, gp + k);
                         const float4 q = sp1[k];
                         const double bb[4] = {b.x, b.y, b.z, b.w}, qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -1237,7 +1241,7 @@ k_rerank_rows(const RerankParams p)
                     }
                 } else {
                     for (int k = tid; k < D4; k += kRrThreads) {
-                        const float4 b = gp[k];
+                        const float4 b = ld_feat4(p.gal, gdt, gp + k);
                         const float4 q0 = sp0[k], q1 = sp1[k], q2 = sp2[k];
                         const double bb[4] = {b.x, b.y, b.z, b.w};
                         const float qq0[4] = {q0.x, q0.y, q0.z, q0.w}, qq1[4] = {q1.x, q1.y, q1.z, q1.w},
@@ -1422,7 +1426,7 @@ const Tunables &tunables()
 {
     static const Tunables t = [] {
         Tunables v;
-        v.order = env_int("EOSVR_ORDER", 1);
+        v.order = env_int("EOSVR_ORDER", -1);          // -1: chosen per call (launch_screen)
         v.tpu = env_int("EOSVR_TPU", 0);
         v.seed = env_int("EOSVR_SEED", 1);
         v.ew = env_int("EOSVR_EW", 0);
@@ -1499,7 +1503,7 @@ struct ScreenView {          // the screening copy of the gallery a launch reads
 
 static int launch_screen(DeviceState *ds, const eosvr_gallery *g, const ScreenView &sv, eosvr_workspace *ws, const MatchPlan &pl,
                          bool seed, const CUtensorMap &tmB, int64_t gallery_tiles, int64_t g_stride, int64_t P,
-                         bool timed, cudaStream_t st)
+                         cudaStream_t st)
 {
     const Tunables &tn = tunables();
     ScreenParams sp;
@@ -1516,7 +1520,17 @@ static int launch_screen(DeviceState *ds, const eosvr_gallery *g, const ScreenVi
     sp.n_chunks = static_cast<int32_t>((sp.GT + tpu - 1) / tpu);
     if (static_cast<int64_t>(sp.n_chunks) * sp.NT > 0x7FFFFFFFll) { set_error("match: too many work units"); return EOSVR_EINVAL; }
     sp.n_units = sp.n_chunks * sp.NT;
-    sp.order = tn.order;
+    // Unit order: the operand that is swept repeatedly should be the one that stays in L2.  Chunk-major (0) streams the
+    // gallery once and re-reads the probe plan per gallery chunk; probe-tile-major (1) does the opposite.  Measured on
+    // B200 (profiles/r02_unit_order.txt): cfg-3 (21 MB of probes, 102 MB gallery) 1.91 -> 1.68 ms and a 1.25 M-row
+    // shard of cfg-4 28.9 -> 21.9 ms with chunk-major; cfg-2 (117 MB of probes, 46 MB gallery) is 2 % better the other
+    // way round.  Chunk-major also gives every probe row to ONE pair at a time, so thresholds are never stale: half
+    // the candidates.
+    {
+        const int64_t probe_bytes = static_cast<int64_t>(pl.NT) * pl.BN * g->Dp * 2;
+        const int64_t gallery_bytes = gallery_tiles * kPairM * static_cast<int64_t>(g->Dp) * 2;
+        sp.order = tn.order >= 0 ? tn.order : (probe_bytes <= gallery_bytes ? 0 : 1);
+    }
     sp.g_stride = g_stride; sp.seed_mode = seed_mode;
     sp.issuers = ds->issuers > 0 ? ds->issuers : kIssuers;
     sp.na = ws->na; sp.wl = ws->wl; sp.wr = ws->wr; sp.epsd = ws->epsd; sp.rowmap = ws->rowmap;
@@ -1526,9 +1540,8 @@ static int launch_screen(DeviceState *ds, const eosvr_gallery *g, const ScreenVi
     sp.idesc = umma_idesc_f16(g->screen_fmt == EOSVR_SCREEN_F16 ? 0 : 1, kPairM, pl.BN);
     sp.dbg = (!seed_mode && ws->dbg && ws->dbg_elems >= P * g->G) ? ws->dbg : nullptr;
     sp.exp_mode = tn.exp;
-    const bool rec = timed && ws->timing_on;
-    const int slot = static_cast<int>(ws->timing_calls % kTimingRing);
-    if (rec) EOSVR_CUDA(cudaEventRecord(ws->ev0[slot], st));
+    const int kid = seed ? EOSVR_KERNEL_SEED : EOSVR_KERNEL_SCREEN;
+    { int trc = timing_begin(ws, kid, st); if (trc) return trc; }
     const int ew = choose_ew(g->Dp);
     const bool diag = sp.dbg != nullptr || (tn.exp & 16) != 0;
     const CUtensorMap &tmA = seed ? *sv.tmapSeed : *sv.tmapA;
@@ -1536,7 +1549,7 @@ static int launch_screen(DeviceState *ds, const eosvr_gallery *g, const ScreenVi
     if (ew == 16) rc = diag ? launch_screen_t<16, true>(ds, tmA, tmB, sp, st) : launch_screen_t<16, false>(ds, tmA, tmB, sp, st);
     else rc = diag ? launch_screen_t<8, true>(ds, tmA, tmB, sp, st) : launch_screen_t<8, false>(ds, tmA, tmB, sp, st);
     if (rc) return rc;
-    if (rec) { EOSVR_CUDA(cudaEventRecord(ws->ev1[slot], st)); ++ws->timing_calls; }
+    { int trc = timing_end(ws, kid, st); if (trc) return trc; }
     EOSVR_COUNT_LAUNCH(1);
     return EOSVR_OK;
 }
@@ -1577,7 +1590,7 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
     RowState rs{ws->best, ws->rowflag, ws->rowcnt, ws->gthr};
 
     RerankParams rp;
-    rp.probes = probes; rp.gal = g->feats; rp.P = P; rp.G = g->G; rp.offset = g->offset;
+    rp.probes = probes; rp.gal = g->feats; rp.gal_dtype = g->dtype; rp.P = P; rp.G = g->G; rp.offset = g->offset;
     rp.D = g->D; rp.rpe = rpe; rp.metric = metric; rp.lam1 = lam1; rp.lam2 = lam2;
     rp.cand = ws->cand; rp.rowcnt = ws->rowcnt; rp.cand_cap = static_cast<int32_t>(ws->cand_cap);
     rp.ctr = ws->counters; rp.gthr = ws->gthr;
@@ -1596,6 +1609,8 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
         EOSVR_COUNT_LAUNCH(1);
     } else {
         const unsigned pblocks = static_cast<unsigned>((ncol * 32 + threads - 1) / threads);
+        rc = timing_begin(ws, EOSVR_KERNEL_PROBE_PREP, st);
+        if (rc) return rc;
 #define EOSVR_PROBE_PREP(T16, NORM)                                                                              \
         k_probe_prep<T16, NORM><<<pblocks, threads, 0, st>>>(probes, pd, g->D, g->Dp, lam1 / lam2, scalars,         \
             static_cast<T16 *>(ws->q16), ws->na, ws->epsd, ws->wl, ws->wr, ws->rowmap, rs, ws->counters)
@@ -1603,6 +1618,8 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
         else { if (cosm) EOSVR_PROBE_PREP(__nv_bfloat16, true); else EOSVR_PROBE_PREP(__nv_bfloat16, false); }
 #undef EOSVR_PROBE_PREP
         EOSVR_CUDA(cudaGetLastError());
+        rc = timing_end(ws, EOSVR_KERNEL_PROBE_PREP, st);
+        if (rc) return rc;
         EOSVR_COUNT_LAUNCH(1);
 
         CUtensorMap tmB;
@@ -1613,10 +1630,10 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
         // seed pass over a strided sample of the gallery: tightens every probe row's threshold before the
         // full pass so that concurrent CTAs do not flood the candidate lists (EOSVR_SEED=0 skips it: experiments)
         if (tn.seed && g->seed_tiles > 0 && GT > g->seed_tiles) {
-            rc = launch_screen(ds, g, sv, ws, pl, true, tmB, tn.seed == 1 ? g->seed_tiles : 1, g->seed_stride, P, false, st);
+            rc = launch_screen(ds, g, sv, ws, pl, true, tmB, tn.seed == 1 ? g->seed_tiles : 1, g->seed_stride, P, st);
             if (rc) return rc;
         }
-        rc = launch_screen(ds, g, sv, ws, pl, false, tmB, GT, 1, P, true, st);
+        rc = launch_screen(ds, g, sv, ws, pl, false, tmB, GT, 1, P, st);
         if (rc) return rc;
         ws->last_tiles = pl.NT * GT;
 
@@ -1628,6 +1645,8 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
         const int64_t rr_blocks = (P + rpb - 1) / rpb;
         const unsigned rr_grid = static_cast<unsigned>(rr_blocks < static_cast<int64_t>(num_sms) * 32 ? rr_blocks : num_sms * 32);
         const size_t rr_smem = static_cast<size_t>(cosm ? 2 : 4) * g->D * sizeof(float);
+        rc = timing_begin(ws, EOSVR_KERNEL_RERANK, st);
+        if (rc) return rc;
         if ((g->D & 3) == 0 && rr_smem <= 96 * 1024) {
             {
                 std::lock_guard<std::mutex> lock(g_dev_mu);
@@ -1642,10 +1661,16 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
         }
         else k_rerank<<<num_sms * 8, 256, 0, st>>>(rp);
         EOSVR_CUDA(cudaGetLastError());
+        rc = timing_end(ws, EOSVR_KERNEL_RERANK, st);
+        if (rc) return rc;
         EOSVR_COUNT_LAUNCH(1);
     }
+    rc = timing_begin(ws, EOSVR_KERNEL_FINISH, st);
+    if (rc) return rc;
     k_finish<<<num_sms * 4, kFinThreads, 0, st>>>(rp, cosm ? 1 : 0, out_packed, out_score, out_idx);
     EOSVR_CUDA(cudaGetLastError());
+    rc = timing_end(ws, EOSVR_KERNEL_FINISH, st);
+    if (rc) return rc;
     EOSVR_COUNT_LAUNCH(1);
     return EOSVR_OK;
 }
@@ -1653,27 +1678,50 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
 // -------------------------------------------------------------------------------------------
 // Winner rows (multi-GPU exchange helper and input of the splice kernel).
 // -------------------------------------------------------------------------------------------
-__global__ void k_gather_rows(const float *__restrict__ gal, int64_t G, int64_t offset, int D,
+__global__ void k_gather_rows(const void *__restrict__ gal, int gdt, int64_t G, int64_t offset, int D,
                               const int64_t *__restrict__ idx, float *__restrict__ out)
 {
     const int64_t p = blockIdx.x;
     const int64_t g = idx[p] - offset;
     const bool own = g >= 0 && g < G;
-    const float *src = gal + (own ? g : 0) * D;
+    const int64_t src = (own ? g : 0) * D;
     float *dst = out + p * D;
     if ((D & 3) == 0) {
-        const float4 *s4 = reinterpret_cast<const float4 *>(src);
         float4 *d4 = reinterpret_cast<float4 *>(dst);
-        for (int k = threadIdx.x; k < D / 4; k += blockDim.x) d4[k] = own ? s4[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = threadIdx.x; k < D / 4; k += blockDim.x) d4[k] = own ? ld_feat4(gal, gdt, src / 4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
-        for (int k = threadIdx.x; k < D; k += blockDim.x) dst[k] = own ? src[k] : 0.f;
+        for (int k = threadIdx.x; k < D; k += blockDim.x) dst[k] = own ? ld_feat(gal, gdt, src + k) : 0.f;
     }
+}
+
+__global__ void k_upcast_bf16(const unsigned short *__restrict__ in, int64_t n, float *__restrict__ out)
+{
+    const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const uint2 u = *reinterpret_cast<const uint2 *>(in + i);
+        *reinterpret_cast<float4 *>(out + i) = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u),
+                                                           __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+    } else {
+        for (int64_t j = i; j < n; ++j) out[j] = __uint_as_float(static_cast<uint32_t>(in[j]) << 16);
+    }
+}
+
+int launch_upcast_bf16(const void *in, int64_t n, float *out, cudaStream_t st)
+{
+    if (n == 0) return EOSVR_OK;
+    const int threads = 256;
+    const int64_t groups = (n + 3) / 4;
+    k_upcast_bf16<<<static_cast<unsigned>((groups + threads - 1) / threads), threads, 0, st>>>(
+        static_cast<const unsigned short *>(in), n, out);
+    EOSVR_CUDA(cudaGetLastError());
+    EOSVR_COUNT_LAUNCH(1);
+    return EOSVR_OK;
 }
 
 int launch_gather_rows(const eosvr_gallery *g, const int64_t *idx, int64_t P, float *out, cudaStream_t st)
 {
     if (P == 0) return EOSVR_OK;
-    k_gather_rows<<<static_cast<unsigned>(P), 128, 0, st>>>(g->feats, g->G, g->offset, g->D, idx, out);
+    k_gather_rows<<<static_cast<unsigned>(P), 128, 0, st>>>(g->feats, g->dtype, g->G, g->offset, g->D, idx, out);
     EOSVR_CUDA(cudaGetLastError());
     EOSVR_COUNT_LAUNCH(1);
     return EOSVR_OK;

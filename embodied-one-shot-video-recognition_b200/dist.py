@@ -72,7 +72,7 @@ class SymmetricGallery:
         ends = [int(allmeta[r, 1] + allmeta[r, 0]) for r in range(world)]
         if any(begins[r + 1] != ends[r] for r in range(world - 1)) or begins[0] != 0:
             raise ValueError("shards must be contiguous, ascending by rank and start at row 0")
-        self.buffer = symm.empty(max_rows, D, dtype=torch.float32, device=dev)
+        self.buffer = symm.empty(max_rows, D, dtype=shard_feats.dtype, device=dev)
         self.buffer[:rows].copy_(shard_feats.to(dev, non_blocking=True))
         self.handle = symm.rendezvous(self.buffer, group)
         torch.cuda.synchronize()

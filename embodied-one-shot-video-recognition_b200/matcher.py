@@ -12,7 +12,10 @@ import ctypes
 import torch
 
 from eosvr_b200 import _lib
-from eosvr_b200._lib import (METRIC_COSINE, METRIC_EUCLID_TEMPORAL, ORIG_REF_QUIRK, SCREEN_F16, check, lib)
+import contextlib
+
+from eosvr_b200._lib import (DTYPE_BF16, DTYPE_F32, KERNELS, METRIC_COSINE, METRIC_EUCLID_TEMPORAL, ORIG_REF_QUIRK,
+                             SCREEN_BF16, SCREEN_F16, check, lib)
 
 LAMDA1, LAMDA2 = 0.1, 1.0     # utils.py:43
 
@@ -22,13 +25,27 @@ def _stream_ptr(stream=None):
     return ctypes.c_void_p(s.cuda_stream)
 
 
+def upcast_bf16(t: torch.Tensor, out: torch.Tensor | None = None, stream=None) -> torch.Tensor:
+    """bfloat16 CUDA tensor -> float32 (exact), by the library's kernel (eosvr_upcast_bf16)."""
+    t = t.contiguous()
+    if out is None:
+        out = torch.empty(t.shape, dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device):
+        check(lib().eosvr_upcast_bf16(_ptr(t), t.numel(), _ptr(out), _stream_ptr(stream)), "eosvr_upcast_bf16")
+    return out
+
+
 def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    """float32 CUDA tensor, contiguous; bfloat16 inputs (the half-size transport format) are upcast exactly on the
+    device by the library."""
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor")
     if not t.is_cuda:
         raise ValueError(f"{name} must live on a CUDA device (there is no CPU fallback)")
+    if t.dtype == torch.bfloat16:
+        return upcast_bf16(t)
     if t.dtype != torch.float32:
-        raise TypeError(f"{name} must be float32, got {t.dtype}")
+        raise TypeError(f"{name} must be float32 (or bfloat16), got {t.dtype}")
     return t.contiguous()
 
 
@@ -36,26 +53,58 @@ def _ptr(t):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
 
+def _stream_scoped(fn):
+    """Run a public call with its `stream=` argument as torch's current stream (see _on_stream)."""
+    import functools
+    import inspect
+    sig = inspect.signature(fn)
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        stream = sig.bind(*args, **kwargs).arguments.get("stream")
+        with _on_stream(stream):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
+def _on_stream(stream):
+    """Context that makes `stream` torch's current stream, so that the tensors a call allocates and the NCCL
+    collectives it issues are ordered on the same stream as the library's kernels (None: leave it alone)."""
+    return contextlib.nullcontext() if stream is None else torch.cuda.stream(stream)
+
+
 class GalleryFeatureCache:
     """Gallery segment features resident in HBM -- replaces the per-run arrays of
     network_test.py:184-189 (``gallery_seg_features``).
 
-    feats: [G, D] float32 CUDA tensor (kept alive by this object; the exact re-rank reads it).
+    feats: [G, D] float32 or bfloat16 CUDA tensor (kept alive by this object; the exact re-rank reads it).
     global_offset: index of row 0 in the un-sharded gallery (multi-GPU sharding by segment).
     """
 
-    def __init__(self, feats: torch.Tensor, global_offset: int = 0, screen_fmt: int = SCREEN_F16, stream=None):
-        feats = _dev_f32(feats, "feats")
+    def __init__(self, feats: torch.Tensor, global_offset: int = 0, screen_fmt: int | None = None, stream=None):
+        if not isinstance(feats, torch.Tensor) or not feats.is_cuda:
+            raise ValueError("feats must be a CUDA tensor (there is no CPU fallback)")
+        if feats.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"feats must be float32 or bfloat16, got {feats.dtype}")
+        feats = feats.contiguous()
         if feats.dim() != 2:
             raise ValueError("feats must be [G, D]")
         self.feats = feats
+        self.dtype = DTYPE_BF16 if feats.dtype == torch.bfloat16 else DTYPE_F32
         self.G, self.D = int(feats.shape[0]), int(feats.shape[1])
         self.global_offset = int(global_offset)
-        self.screen_fmt = int(screen_fmt)
+        # bfloat16 rows are screened as bfloat16 (exact, and in place: no second copy); float32 rows as float16
+        self.screen_fmt = int(screen_fmt) if screen_fmt is not None else (SCREEN_BF16 if self.dtype == DTYPE_BF16 else SCREEN_F16)
         self._h = ctypes.c_void_p()
         with torch.cuda.device(feats.device):
-            check(lib().eosvr_gallery_create(_ptr(feats), self.G, self.D, 0, self.global_offset, self.screen_fmt,
+            check(lib().eosvr_gallery_create(_ptr(feats), self.G, self.D, self.dtype, self.global_offset, self.screen_fmt,
                                              _stream_ptr(stream), ctypes.byref(self._h)), "eosvr_gallery_create")
+
+    def info(self) -> dict:
+        """dict(dtype, owns_screen_copy): storage type and whether the library holds its own 16-bit copy."""
+        dt, own = ctypes.c_int32(), ctypes.c_int32()
+        check(lib().eosvr_gallery_info(self._h, ctypes.byref(dt), ctypes.byref(own)), "eosvr_gallery_info")
+        return dict(dtype=int(dt.value), owns_screen_copy=bool(own.value))
 
     @property
     def handle(self):
@@ -110,8 +159,14 @@ class MatchWorkspace:
 
     def screen_ms(self):
         """(sum of screening-kernel durations in ms, number of calls recorded)."""
+        return self.kernel_ms("screen")
+
+    def kernel_ms(self, kernel):
+        """(sum of durations in ms, launches recorded) of one kernel class since set_timing(True): 'probe_prep',
+        'seed', 'screen', 'rerank', 'finish', 'episode' (the last 128 launches of each)."""
         tot, n = ctypes.c_double(), ctypes.c_int64()
-        check(lib().eosvr_workspace_screen_ms(self._h, ctypes.byref(tot), ctypes.byref(n)), "eosvr_workspace_screen_ms")
+        check(lib().eosvr_workspace_kernel_ms(self._h, KERNELS[kernel] if isinstance(kernel, str) else int(kernel),
+                                              ctypes.byref(tot), ctypes.byref(n)), "eosvr_workspace_kernel_ms")
         return tot.value, n.value
 
     def stats(self, stream=None) -> dict:
@@ -147,6 +202,7 @@ def _metric_id(metric):
     raise ValueError(f"unknown metric {metric!r} (use 'euclidean' or 'cosine')")
 
 
+@_stream_scoped
 def _match(fn_name, gallery, ws, probes, rows_per_episode, lam1, lam2, want_packed, stream, metric=METRIC_EUCLID_TEMPORAL):
     probes = _dev_f32(probes, "probes")
     if probes.dim() != 2 or probes.shape[1] != gallery.D:
@@ -179,6 +235,7 @@ def match_segments_exact(gallery, ws, probes, rows_per_episode, lam1=LAMDA1, lam
     return _match("eosvr_match_exact", gallery, ws, probes, rows_per_episode, lam1, lam2, want_packed, stream, metric)
 
 
+@_stream_scoped
 def merge_top1(gathered_packed: torch.Tensor, stream=None):
     """[nshards, P] packed winners (e.g. after all_gather) -> (idx, score, packed) of the global winner."""
     g = gathered_packed.contiguous()
@@ -194,6 +251,7 @@ def merge_top1(gathered_packed: torch.Tensor, stream=None):
     return idx, score, packed
 
 
+@_stream_scoped
 def gather_winner_rows(gallery: GalleryFeatureCache, idx: torch.Tensor, stream=None) -> torch.Tensor:
     """Rows of the winners this shard owns (zeros elsewhere): [P, D] float32."""
     idx = idx.contiguous()
@@ -204,6 +262,7 @@ def gather_winner_rows(gallery: GalleryFeatureCache, idx: torch.Tensor, stream=N
     return out
 
 
+@_stream_scoped
 def splice_augmented(probes: torch.Tensor, winner_rows: torch.Tensor, n: int, S: int,
                      orig_mode: int = ORIG_REF_QUIRK, stream=None) -> torch.Tensor:
     """network_test.py:220-250 in feature space.  probes [E*n*S, D] (or [E, n, S, D]); winner_rows
@@ -221,6 +280,7 @@ def splice_augmented(probes: torch.Tensor, winner_rows: torch.Tensor, n: int, S:
     return out
 
 
+@_stream_scoped
 def proto_score(support: torch.Tensor, support_y: torch.Tensor, query: torch.Tensor, max_proto: int = 0, stream=None):
     """classifier.py:9-90 for E episodes.  support [E,R,D], support_y [E,R] float32, query [E,Q,D].
     Returns dict(pred int64[E,Q] prototype position, dist float32[E,Q,max_proto] (logits = -dist),
@@ -242,6 +302,7 @@ def proto_score(support: torch.Tensor, support_y: torch.Tensor, query: torch.Ten
     return dict(pred=pred, dist=dist, prob=prob, nproto=nproto)
 
 
+@_stream_scoped
 def episode_score(probes: torch.Tensor, support_y: torch.Tensor, query: torch.Tensor, n: int, S: int,
                   winner_rows: torch.Tensor | None = None, gallery: GalleryFeatureCache | None = None,
                   idx: torch.Tensor | None = None, orig_mode: int = ORIG_REF_QUIRK, max_proto: int = 0, stream=None):
@@ -281,9 +342,10 @@ def episode_score(probes: torch.Tensor, support_y: torch.Tensor, query: torch.Te
     return dict(pred=pred, dist=dist, prob=prob, nproto=nproto)
 
 
+@_stream_scoped
 def episode_score_sharded(probes: torch.Tensor, support_y: torch.Tensor, query: torch.Tensor, n: int, S: int,
                           bases: torch.Tensor, begin: torch.Tensor, idx: torch.Tensor, orig_mode: int = ORIG_REF_QUIRK,
-                          max_proto: int = 0, stream=None):
+                          max_proto: int = 0, stream=None, shard_dtype: int = DTYPE_F32):
     """episode_score with the gallery sharded by segment over the GPUs of the box: winner rows are read in place
     from the owning GPU (``bases``/``begin`` = eosvr_b200.dist.SymmetricGallery tables)."""
     D = int(probes.shape[-1])
@@ -304,13 +366,14 @@ def episode_score_sharded(probes: torch.Tensor, support_y: torch.Tensor, query: 
     pred = torch.empty(E, Q, dtype=torch.int64, device=dev)
     nproto = torch.empty(E, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        check(lib().eosvr_episode_score_sharded(_ptr(probes), _ptr(bases), _ptr(begin), nshards, _ptr(idx),
+        check(lib().eosvr_episode_score_sharded(_ptr(probes), _ptr(bases), int(shard_dtype), _ptr(begin), nshards, _ptr(idx),
                                                 _ptr(support_y), _ptr(query), E, int(n), int(S), Q, D, int(orig_mode),
                                                 mp, _ptr(dist), _ptr(prob), _ptr(pred), _ptr(nproto),
                                                 _stream_ptr(stream)), "eosvr_episode_score_sharded")
     return dict(pred=pred, dist=dist, prob=prob, nproto=nproto)
 
 
+@_stream_scoped
 def temporal_smooth(dist64: torch.Tensor, rows_per_episode: int | None = None, lam1: float = LAMDA1,
                     lam2: float = LAMDA2, stream=None) -> torch.Tensor:
     """network_test.py:103-117 on an explicit float64 [P,G] CUDA distance matrix -> float32 [P,G]."""
@@ -325,6 +388,7 @@ def temporal_smooth(dist64: torch.Tensor, rows_per_episode: int | None = None, l
     return out
 
 
+@_stream_scoped
 def cosine_predict(support: torch.Tensor, query: torch.Tensor, want_sim: bool = False, stream=None,
                    support_y: torch.Tensor | None = None):
     """classifier.py:117-120 for E episodes: support [E,R,D], query [E,Q,D] -> best support-row index [E,Q]
@@ -343,6 +407,7 @@ def cosine_predict(support: torch.Tensor, query: torch.Tensor, want_sim: bool = 
     return (best, sim) if want_sim else best
 
 
+@_stream_scoped
 def segment_features(frames: torch.Tensor, seg_len: int, l2: bool = True, stream=None) -> torch.Tensor:
     """network_test.py:187-189 / :203-205 (+ per-frame L2 of :79-80): [N*seg_len, D] -> [N, D]."""
     frames = _dev_f32(frames, "frames")
@@ -380,14 +445,58 @@ class EpisodePipeline:
         self.group = group
         self.ws = MatchWorkspace(max_episodes * self.rpe, gallery.D, cand_capacity, device=gallery.device)
 
+    def _out_buffers(self, Q: int):
+        """Persistent device outputs of the one-call path (two sets, used alternately: a result stays valid until the
+        second-next run())."""
+        key = int(Q)
+        st = getattr(self, "_outs", None)
+        if st is None or st["Q"] != key:
+            dev, P, E, mp = self.gallery.device, self.ws.max_probe_rows, self.ws.max_probe_rows // self.rpe, self.n_way
+            sets = [dict(packed=torch.empty(P, dtype=torch.int64, device=dev), score=torch.empty(P, dtype=torch.float32, device=dev),
+                         idx=torch.empty(P, dtype=torch.int64, device=dev),
+                         dist=torch.empty(E, key, mp, dtype=torch.float32, device=dev),
+                         prob=torch.empty(E, key, mp, dtype=torch.float32, device=dev),
+                         pred=torch.empty(E, key, dtype=torch.int64, device=dev),
+                         nproto=torch.empty(E, dtype=torch.int32, device=dev)) for _ in range(2)]
+            st = dict(Q=key, sets=sets, turn=0)
+            self._outs = st
+        st["turn"] ^= 1
+        return st["sets"][st["turn"]]
+
     def run(self, probes: torch.Tensor, support_y: torch.Tensor, query: torch.Tensor, stream=None,
-            return_support: bool = False) -> dict:
+            return_support: bool = False, reuse_outputs: bool = False) -> dict:
         """probes [E, n, S, D] (device), support_y [E, n] float32, query [E, Q, D].
-        Returns dict(pred [E,Q], idx [E,n,S], score [E,n,S], dist, prob).  return_support=True goes through the
-        un-fused splice + proto_score calls and also returns the augmented support set."""
+        Returns dict(pred [E,Q], idx [E,n,S], score [E,n,S], dist, prob).  On one GPU this is ONE library call
+        (eosvr_episode_batch) writing into buffers the pipeline owns.  reuse_outputs=True returns views of those buffers
+        (no allocation, no copy; valid until the second-next run() -- the serving loop / bench form); the default
+        returns copies.  return_support=True goes through the un-fused splice + proto_score calls and also returns the
+        augmented support set."""
+        with _on_stream(stream):
+            r = self._run(probes, support_y, query, stream, return_support)
+            if not reuse_outputs and self.group is None and not return_support:
+                r = {k: v.clone() for k, v in r.items()}
+            return r
+
+    def _run(self, probes, support_y, query, stream, return_support):
         E = int(probes.shape[0])
         D = self.gallery.D
-        flat = probes.reshape(E * self.rpe, D)
+        flat = _dev_f32(probes.reshape(E * self.rpe, D), "probes")
+        if self.group is None and not return_support:
+            y, query = _dev_f32(support_y.to(torch.float32), "support_y"), _dev_f32(query, "query")
+            if tuple(y.shape) != (E, self.n) or query.dim() != 3 or query.shape[0] != E or query.shape[2] != D:
+                raise ValueError("support_y [E,n] and query [E,Q,D] expected")
+            Q = int(query.shape[1])
+            o = self._out_buffers(Q)
+            with torch.cuda.device(flat.device):
+                check(lib().eosvr_episode_batch(self.gallery.handle, self.ws.handle, _ptr(flat), _ptr(y), _ptr(query), E,
+                                                self.n, self.S, Q, self.metric, float(self.lam1), float(self.lam2),
+                                                int(self.orig_mode), self.n_way, _ptr(o["packed"]), _ptr(o["score"]),
+                                                _ptr(o["idx"]), _ptr(o["dist"]), _ptr(o["prob"]), _ptr(o["pred"]),
+                                                _ptr(o["nproto"]), _stream_ptr(stream)), "eosvr_episode_batch")
+            P = E * self.rpe
+            return dict(pred=o["pred"][:E], dist=o["dist"][:E], prob=o["prob"][:E], nproto=o["nproto"][:E],
+                        idx=o["idx"][:P].view(E, self.n, self.S), score=o["score"][:P].view(E, self.n, self.S),
+                        packed=o["packed"][:P])
         idx, score, packed = match_segments(self.gallery, self.ws, flat, self.rpe, self.lam1, self.lam2, True, stream,
                                             self.metric)
         rows = None
@@ -430,7 +539,7 @@ class EpisodePipeline:
         if e > b:
             r = episode_score_sharded(flat[b * self.rpe:e * self.rpe], y[b:e], query[b:e], self.n, self.S,
                                       self.shards.bases, self.shards.begin, idx[b * self.rpe:e * self.rpe],
-                                      self.orig_mode, mp, stream)
+                                      self.orig_mode, mp, stream, shard_dtype=self.gallery.dtype)
             mine[:e - b, :, :mp] = r["dist"]
             mine[:e - b, :, mp:2 * mp] = r["prob"]
             mine[:e - b, :, 2 * mp] = r["pred"].to(torch.float32)
@@ -442,67 +551,91 @@ class EpisodePipeline:
                     prob=allr[:, :, mp:2 * mp].contiguous(), nproto=allr[:, 0, 2 * mp + 1].to(torch.int32),
                     idx=idx.view(E, self.n, self.S), score=score.view(E, self.n, self.S))
 
-    def run_host(self, probes_host: torch.Tensor, support_y_host: torch.Tensor, query_host: torch.Tensor,
-                 chunks: int = 8) -> dict:
-        """End-to-end call with HOST tensors (pinned for speed): H2D copies, the pipeline, and the D2H read of
-        predictions and winner indices.  The batch is cut into `chunks` groups of episodes; the copy of group
-        i+1 (on a side stream) overlaps the matching of group i, so the call is bounded by max(PCIe, compute)
-        instead of their sum.  Results are identical to one un-chunked call (episodes are independent)."""
+    # ---- host-buffer entry points --------------------------------------------------------------------------------
+    def _host_slots(self, probes_host, support_y_host, query_host):
         dev = self.gallery.device
-        E = int(probes_host.shape[0])
-        Q = int(query_host.shape[1])
-        chunks = max(1, min(int(chunks), E))
-        key = (E, Q, tuple(probes_host.shape[1:]))
+        E, Q = int(probes_host.shape[0]), int(query_host.shape[1])
+        key = (E, Q, tuple(probes_host.shape[1:]), probes_host.dtype)
         st = getattr(self, "_host_state", None)
         if st is None or st["key"] != key:
-            st = dict(key=key,
-                      p=torch.empty(probes_host.shape, dtype=torch.float32, device=dev),
-                      y=torch.empty(support_y_host.shape, dtype=torch.float32, device=dev),
-                      q=torch.empty(query_host.shape, dtype=torch.float32, device=dev),
-                      pred=torch.empty(E, Q, dtype=torch.int64, device=dev),
-                      idx=torch.empty(E, self.n, self.S, dtype=torch.int64, device=dev),
-                      pred_h=torch.empty(E, Q, dtype=torch.int64).pin_memory(),
-                      idx_h=torch.empty(E, self.n, self.S, dtype=torch.int64).pin_memory(),
-                      copy=torch.cuda.Stream(device=dev))
+            def slot():
+                return dict(p=torch.empty(probes_host.shape, dtype=probes_host.dtype, device=dev),
+                            y=torch.empty(support_y_host.shape, dtype=torch.float32, device=dev),
+                            q=torch.empty(query_host.shape, dtype=query_host.dtype, device=dev),
+                            pred=torch.empty(E, Q, dtype=torch.int64, device=dev),
+                            idx=torch.empty(E, self.n, self.S, dtype=torch.int64, device=dev),
+                            pred_h=torch.empty(E, Q, dtype=torch.int64).pin_memory(),
+                            idx_h=torch.empty(E, self.n, self.S, dtype=torch.int64).pin_memory(),
+                            done=None)
+            st = dict(key=key, slots=[slot(), slot()], turn=0, copy=torch.cuda.Stream(device=dev))
             self._host_state = st
-        compute = torch.cuda.current_stream(dev)
+        return st
+
+    def submit_host(self, probes_host: torch.Tensor, support_y_host: torch.Tensor, query_host: torch.Tensor,
+                    chunks: int = 4) -> int:
+        """Queue one batch given as HOST tensors (pinned for speed) and return a ticket for collect_host().  Nothing
+        here waits for the GPU: the H2D copies run on a side stream, cut into `chunks` groups of episodes so that the
+        copy of group i+1 overlaps the matching of group i, and two input/output slots alternate, so the copies of
+        batch k+1 also overlap the compute and the D2H read of batch k.  Episodes are independent: results equal one
+        un-chunked call."""
+        dev = self.gallery.device
+        E = int(probes_host.shape[0])
+        st = self._host_slots(probes_host, support_y_host, query_host)
+        st["turn"] ^= 1
+        sl = st["slots"][st["turn"]]
+        compute, copy = torch.cuda.current_stream(dev), st["copy"]
+        if sl["done"] is not None:
+            copy.wait_event(sl["done"])          # the batch that used this slot last has been read back
         if self.group is not None:
             import torch.distributed as dist
             world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+            compute.wait_stream(copy)
             if E % world == 0 and world > 1:
                 # every rank holds the same host batch: copy 1/world of it over PCIe and replicate it over NVLink
                 # (one all_gather per tensor) instead of pushing the whole batch through every GPU's PCIe link
                 b, e = E * rank // world, E * (rank + 1) // world
                 for key, host in (("p", probes_host), ("y", support_y_host), ("q", query_host)):
                     part = host[b:e].to(dev, non_blocking=True)
-                    dist.all_gather_into_tensor(st[key].view(-1), part.reshape(-1), group=self.group)
+                    dist.all_gather_into_tensor(sl[key].view(-1), part.reshape(-1), group=self.group)
             else:
-                st["p"].copy_(probes_host, non_blocking=True)
-                st["y"].copy_(support_y_host, non_blocking=True)
-                st["q"].copy_(query_host, non_blocking=True)
-            r = self.run(st["p"], st["y"], st["q"])
-            st["pred_h"].copy_(r["pred"], non_blocking=True)
-            st["idx_h"].copy_(r["idx"], non_blocking=True)
-            compute.synchronize()
-            return dict(pred=st["pred_h"], idx=st["idx_h"])
-        copy = st["copy"]
-        copy.wait_stream(compute)           # the previous call may still be reading the device buffers
-        bounds = [(E * c // chunks, E * (c + 1) // chunks) for c in range(chunks)]
-        events = []
-        with torch.cuda.stream(copy):
-            for b, e in bounds:
-                st["p"][b:e].copy_(probes_host[b:e], non_blocking=True)
-                st["y"][b:e].copy_(support_y_host[b:e], non_blocking=True)
-                st["q"][b:e].copy_(query_host[b:e], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy)
-                events.append(ev)
-        for (b, e), ev in zip(bounds, events):
-            compute.wait_event(ev)
-            r = self.run(st["p"][b:e], st["y"][b:e], st["q"][b:e])
-            st["pred"][b:e].copy_(r["pred"])
-            st["idx"][b:e].copy_(r["idx"])
-        st["pred_h"].copy_(st["pred"], non_blocking=True)
-        st["idx_h"].copy_(st["idx"], non_blocking=True)
-        compute.synchronize()
-        return dict(pred=st["pred_h"], idx=st["idx_h"])
+                sl["p"].copy_(probes_host, non_blocking=True)
+                sl["y"].copy_(support_y_host, non_blocking=True)
+                sl["q"].copy_(query_host, non_blocking=True)
+            r = self.run(sl["p"], sl["y"], sl["q"])
+            sl["pred_h"].copy_(r["pred"], non_blocking=True)
+            sl["idx_h"].copy_(r["idx"], non_blocking=True)
+        else:
+            chunks = max(1, min(int(chunks), E))
+            bounds = [(E * c // chunks, E * (c + 1) // chunks) for c in range(chunks)]
+            events = []
+            with torch.cuda.stream(copy):
+                for b, e in bounds:
+                    sl["p"][b:e].copy_(probes_host[b:e], non_blocking=True)
+                    sl["y"][b:e].copy_(support_y_host[b:e], non_blocking=True)
+                    sl["q"][b:e].copy_(query_host[b:e], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy)
+                    events.append(ev)
+            for (b, e), ev in zip(bounds, events):
+                compute.wait_event(ev)
+                r = self.run(sl["p"][b:e], sl["y"][b:e], sl["q"][b:e], reuse_outputs=True)
+                sl["pred"][b:e].copy_(r["pred"])
+                sl["idx"][b:e].copy_(r["idx"])
+            sl["pred_h"].copy_(sl["pred"], non_blocking=True)
+            sl["idx_h"].copy_(sl["idx"], non_blocking=True)
+        sl["done"] = torch.cuda.Event()
+        sl["done"].record(compute)
+        return st["turn"]
+
+    def collect_host(self, ticket: int) -> dict:
+        """Wait for the batch submitted under `ticket`; returns pinned host tensors dict(pred [E,Q], idx [E,n,S]) that
+        stay valid until the second-next submit_host()."""
+        sl = self._host_state["slots"][ticket]
+        sl["done"].synchronize()
+        return dict(pred=sl["pred_h"], idx=sl["idx_h"])
+
+    def run_host(self, probes_host: torch.Tensor, support_y_host: torch.Tensor, query_host: torch.Tensor,
+                 chunks: int = 4) -> dict:
+        """End-to-end call with HOST tensors: H2D copies, the pipeline, and the D2H read of predictions and winner
+        indices (submit_host + collect_host)."""
+        return self.collect_host(self.submit_host(probes_host, support_y_host, query_host, chunks))

@@ -38,6 +38,10 @@ extern "C" {
 
 /* feature storage types */
 #define EOSVR_F32  0          /* float32 rows (the reference's dtype, network_test.py:187-189) */
+#define EOSVR_BF16 1          /* bfloat16 rows: half the HBM and PCIe bytes.  All arithmetic runs on the exactly
+                               * upcast values, so results are bit-equal to the reference evaluated on the same
+                               * (bfloat16-rounded) inputs.  With EOSVR_SCREEN_BF16 and D % 8 == 0 the tensor-core
+                               * pass reads the caller's rows in place: no second copy of the gallery in HBM. */
 
 /* 16-bit format of the tensor-core screening copy */
 #define EOSVR_SCREEN_F16   0  /* default: fp16, 11-bit significand -> tight error bound */
@@ -77,6 +81,11 @@ int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtyp
                          eosvr_gallery_t **out);
 int eosvr_gallery_destroy(eosvr_gallery_t *g);
 int eosvr_gallery_rows(const eosvr_gallery_t *g, int64_t *G, int32_t *D, int64_t *global_offset);
+/* Storage type (EOSVR_F32 / EOSVR_BF16) of the handle's rows and whether the library holds its own 16-bit copy. */
+int eosvr_gallery_info(const eosvr_gallery_t *g, int32_t *dtype, int32_t *owns_screen_copy);
+
+/* bfloat16 -> float32 (exact) for probe / query batches that travelled as bfloat16: d_in [n] bf16, d_out [n] f32. */
+int eosvr_upcast_bf16(const void *d_in, int64_t n, float *d_out, void *stream);
 
 /* ---- workspace --------------------------------------------------------------------
  * Scratch for up to max_probe_rows probe segments of dimension D per call.
@@ -176,12 +185,26 @@ int eosvr_episode_score(const float *d_probes, const float *d_winner_rows, const
                         int32_t max_proto, float *d_dist, float *d_prob, int64_t *d_pred,
                         int32_t *d_nproto, void *stream);
 
+/* ---- the whole path in ONE call (`eosvr_episode_batch`) ------------------
+ * eosvr_match followed by eosvr_episode_score on the local gallery g for E episodes of n support clips x S
+ * segments: the loop body of TestNetwork.test_network_aug_segment (network_test.py:195-259) from the cached
+ * embeddings to the predictions.  d_probes [E*n*S, D], d_support_y [E, n], d_query [E, Q, D].
+ * Outputs are caller-provided device buffers: d_out_packed [E*n*S] is required (it is also the shard-merge
+ * payload), d_out_score / d_out_idx [E*n*S] and d_dist / d_prob [E,Q,max_proto], d_pred [E,Q], d_nproto [E] may
+ * be NULL.  No allocation, no host synchronisation; 5 kernel launches (probe prep, seed pass, screening,
+ * re-rank, finish) + 1 (fused splice + ProtoNet). */
+int eosvr_episode_batch(const eosvr_gallery_t *g, eosvr_workspace_t *ws, const float *d_probes,
+                        const float *d_support_y, const float *d_query, int64_t E, int32_t n, int32_t S,
+                        int32_t Q, int32_t metric, float lam1, float lam2, int32_t orig_mode, int32_t max_proto,
+                        uint64_t *d_out_packed, float *d_out_score, int64_t *d_out_idx, float *d_dist,
+                        float *d_prob, int64_t *d_pred, int32_t *d_nproto, void *stream);
+
 /* Same, with the gallery SHARDED by segment over the GPUs of one box (new): shard s holds the
- * global rows [d_shard_begin[s], d_shard_begin[s+1]) at d_shard_bases[s], a float32 [rows, D] array in the memory
+ * global rows [d_shard_begin[s], d_shard_begin[s+1]) at d_shard_bases[s], a float32 / bfloat16 (shard_dtype) [rows, D] array in the memory
  * of the GPU that owns it, mapped into this process (peer / symmetric memory).  Winner rows are read IN PLACE over
  * NVLink by the scoring kernel -- no dense row exchange.  d_shard_bases [nshards] and d_shard_begin [nshards+1] are
  * device arrays.  Needs D % 4 == 0, D >= 256 and S in {2,4,8}. */
-int eosvr_episode_score_sharded(const float *d_probes, const float *const *d_shard_bases,
+int eosvr_episode_score_sharded(const float *d_probes, const void *const *d_shard_bases, int32_t shard_dtype,
                                 const int64_t *d_shard_begin, int32_t nshards, const int64_t *d_idx,
                                 const float *d_support_y, const float *d_query, int64_t E, int32_t n, int32_t S,
                                 int32_t Q, int32_t D, int32_t orig_mode, int32_t max_proto, float *d_dist,
@@ -206,11 +229,20 @@ int eosvr_segment_features(const float *d_frames, int64_t N, int32_t seg_len, in
                            int32_t l2, float *d_out, void *stream);
 
 /* ---- measurement hooks -----------------------------------------------------------------
- * set_timing(on): bracket the screening kernel of every following eosvr_match on this
- * workspace with CUDA events on the call's stream (ring of 256 calls, restarted by this call).
- * screen_ms: sum of the recorded kernel durations and their count (synchronises the events).
+ * set_timing(on): bracket every kernel the following calls on this workspace launch with CUDA
+ * events on the call's stream (per kernel class a ring of the last 128 launches, restarted by
+ * this call).  kernel_ms: sum of the recorded durations of one kernel class and their count
+ * (synchronises the events); screen_ms = kernel_ms(EOSVR_KERNEL_SCREEN).
  * launch_count: kernels this library has launched in the process (host-side count). */
+#define EOSVR_KERNEL_PROBE_PREP 0  /* k_probe_prep: 16-bit probe plan, norms, error bounds, row-state reset */
+#define EOSVR_KERNEL_SEED       1  /* k_match_screen over the strided seed sample                           */
+#define EOSVR_KERNEL_SCREEN     2  /* k_match_screen, main pass (the dominant kernel)                       */
+#define EOSVR_KERNEL_RERANK     3  /* k_rerank_rows: exact re-rank of the candidates                        */
+#define EOSVR_KERNEL_FINISH     4  /* k_finish: unpack winners (+ exhaustive fallback)                      */
+#define EOSVR_KERNEL_EPISODE    5  /* k_episode_partial: fused splice + ProtoNet (eosvr_episode_batch only) */
+#define EOSVR_KERNEL_COUNT      6
 int      eosvr_workspace_set_timing(eosvr_workspace_t *ws, int32_t on);
+int      eosvr_workspace_kernel_ms(eosvr_workspace_t *ws, int32_t kernel, double *sum_ms, int64_t *calls);
 int      eosvr_workspace_screen_ms(eosvr_workspace_t *ws, double *sum_ms, int64_t *calls);
 uint64_t eosvr_launch_count(void);
 /* Host-only: the probe tiling eosvr_match uses for (P, rows_per_episode):

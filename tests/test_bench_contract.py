@@ -24,13 +24,15 @@ def test_reference_arm_line():
     assert d["impl"] == "reference"
     assert d["metric"] == "gallery_segment_comparisons_per_s" and d["unit"] == "comparisons/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
-    assert d["config"]["workload"].startswith("cfg-2 UnrealAction-shaped 14-way 1-shot")
+    assert d["config"]["workload"].startswith("cfg-3 5-way 1-shot episodes")
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     sys.path.insert(0, ROOT)
     import bench
-    assert d["config"]["workload"] == bench.WORKLOAD and d["metric"] == bench.METRIC
+    # the reference arm carries exactly the config object of our arm for the same run (driver: same_config)
+    assert d["config"] == bench.config_of(bench.CFG3, 1) and d["metric"] == bench.METRIC
+    assert bench.config_of(bench.CFG4, 8)["gallery_segments_total"] == 10_000_000
 
 
 def test_reference_arm_other_ranks_are_silent():

@@ -1,0 +1,41 @@
+"""Results do not depend on how the screening kernel walks its work units (gallery chunk x probe tile), on the number
+of epilogue warps, or on the number of MMA issuer warps: each setting runs in a fresh process (the knobs are read once
+per process) and must reproduce the oracle bit for bit."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import eosvr_b200 as ev, oracle as O, synth
+E, n_way, S, D, G = 24, 5, 4, 256, 9000
+rpe = n_way * S
+ep = synth.episode_batch(61, E, n_way, 1, S, D)
+gal = synth.gallery(62, G, D, centroid_seed=61)
+A = ep["probe"].reshape(-1, D)
+cache = ev.GalleryFeatureCache(torch.from_numpy(gal).cuda())
+ws = ev.MatchWorkspace(E * rpe, D)
+idx, score = ev.match_segments(cache, ws, torch.from_numpy(A).cuda(), rpe)
+oid, oval = O.c_match(A, gal, rpe)
+assert np.array_equal(idx.cpu().numpy(), oid) and np.array_equal(score.cpu().numpy(), oval), ws.stats()
+assert ws.stats()["fallback_rows"] == 0
+print("OK")
+"""
+
+
+@pytest.mark.parametrize("env", [{"EOSVR_ORDER": "0"}, {"EOSVR_ORDER": "1"}, {"EOSVR_ORDER": "2"}, {"EOSVR_EW": "8"},
+                                 {"EOSVR_EW": "16"}, {"EOSVR_ISSUERS": "1"}, {"EOSVR_SEED": "0"}, {"EOSVR_TPU": "3"},
+                                 {"EOSVR_EXP": "63"}])
+def test_knobs_do_not_change_results(env):
+    """(EOSVR_EXP=63 asks for the result-destroying timing modes: the shipped library must ignore them.)"""
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", SCRIPT % (ROOT, os.path.join(ROOT, "oracle"))], capture_output=True, text=True,
+                       env=e, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, (env, r.stdout[-500:], r.stderr[-1500:])

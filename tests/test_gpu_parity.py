@@ -519,3 +519,109 @@ def test_full_size_properties():
         d64 = O.lib_cdist(A[e0:e0 + rpe], gal[idx_h[p]:idx_h[p] + 1])
         t = O.c_temporal_smooth(d64, rpe)
         assert t[p - e0, 0] == score_h[p]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: native bfloat16 storage, the one-call batch entry, per-kernel timing, unit orders, submit / collect
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("D,G", [(512, 3000), (96, 700), (100, 257)])
+def test_native_bf16_storage(D, G):
+    """Real torch.bfloat16 gallery AND probes through the ABI (EOSVR_BF16): all arithmetic runs on the exactly upcast
+    values, so winners and scores are bit-equal to the oracle evaluated on the same rounded inputs.  D % 8 == 0: the
+    tensor-core pass reads the caller's rows in place (no second copy); otherwise the library keeps a padded copy."""
+    E, n_way, S = 6, 5, 4
+    rpe = n_way * S
+    ep = synth.episode_batch(71, E, n_way, 1, S, D)
+    gal16 = torch.from_numpy(synth.gallery(72, G, D, centroid_seed=71)).to(torch.bfloat16)
+    A16 = torch.from_numpy(ep["probe"].reshape(-1, D)).to(torch.bfloat16)
+    q16 = torch.from_numpy(ep["query"]).to(torch.bfloat16)
+    A, gal, q = A16.to(torch.float32).numpy(), gal16.to(torch.float32).numpy(), q16.to(torch.float32).numpy()
+    cache = ev.GalleryFeatureCache(gal16.cuda())
+    assert cache.info() == dict(dtype=ev.DTYPE_BF16, owns_screen_copy=(D % 8 != 0))
+    ws = ev.MatchWorkspace(E * rpe, D)
+    idx, score = ev.match_segments(cache, ws, A16.cuda(), rpe)
+    oid, oval = O.c_match(A, gal, rpe)
+    assert np.array_equal(idx.cpu().numpy(), oid) and np.array_equal(score.cpu().numpy(), oval), ws.stats()
+    i2, s2 = ev.match_segments_exact(cache, ws, A16.cuda(), rpe)
+    assert np.array_equal(i2.cpu().numpy(), oid) and np.array_equal(s2.cpu().numpy(), oval)
+    # whole path on the bfloat16 tensors: equal to the oracle on the rounded values
+    pipe = ev.EpisodePipeline(cache, n_way, 1, S, E)
+    r = pipe.run(A16.cuda().view(E, n_way, S, D), _cuda(ep["support_y"]), q16.cuda())
+    for e in range(E):
+        o = O.lib_episode(A[e * rpe:(e + 1) * rpe].reshape(n_way, S, D), ep["support_y"][e], q[e], gal)
+        assert np.array_equal(r["idx"][e].cpu().numpy(), o["ids"]) and np.array_equal(r["pred"][e].cpu().numpy(), o["pred"])
+        assert np.array_equal(r["dist"][e, :, :n_way].cpu().numpy(), o["dist32"])
+    # the same values stored as float32 give the same answer (storage type does not matter)
+    cache32 = ev.GalleryFeatureCache(gal16.to(torch.float32).cuda())
+    i3, s3 = ev.match_segments(cache32, ws, _cuda(A), rpe)
+    assert torch.equal(i3, idx) and torch.equal(s3, score)
+    # winner rows from the bfloat16 gallery
+    rows = ev.gather_winner_rows(cache, idx)
+    assert np.array_equal(rows.cpu().numpy(), gal[oid])
+
+
+def test_episode_batch_one_call_equals_two_calls():
+    """eosvr_episode_batch (one ABI call, caller-provided outputs) == eosvr_match + eosvr_episode_score, for both
+    metrics, and it launches 6 kernels (probe prep, seed pass, screening, re-rank, finish, fused splice + ProtoNet)."""
+    E, n_way, S, D, G = 40, 5, 4, 512, 30000
+    ep = synth.episode_batch(81, E, n_way, 1, S, D)
+    cache = ev.GalleryFeatureCache(_cuda(synth.gallery(82, G, D, centroid_seed=81)))
+    p, y, q = _cuda(ep["probe"]), _cuda(ep["support_y"]), _cuda(ep["query"])
+    for metric in ("euclidean", "cosine"):
+        pipe = ev.EpisodePipeline(cache, n_way, 1, S, E, metric=metric)
+        pipe.run(p, y, q)                                             # warm: self-check, lazy cosine copy
+        n0 = int(ev.lib().eosvr_launch_count())
+        r = pipe.run(p, y, q, reuse_outputs=True)
+        launches = int(ev.lib().eosvr_launch_count()) - n0
+        assert launches == 6, launches
+        idx, score = ev.match_segments(cache, pipe.ws, p.reshape(-1, D), n_way * S, metric=metric)
+        two = ev.episode_score(p.reshape(-1, D), y, q, n_way, S, gallery=cache, idx=idx, max_proto=n_way)
+        assert torch.equal(r["idx"].reshape(-1), idx) and torch.equal(r["score"].reshape(-1), score)
+        assert torch.equal(r["pred"], two["pred"]) and torch.equal(r["dist"], two["dist"]) and torch.equal(r["prob"], two["prob"])
+
+
+def test_kernel_timing_hooks():
+    E, n_way, S, D, G = 16, 5, 4, 256, 20000
+    ep = synth.episode_batch(83, E, n_way, 1, S, D)
+    cache = ev.GalleryFeatureCache(_cuda(synth.gallery(84, G, D, centroid_seed=83)))
+    pipe = ev.EpisodePipeline(cache, n_way, 1, S, E)
+    p, y, q = _cuda(ep["probe"]), _cuda(ep["support_y"]), _cuda(ep["query"])
+    pipe.run(p, y, q)
+    pipe.ws.set_timing(True)
+    for _ in range(3):
+        pipe.run(p, y, q)
+    for k in ("probe_prep", "seed", "screen", "rerank", "finish", "episode"):
+        ms, calls = pipe.ws.kernel_ms(k)
+        assert calls == 3 and 0.0 < ms < 1000.0, (k, ms, calls)
+    assert pipe.ws.screen_ms() == pipe.ws.kernel_ms("screen")
+    pipe.ws.set_timing(False)
+    assert pipe.ws.kernel_ms("screen") == (0.0, 0)
+
+
+def test_submit_collect_two_batches_in_flight():
+    """submit_host / collect_host with two batches in flight return what run() returns for each batch."""
+    E, n_way, S, D, G = 12, 5, 4, 256, 5000
+    cache = ev.GalleryFeatureCache(_cuda(synth.gallery(86, G, D, centroid_seed=85)))
+    pipe = ev.EpisodePipeline(cache, n_way, 1, S, E)
+    eps = [synth.episode_batch(85 + i, E, n_way, 1, S, D) for i in range(4)]
+    want = []
+    for ep in eps:
+        r = pipe.run(_cuda(ep["probe"]), _cuda(ep["support_y"]), _cuda(ep["query"]))
+        want.append((r["pred"].cpu(), r["idx"].cpu()))
+    hosts = [[torch.from_numpy(ep[k]).pin_memory() for k in ("probe", "support_y", "query")] for ep in eps]
+    tickets, got = [], []
+    for i, h in enumerate(hosts):
+        tickets.append(pipe.submit_host(*h, chunks=3))
+        if len(tickets) > 1:
+            r = pipe.collect_host(tickets.pop(0))
+            got.append((r["pred"].clone(), r["idx"].clone()))
+    r = pipe.collect_host(tickets.pop(0))
+    got.append((r["pred"].clone(), r["idx"].clone()))
+    for (wp, wi), (gp, gi) in zip(want, got):
+        assert torch.equal(wp, gp) and torch.equal(wi, gi)
+    # bfloat16 transport: half the bytes over PCIe, results equal to the device run on the rounded values
+    ep = eps[0]
+    p16, q16 = torch.from_numpy(ep["probe"]).to(torch.bfloat16), torch.from_numpy(ep["query"]).to(torch.bfloat16)
+    rd = pipe.run(p16.cuda(), _cuda(ep["support_y"]), q16.cuda())
+    rh = pipe.run_host(p16.pin_memory(), torch.from_numpy(ep["support_y"]).pin_memory(), q16.pin_memory())
+    assert torch.equal(rh["pred"], rd["pred"].cpu()) and torch.equal(rh["idx"], rd["idx"].cpu())
