@@ -388,7 +388,10 @@ def run_workload(cfg, args, dev, world, rank, group, dist, steps, warmup, oracle
     else:
         d_gal = feats
     cache = ev.GalleryFeatureCache(d_gal, global_offset=begin)
-    pipe = ev.EpisodePipeline(cache, cfg["n_way"], cfg["k_shot"], cfg["S"], E, group=group, shards=shards)
+    # candidate lists: 128 per probe row by default; the 10 M-row gallery gets 1024 (the number of gallery rows that come
+    # within the screening margin of a row's running best match grows with the gallery: ~235 per row on one GPU here)
+    cand = E * R * 1024 if cfg["G"] > 1_000_000 else 0
+    pipe = ev.EpisodePipeline(cache, cfg["n_way"], cfg["k_shot"], cfg["S"], E, group=group, shards=shards, cand_capacity=cand)
     torch.cuda.synchronize()
     m = measure(cfg, pipe, batches, dev, world, steps, warmup, dist, e2e=e2e)
 
@@ -531,14 +534,14 @@ def run_ours(args):
             m2 = run_workload(CFG2, args, dev, 1, 0, None, dist, sec_steps, sec_warm)
             l2 = line_of(CFG2, m2, 1, sec_steps, sec_warm, peaks, peak_src)
             line["cfg2"] = {k: l2[k] for k in ("value", "ms_per_step", "episodes_per_s", "e2e", "parity_ok", "roofline", "config",
-                                               "steps", "gpu_launches")}
+                                               "steps", "gpu_launches", "matcher_stats")}
             del m2
             torch.cuda.empty_cache()
             s4 = max(3, min(args.steps, 5))
             m4 = run_workload(CFG4, args, dev, 1, 0, None, dist, s4, 3, e2e=False, plant=True)
             l4 = line_of(CFG4, m4, 1, s4, 3, peaks, peak_src)
             line["cfg4_strong_scaling_n1"] = {k: l4[k] for k in ("value", "ms_per_step", "episodes_per_s", "parity_ok", "parity",
-                                                                  "roofline", "config", "steps")}
+                                                                  "roofline", "config", "steps", "matcher_stats")}
             line["parity_ok"] = bool(line["parity_ok"] and l2["parity_ok"] and l4["parity_ok"])
         print(json.dumps(line), flush=True)
         return

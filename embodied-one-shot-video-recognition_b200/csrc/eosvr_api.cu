@@ -7,9 +7,18 @@
 #include <mutex>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "eosvr_internal.h"
 
 namespace eosvr {
+
+// NVTX range around every compute entry point (header-only NVTX v3: a no-op unless a profiler injects itself).
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define EOSVR_RANGE(name) ::eosvr::NvtxRange nvtx_range__(name)
 
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
@@ -142,6 +151,7 @@ int eosvr_device_check(void)
 int eosvr_gallery_create(const void *d_feats, int64_t G, int32_t D, int32_t dtype, int64_t global_offset,
                          int32_t screen_fmt, void *stream, eosvr_gallery_t **out)
 {
+    EOSVR_RANGE("eosvr_gallery_create");
     if (!out) { set_error("gallery_create: out is NULL"); return EOSVR_EINVAL; }
     *out = nullptr;
     if (!d_feats || G < 1 || D < 1) { set_error("gallery_create: need d_feats != NULL, G >= 1, D >= 1"); return EOSVR_EINVAL; }
@@ -232,6 +242,7 @@ int eosvr_gallery_info(const eosvr_gallery_t *g, int32_t *dtype, int32_t *owns_s
 
 int eosvr_upcast_bf16(const void *d_in, int64_t n, float *d_out, void *stream)
 {
+    EOSVR_RANGE("eosvr_upcast_bf16");
     if (n < 0 || (n > 0 && (!d_in || !d_out))) { set_error("upcast_bf16: bad arguments"); return EOSVR_EINVAL; }
     if ((reinterpret_cast<uintptr_t>(d_in) & 7) || (reinterpret_cast<uintptr_t>(d_out) & 15)) { set_error("upcast_bf16: d_in must be 8-byte and d_out 16-byte aligned"); return EOSVR_EINVAL; }
     return launch_upcast_bf16(d_in, n, d_out, static_cast<cudaStream_t>(stream));
@@ -262,7 +273,12 @@ int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capac
     const size_t o_thr = carve(ws->maxP * 4), o_best = carve(ws->maxP * 8), o_rf = carve(ws->maxP * 4);
     const size_t o_rc = carve(ws->maxP * 4), o_ix = carve(ws->maxP * 8);
     const size_t o_cd = carve(static_cast<size_t>(ws->maxP) * ws->cand_cap * sizeof(Cand)), o_ct = carve(sizeof(Counters));
-    ws->ovf_cap = ws->maxP * 16 > (1ll << 16) ? ws->maxP * 16 : (1ll << 16);
+    // shared spill-over buffer of full row lists (16 B per entry): large, because running out of it sends rows to the
+    // exhaustive evaluation, which costs G x D float64 operations per row (53 s per step on a 10 M-row gallery)
+    // (sized like the row lists: half their total, at least 1 Mi and at most 16 Mi entries)
+    ws->ovf_cap = ws->maxP * ws->cand_cap / 2;
+    if (ws->ovf_cap < (1ll << 20)) ws->ovf_cap = 1ll << 20;
+    if (ws->ovf_cap > (1ll << 24)) ws->ovf_cap = 1ll << 24;
     const size_t o_ov = carve(static_cast<size_t>(ws->ovf_cap) * sizeof(OvfCand));
     if (cudaMalloc(&ws->slab, off) != cudaSuccess) {
         cudaGetLastError();
@@ -378,6 +394,7 @@ int eosvr_match(const eosvr_gallery_t *g, eosvr_workspace_t *ws, const float *d_
                 int32_t rows_per_episode, int32_t metric, float lam1, float lam2, uint64_t *d_out_packed,
                 float *d_out_score, int64_t *d_out_idx, void *stream)
 {
+    EOSVR_RANGE("eosvr_match");
     int rc = check_match_args(g, ws, d_probes, P, rows_per_episode, metric, lam1, lam2, d_out_packed);
     if (rc) return rc;
     // (the handle is logically const: the cosine screening copy is a lazily built cache behind a mutex)
@@ -389,6 +406,7 @@ int eosvr_match_exact(const eosvr_gallery_t *g, eosvr_workspace_t *ws, const flo
                       int32_t rows_per_episode, int32_t metric, float lam1, float lam2, uint64_t *d_out_packed,
                       float *d_out_score, int64_t *d_out_idx, void *stream)
 {
+    EOSVR_RANGE("eosvr_match_exact");
     int rc = check_match_args(g, ws, d_probes, P, rows_per_episode, metric, lam1, lam2, d_out_packed);
     if (rc) return rc;
     return launch_match(const_cast<eosvr_gallery_t *>(g), ws, d_probes, P, rows_per_episode, metric, lam1, lam2, true,
@@ -428,12 +446,14 @@ int eosvr_workspace_debug_cycles(eosvr_workspace_t *ws, void *stream, int64_t ou
 int eosvr_merge_top1(const uint64_t *d_gathered, int32_t nshards, int64_t P, uint64_t *d_out_packed,
                      float *d_out_score, int64_t *d_out_idx, void *stream)
 {
+    EOSVR_RANGE("eosvr_merge_top1");
     if (nshards < 1 || P < 0 || (P > 0 && !d_gathered)) { set_error("merge_top1: bad arguments"); return EOSVR_EINVAL; }
     return launch_merge(d_gathered, nshards, P, d_out_packed, d_out_score, d_out_idx, static_cast<cudaStream_t>(stream));
 }
 
 int eosvr_gather_rows(const eosvr_gallery_t *g, const int64_t *d_idx, int64_t P, float *d_out_rows, void *stream)
 {
+    EOSVR_RANGE("eosvr_gather_rows");
     if (!g || P < 0 || (P > 0 && (!d_idx || !d_out_rows))) { set_error("gather_rows: bad arguments"); return EOSVR_EINVAL; }
     return launch_gather_rows(g, d_idx, P, d_out_rows, static_cast<cudaStream_t>(stream));
 }
@@ -441,6 +461,7 @@ int eosvr_gather_rows(const eosvr_gallery_t *g, const int64_t *d_idx, int64_t P,
 int eosvr_splice(const float *d_probes, const float *d_winner_rows, int64_t E, int32_t n, int32_t S, int32_t D,
                  int32_t orig_mode, float *d_out, void *stream)
 {
+    EOSVR_RANGE("eosvr_splice");
     if (E < 0 || n < 1 || S < 1 || D < 1 || (E > 0 && (!d_probes || !d_winner_rows || !d_out))) { set_error("splice: bad arguments"); return EOSVR_EINVAL; }
     if (orig_mode != EOSVR_ORIG_REF_QUIRK && orig_mode != EOSVR_ORIG_CLIP_MEAN) { set_error("splice: bad orig_mode %d", orig_mode); return EOSVR_EINVAL; }
     if (orig_mode == EOSVR_ORIG_REF_QUIRK && n > n * S) { set_error("splice: internal"); return EOSVR_EINVAL; }
@@ -452,6 +473,7 @@ int eosvr_proto_score(const float *d_support, const float *d_support_y, const fl
                       int32_t Q, int32_t D, int32_t max_proto, float *d_dist, float *d_prob, int64_t *d_pred,
                       int32_t *d_nproto, void *stream)
 {
+    EOSVR_RANGE("eosvr_proto_score");
     if (E < 0 || D < 1 || (E > 0 && (!d_support || !d_support_y || !d_query))) { set_error("proto_score: bad arguments"); return EOSVR_EINVAL; }
     return launch_proto_score(d_support, d_support_y, d_query, E, R, Q, D, max_proto, d_dist, d_prob, d_pred, d_nproto,
                               static_cast<cudaStream_t>(stream));
@@ -462,6 +484,7 @@ int eosvr_episode_score(const float *d_probes, const float *d_winner_rows, const
                         int32_t S, int32_t Q, int32_t D, int32_t orig_mode, int32_t max_proto, float *d_dist,
                         float *d_prob, int64_t *d_pred, int32_t *d_nproto, void *stream)
 {
+    EOSVR_RANGE("eosvr_episode_score");
     if (E < 0 || D < 1 || (E > 0 && (!d_probes || !d_support_y || !d_query))) { set_error("episode_score: bad arguments"); return EOSVR_EINVAL; }
     if (E == 0) return EOSVR_OK;
     if (!d_winner_rows && !(g && d_idx)) { set_error("episode_score: need d_winner_rows, or a gallery handle and d_idx"); return EOSVR_EINVAL; }
@@ -479,6 +502,7 @@ int eosvr_episode_batch(const eosvr_gallery_t *g, eosvr_workspace_t *ws, const f
                         uint64_t *d_out_packed, float *d_out_score, int64_t *d_out_idx, float *d_dist,
                         float *d_prob, int64_t *d_pred, int32_t *d_nproto, void *stream)
 {
+    EOSVR_RANGE("eosvr_episode_batch");
     if (E < 0 || n < 1 || S < 1) { set_error("episode_batch: bad shape"); return EOSVR_EINVAL; }
     const int64_t P = E * n * S;
     int rc = check_match_args(g, ws, d_probes, P, n * S, metric, lam1, lam2, d_out_packed);
@@ -501,6 +525,7 @@ int eosvr_episode_score_sharded(const float *d_probes, const void *const *d_shar
                                 int32_t max_proto, float *d_dist, float *d_prob, int64_t *d_pred, int32_t *d_nproto,
                                 void *stream)
 {
+    EOSVR_RANGE("eosvr_episode_score_sharded");
     if (E < 0 || D < 1 || nshards < 1 || nshards > 64 || !d_shard_bases || !d_shard_begin ||
         (E > 0 && (!d_probes || !d_support_y || !d_query || !d_idx))) { set_error("episode_score_sharded: bad arguments"); return EOSVR_EINVAL; }
     if (orig_mode != EOSVR_ORIG_REF_QUIRK && orig_mode != EOSVR_ORIG_CLIP_MEAN) { set_error("episode_score_sharded: bad orig_mode %d", orig_mode); return EOSVR_EINVAL; }
@@ -515,6 +540,7 @@ int eosvr_episode_score_sharded(const float *d_probes, const void *const *d_shar
 int eosvr_temporal_smooth(const double *d_dist64, int64_t P, int64_t G, int32_t rows_per_episode, float lam1,
                           float lam2, float *d_out, void *stream)
 {
+    EOSVR_RANGE("eosvr_temporal_smooth");
     if (P < 0 || G < 0 || rows_per_episode < 1 || (P * G > 0 && (!d_dist64 || !d_out))) { set_error("temporal_smooth: bad arguments"); return EOSVR_EINVAL; }
     int rc = eosvr_device_check();
     if (rc) return rc;
@@ -524,6 +550,7 @@ int eosvr_temporal_smooth(const double *d_dist64, int64_t P, int64_t G, int32_t 
 int eosvr_cosine_predict(const float *d_support, const float *d_query, int64_t E, int32_t R, int32_t Q, int32_t D,
                          float *d_sim, int64_t *d_best, void *stream)
 {
+    EOSVR_RANGE("eosvr_cosine_predict");
     if (E < 0 || R < 1 || Q < 1 || D < 1 || (E > 0 && (!d_support || !d_query || !d_best))) { set_error("cosine_predict: bad arguments"); return EOSVR_EINVAL; }
     int rc = eosvr_device_check();
     if (rc) return rc;
@@ -533,6 +560,7 @@ int eosvr_cosine_predict(const float *d_support, const float *d_query, int64_t E
 int eosvr_segment_features(const float *d_frames, int64_t N, int32_t seg_len, int32_t D, int32_t l2, float *d_out,
                            void *stream)
 {
+    EOSVR_RANGE("eosvr_segment_features");
     if (N < 0 || D < 1 || (N > 0 && (!d_frames || !d_out))) { set_error("segment_features: bad arguments"); return EOSVR_EINVAL; }
     return launch_segment_features(d_frames, N, seg_len, D, l2, d_out, static_cast<cudaStream_t>(stream));
 }

@@ -622,6 +622,7 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int cend = nchunks * (grp + 1) / EG;
         const float xfloor = __uint_as_float(p.ctr->xfloor_bits);
         const float dfloor = sqrtf(xfloor) * 1.000001f;
+        const float dfloor_hard = dfloor * 0.24806947f;      // sqrt(4/65): x~ < 4 E2
         const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
         const int64_t row_in_tile = static_cast<int64_t>(rank) * kBM + q * 32 + lane;
         int acc = 0; uint32_t accphase = 0;
@@ -803,7 +804,32 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 if (rm >= 0) p.dbg[static_cast<int64_t>(rm) * p.G + g] = t[j];
                             }
                         }
-                        if (guard) cm = 0xFFFFu;
+                        if (p.seed_mode) {
+                            // seed pass: nothing is appended, thresholds only.  Warp minimum of every column in one REDUX
+                            // each (lanes inside the cancellation guard stay out: their values are not trusted), then
+                            // lane j publishes column j -- sixteen columns at once instead of a serial loop with ballots
+                            // (the seed pass starts from infinite thresholds, so EVERY chunk comes through here).
+                            const bool okl = rowok && !guard;
+                            unsigned mine = 0x7f800000u;
+#pragma unroll
+                            for (int j = 0; j < kChunk; ++j) {
+                                const unsigned m = __reduce_min_sync(0xffffffffu, okl ? __float_as_uint(t[j]) : 0x7f800000u);
+                                if (lane == j) mine = m;
+                            }
+                            if (lane < kChunk && mine != 0x7f800000u) {
+                                const int c = c0 + lane;
+                                const int32_t rm = tl->row[c];
+                                if (rm >= 0) {
+                                    const float nt = fmaf(__uint_as_float(mine), kSlopMul, tl->mg[c]);
+                                    if (nt < __uint_as_float(*reinterpret_cast<volatile unsigned int *>(&tl->thr[c]))) {
+                                        atomicMin(&tl->thr[c], __float_as_uint(nt));
+                                        atomicMin(p.gthr + rm, __float_as_uint(nt));
+                                    }
+                                }
+                            }
+                            cm = 0;
+                        }
+                        if (guard) cm = p.seed_mode ? 0u : 0xFFFFu;
                         cm = __reduce_or_sync(0xffffffffu, cm);
                         const bool any_guard = __any_sync(0xffffffffu, guard);
 #pragma unroll 1
@@ -815,19 +841,26 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (rm < 0) continue;                          // warp-uniform
                             const float tj = pick16(t, jc);                // warp-uniform index: a jump, no local memory
                             bool uns = false;
+                            float extra = 0.f;
                             if (any_guard) {
-                                // inside the cancellation guard the screening value is not trusted: always a candidate
+                                // Small squared distances amplify the screening error of the distance: |d~ - d| <=
+                                // E2 / (d~ + d).  Three bands of the smallest tap (DESIGN.md "Error bound"):
+                                //   x~ >= 65 E2 : the margin in mg[] holds (|d~ - d| <= sqrt(E2)/16);
+                                //   4 E2 <= x~ < 65 E2 : |d~ - d| <= 0.268 sqrt(E2) = 4.29 x that -- still screened, with
+                                //     3.5 margins of slack on either side (candidate test, threshold update, stored value);
+                                //   x~ < 4 E2 : not trusted at all, always a candidate ("unsafe").
                                 const float dj = pick16(d, jc);
                                 const float dl = jc ? pick16(d, jc - 1) : dprev_in;
                                 const float dr = (jc < kChunk - 1) ? pick16(d, jc + 1) : dn;
                                 const float m3 = fminf(dj, fminf(tl->wl[c] > 0.f ? dl : kBig, tl->wr[c] > 0.f ? dr : kBig));
-                                uns = rowok && (m3 < dfloor);
+                                if (m3 < dfloor_hard) uns = rowok;
+                                else if (m3 < dfloor) extra = 3.5f * tl->mg[c];
                             }
                             float thr = __uint_as_float(*reinterpret_cast<volatile unsigned int *>(&tl->thr[c]));
-                            bool pass = rowok && !uns && (tj <= thr);
+                            bool pass = rowok && !uns && (tj <= thr + extra);
                             if (__ballot_sync(0xffffffffu, pass)) {
                                 // warp minimum in one instruction: t >= 0, so float order == unsigned order of the bits
-                                const float mn = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(pass ? tj : kBig)));
+                                const float mn = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(pass ? tj + extra : kBig)));
                                 const float nt = fmaf(mn, kSlopMul, tl->mg[c]);
                                 if (nt < thr) {
                                     if (lane == 0) {
@@ -836,16 +869,17 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     }
                                     thr = nt;
                                 }
-                                pass = pass && (tj <= thr);
+                                pass = pass && (tj <= thr + extra);
                             }
-                            if (p.seed_mode) continue;
                             const bool app = pass || uns;
                             const unsigned ma = __ballot_sync(0xffffffffu, app);
                             if (ma) {
                                 if (app) {
                                     StagedCand sc;
                                     sc.rm = rm; sc.g = static_cast<int32_t>(g);
-                                    sc.tbits = uns ? kCandUnsafe : __float_as_uint(tj);
+                                    // (wide-band values are stored 3.5 margins low: the re-rank may rely on
+                                    //  stored value - margin/2 <= true value for every candidate)
+                                    sc.tbits = uns ? kCandUnsafe : __float_as_uint(fmaxf(tj - extra, 0.f));
                                     wstage[wn + __popc(ma & ((1u << lane) - 1u))] = sc;
                                 }
                                 wn += __popc(ma);

@@ -63,11 +63,32 @@ def main():
         ok4 = torch.equal(oh["pred"], ref["pred"].cpu()) and torch.equal(oh["idx"], ref["idx"].cpu())
         p2p = f"identical={ok2} cosine_identical={ok3} host_entry_identical={ok4}"
         ok = ok and ok2 and ok3 and ok4
+    # the metric's own shape (5-way 1-shot, S = 4, D = 512) with bfloat16 shards in symmetric memory: the in-place
+    # screening copy, peer loads of bfloat16 winner rows, a tie planted across the first and the last shard
+    bf16 = "skipped"
+    if sg is not None:
+        E5, G5 = 64, 50000
+        ep5 = synth.episode_batch(9, E5, 5, 1, 4, 512)
+        gal5 = torch.from_numpy(synth.gallery(59, G5, 512, centroid_seed=9)).to(torch.bfloat16)
+        p5 = torch.from_numpy(ep5["probe"]).to(torch.bfloat16)
+        gal5[G5 - 9] = gal5[77] = p5.reshape(-1, 512)[123]
+        q5, y5 = torch.from_numpy(ep5["query"]).to(torch.bfloat16).to(dev), torch.from_numpy(ep5["support_y"]).to(dev)
+        p5 = p5.to(dev)
+        ref5 = ev.EpisodePipeline(ev.GalleryFeatureCache(gal5.to(dev)), 5, 1, 4, E5).run(p5, y5, q5)
+        b5, e5 = shard_range(G5, rank, world)
+        sg5 = SymmetricGallery(gal5[b5:e5], b5, dist.group.WORLD)
+        c5 = ev.GalleryFeatureCache(sg5.feats, global_offset=b5)
+        out5 = ev.EpisodePipeline(c5, 5, 1, 4, E5, group=dist.group.WORLD, shards=sg5).run(p5, y5, q5)
+        torch.cuda.synchronize()
+        ok5 = all(torch.equal(ref5[k], out5[k]) for k in ("idx", "score", "pred", "dist"))
+        tie = int(out5["idx"].reshape(-1)[123].item()) == 77
+        bf16 = f"identical={ok5} in_place_copy={not c5.info()['owns_screen_copy']} cross_shard_tie_lowest_index={tie}"
+        ok = ok and ok5 and tie
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"multi_gpu_check world={world} shards={[shard_range(G, r, world) for r in range(world)]} "
-              f"identical_to_single_gpu={bool(flag.item())} peer_memory_path[{p2p}] acc={float((out['pred'].cpu().numpy() == ep['query_y']).mean()):.3f}",
+              f"identical_to_single_gpu={bool(flag.item())} peer_memory_path[{p2p}] bf16_5way_d512[{bf16}] acc={float((out['pred'].cpu().numpy() == ep['query_y']).mean()):.3f}",
               flush=True)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() else 1)
