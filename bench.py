@@ -10,7 +10,9 @@ One step = one pass of the whole hot path over one batch of E = 1024 synthetic e
 
   --gpus 1  workload cfg-3 (BASELINE.json configs[2]): 5-way 1-shot, S = 4 segments/clip, D = 512, gallery of
             100 000 segments, E = 1024 episodes/step (P = 20 480 probe segments).  Secondary measurements in the same
-            JSON line: cfg-2 (configs[1], the round-1 headline: 14-way, S = 8, D = 2048, G = 11 200, E = 256) and
+            JSON line: cfg-3 with bfloat16 features (configs[2] "fp32 vs bf16 features": gallery, probes and queries
+            held and transported as bfloat16), cfg-2 (configs[1], the round-1 headline: 14-way, S = 8, D = 2048,
+            G = 11 200, E = 256) and
             the 1-GPU arm of cfg-4 (the 10 M-segment gallery on ONE GPU), which is the strong-scaling baseline of
             the N > 1 runs.
   --gpus N  workload cfg-4 (configs[3]): the SAME 10 M-segment gallery sharded by segment over the N GPUs (strong
@@ -267,12 +269,16 @@ def kernel_table(cfg, kernel_ms, stats, G_local, peaks):
     return out
 
 
+def _t(a):
+    import torch
+    return a if isinstance(a, torch.Tensor) else torch.from_numpy(a)
+
+
 def measure(cfg, pipe, batches, dev, world, steps, warmup, dist, e2e=True, chunks=2):
     """Device-resident throughput, per-kernel timings and (optionally) the end-to-end host-buffer throughput."""
     import torch
     nb = len(batches)
-    dev_in = [(torch.from_numpy(b["probe"]).to(dev), torch.from_numpy(b["support_y"]).to(dev),
-               torch.from_numpy(b["query"]).to(dev)) for b in batches]
+    dev_in = [(_t(b["probe"]).to(dev), _t(b["support_y"]).to(dev), _t(b["query"]).to(dev)) for b in batches]
     last = {}
 
     def barrier():
@@ -313,8 +319,7 @@ def measure(cfg, pipe, batches, dev, world, steps, warmup, dist, e2e=True, chunk
     res["stats"] = pipe.ws.stats()
     if e2e:
         pipe.ws.set_timing(False)
-        host_in = [(torch.from_numpy(b["probe"]).pin_memory(), torch.from_numpy(b["support_y"]).pin_memory(),
-                    torch.from_numpy(b["query"]).pin_memory()) for b in batches]
+        host_in = [(_t(b["probe"]).pin_memory(), _t(b["support_y"]).pin_memory(), _t(b["query"]).pin_memory()) for b in batches]
         pending = []
 
         def step_host(i):
@@ -356,8 +361,9 @@ def digest_of(idx):
     return hashlib.sha256(np.ascontiguousarray(idx.cpu().numpy()).tobytes()).hexdigest()[:16]
 
 
-def run_workload(cfg, args, dev, world, rank, group, dist, steps, warmup, oracle_ref=None, e2e=True, plant=False):
-    """Build the gallery (shard), run the measurements and the in-run parity checks of one workload."""
+def run_workload(cfg, args, dev, world, rank, group, dist, steps, warmup, oracle_ref=None, e2e=True, plant=False, bf16=False):
+    """Build the gallery (shard), run the measurements and the in-run parity checks of one workload.  bf16=True: the
+    same embeddings rounded once to bfloat16 and held / transported as bfloat16 (EOSVR_BF16 storage)."""
     import torch
     import eosvr_b200 as ev
     from eosvr_b200.dist import shard_range
@@ -375,6 +381,11 @@ def run_workload(cfg, args, dev, world, rank, group, dist, steps, warmup, oracle
         feats = device_gallery(cfg, begin, end, dev, plant_row)
     else:
         feats = torch.from_numpy(host_gallery(cfg)[begin:end]).to(dev)
+    if bf16:
+        feats = feats.to(torch.bfloat16)
+        for b in batches:
+            for k in ("probe", "query"):
+                b[k] = torch.from_numpy(b[k]).to(torch.bfloat16)
     if world > 1:
         try:        # shards in symmetric memory: winner rows are read in place over NVLink by the scoring kernel
             from eosvr_b200.dist import SymmetricGallery
@@ -398,7 +409,7 @@ def run_workload(cfg, args, dev, world, rank, group, dist, steps, warmup, oracle
     # ---- in-run parity -------------------------------------------------------------------------------------------
     parity = {}
     b0 = batches[0]
-    p0, y0, q0 = (torch.from_numpy(b0[k]).to(dev) for k in ("probe", "support_y", "query"))
+    p0, y0, q0 = (_t(b0[k]).to(dev) for k in ("probe", "support_y", "query"))
     r = pipe.run(p0, y0, q0)
     idx, score, pred = r["idx"].reshape(-1), r["score"].reshape(-1), r["pred"].reshape(-1)
     parity["winners_digest"] = digest_of(idx)
@@ -441,7 +452,9 @@ def run_workload(cfg, args, dev, world, rank, group, dist, steps, warmup, oracle
         t = torch.tensor([1 if parity["ok"] else 0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         parity["ok"] = bool(int(t.item()) == 1)
-    m.update(parity=parity, row_exchange=row_exchange, G_local=end - begin, pipe=pipe, cache=cache)
+    m.update(parity=parity, row_exchange=row_exchange, G_local=end - begin, pipe=pipe, cache=cache,
+             storage="bfloat16 gallery, probes and queries (EOSVR_BF16; tensor-core pass reads the caller's rows in place)"
+             if bf16 else "float32")
     return m
 
 
@@ -473,6 +486,7 @@ def line_of(cfg, m, world, steps, warmup, peaks, peak_src):
         "config": dict(config_of(cfg, world)), "episodes_per_s": E / (m["ms_step"] * 1e-3),
         "gpu_launches": m["launches"], "launches_per_step": m["launches"] / max(steps, 1),
         "parity_ok": m["parity"]["ok"], "parity": m["parity"], "winner_row_exchange": m["row_exchange"],
+        "feature_storage": m["storage"],
         "roofline": roofline, "matcher_stats": m["stats"],
     }
     if m.get("ms_e2e"):
@@ -531,6 +545,12 @@ def run_ours(args):
         torch.cuda.empty_cache()
         sec_steps, sec_warm = max(3, min(args.steps, 10)), 3
         if not args.primary_only:
+            mb = run_workload(CFG3, args, dev, 1, 0, None, dist, sec_steps, sec_warm, bf16=True)
+            lb = line_of(CFG3, mb, 1, sec_steps, sec_warm, peaks, peak_src)
+            line["cfg3_bf16_features"] = {k: lb[k] for k in ("value", "ms_per_step", "episodes_per_s", "e2e", "parity_ok", "parity",
+                                                             "roofline", "feature_storage", "steps", "matcher_stats")}
+            del mb
+            torch.cuda.empty_cache()
             m2 = run_workload(CFG2, args, dev, 1, 0, None, dist, sec_steps, sec_warm)
             l2 = line_of(CFG2, m2, 1, sec_steps, sec_warm, peaks, peak_src)
             line["cfg2"] = {k: l2[k] for k in ("value", "ms_per_step", "episodes_per_s", "e2e", "parity_ok", "roofline", "config",
@@ -542,7 +562,7 @@ def run_ours(args):
             l4 = line_of(CFG4, m4, 1, s4, 3, peaks, peak_src)
             line["cfg4_strong_scaling_n1"] = {k: l4[k] for k in ("value", "ms_per_step", "episodes_per_s", "parity_ok", "parity",
                                                                   "roofline", "config", "steps", "matcher_stats")}
-            line["parity_ok"] = bool(line["parity_ok"] and l2["parity_ok"] and l4["parity_ok"])
+            line["parity_ok"] = bool(line["parity_ok"] and lb["parity_ok"] and l2["parity_ok"] and l4["parity_ok"])
         print(json.dumps(line), flush=True)
         return
 

@@ -8,7 +8,9 @@ from eosvr_b200._lib import (EosvrError, lib, lib_path, load_library, ORIG_CLIP_
                              ORIG_REF_QUIRK, SCREEN_BF16, SCREEN_F16, METRIC_COSINE, METRIC_EUCLID_TEMPORAL, DTYPE_BF16, DTYPE_F32)
 from eosvr_b200.matcher import (EpisodePipeline, GalleryFeatureCache, MatchWorkspace,  # noqa: F401
                                 episode_score, gather_winner_rows, match_segments, match_segments_exact, merge_top1, proto_score,
-                                segment_features, splice_augmented, temporal_smooth, cosine_predict, upcast_bf16)
+                                segment_features, splice_augmented, temporal_smooth, cosine_predict, upcast_bf16, clip_features,
+                                take_rows)
+from eosvr_b200.sampler import DeviceEpisodeSampler  # noqa: F401
 
 from eosvr_b200.augment import load_gallery_cache, save_gallery_cache, trainaug_manifest  # noqa: F401
 
@@ -23,4 +25,4 @@ def dropin_path() -> str:
 __all__ = ["dropin_path", "load_gallery_cache", "save_gallery_cache", "trainaug_manifest", "EosvrError", "lib", "lib_path", "load_library", "GalleryFeatureCache", "MatchWorkspace",
            "EpisodePipeline", "episode_score", "gather_winner_rows", "match_segments", "match_segments_exact", "merge_top1", "proto_score",
            "segment_features", "splice_augmented", "temporal_smooth", "cosine_predict", "ORIG_REF_QUIRK", "ORIG_CLIP_MEAN", "SCREEN_F16",
-           "SCREEN_BF16", "METRIC_COSINE", "METRIC_EUCLID_TEMPORAL", "DTYPE_BF16", "DTYPE_F32", "upcast_bf16"]
+           "SCREEN_BF16", "METRIC_COSINE", "METRIC_EUCLID_TEMPORAL", "DTYPE_BF16", "DTYPE_F32", "upcast_bf16", "clip_features", "take_rows", "DeviceEpisodeSampler"]

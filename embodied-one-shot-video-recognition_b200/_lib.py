@@ -66,6 +66,8 @@ SIGNATURES = {
     "eosvr_temporal_smooth": (_c.c_int, [_vp, _i64, _i64, _i32, _f32, _f32, _vp, _vp]),
     "eosvr_cosine_predict": (_c.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
     "eosvr_segment_features": (_c.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "eosvr_clip_features": (_c.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp]),
+    "eosvr_take_rows": (_c.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
 }
 
 

@@ -275,8 +275,8 @@ int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capac
     const size_t o_cd = carve(static_cast<size_t>(ws->maxP) * ws->cand_cap * sizeof(Cand)), o_ct = carve(sizeof(Counters));
     // shared spill-over buffer of full row lists (16 B per entry): large, because running out of it sends rows to the
     // exhaustive evaluation, which costs G x D float64 operations per row (53 s per step on a 10 M-row gallery)
-    // (sized like the row lists: half their total, at least 1 Mi and at most 16 Mi entries)
-    ws->ovf_cap = ws->maxP * ws->cand_cap / 2;
+    // (256 entries per probe row or half the row lists' total, whichever is larger; 1 Mi .. 16 Mi entries)
+    ws->ovf_cap = ws->maxP * 256 > ws->maxP * ws->cand_cap / 2 ? ws->maxP * 256 : ws->maxP * ws->cand_cap / 2;
     if (ws->ovf_cap < (1ll << 20)) ws->ovf_cap = 1ll << 20;
     if (ws->ovf_cap > (1ll << 24)) ws->ovf_cap = 1ll << 24;
     const size_t o_ov = carve(static_cast<size_t>(ws->ovf_cap) * sizeof(OvfCand));
@@ -563,6 +563,26 @@ int eosvr_segment_features(const float *d_frames, int64_t N, int32_t seg_len, in
     EOSVR_RANGE("eosvr_segment_features");
     if (N < 0 || D < 1 || (N > 0 && (!d_frames || !d_out))) { set_error("segment_features: bad arguments"); return EOSVR_EINVAL; }
     return launch_segment_features(d_frames, N, seg_len, D, l2, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int eosvr_clip_features(const float *d_frames, int64_t N, int32_t F, int32_t D, const int32_t *d_nframes, int32_t l2,
+                        float *d_out, void *stream)
+{
+    EOSVR_RANGE("eosvr_clip_features");
+    if (N < 0 || F < 1 || D < 1 || (N > 0 && (!d_frames || !d_out))) { set_error("clip_features: bad arguments"); return EOSVR_EINVAL; }
+    int rc = eosvr_device_check();
+    if (rc) return rc;
+    return launch_clip_features(d_frames, N, F, D, d_nframes, l2, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int eosvr_take_rows(const float *d_src, int64_t n_src, int64_t row_elems, const int64_t *d_idx, int64_t n, float *d_out,
+                    void *stream)
+{
+    EOSVR_RANGE("eosvr_take_rows");
+    if (n < 0 || n_src < 1 || row_elems < 1 || (n > 0 && (!d_src || !d_idx || !d_out))) { set_error("take_rows: bad arguments"); return EOSVR_EINVAL; }
+    int rc = eosvr_device_check();
+    if (rc) return rc;
+    return launch_take_rows(d_src, n_src, row_elems, d_idx, n, d_out, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

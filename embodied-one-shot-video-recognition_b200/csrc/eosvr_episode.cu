@@ -729,4 +729,89 @@ int launch_segment_features(const float *frames, int64_t N, int32_t seg_len, int
     return EOSVR_OK;
 }
 
+// -------------------------------------------------------------------------------------------
+// Clip features with per-clip frame counts: TestNetwork.generate_epoch_features (network_test.py:49-68) for a
+// batch of clips -- the mean over the first nframes[i] frames of the (optionally per-frame L2-normalised, :63)
+// frame features; the baseline test truncates every support clip to its real frame count (:54-55, :145).
+// Sequential float32 accumulation and one true division (numpy's np.mean order).  One warp per clip.
+// -------------------------------------------------------------------------------------------
+__global__ void k_clip_features(const float *__restrict__ frames, int64_t N, int F, int D, const int32_t *__restrict__ nframes,
+                                int l2, float *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t clip = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (clip >= N) return;
+    int nf = nframes ? nframes[clip] : F;
+    nf = nf < 1 ? 1 : (nf > F ? F : nf);
+    const float *base = frames + clip * F * D;
+    for (int k0 = 0; k0 < D; k0 += 32 * 4) {                  // 4 feature columns per lane and sweep
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int f = 0; f < nf; ++f) {
+            const float *x = base + static_cast<int64_t>(f) * D;
+            float nrm = 1.f;
+            if (l2) {
+                double s = 0.0;
+                for (int k = lane; k < D; k += 32) s += static_cast<double>(x[k]) * static_cast<double>(x[k]);
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                nrm = fmaxf(static_cast<float>(sqrt(s)), 1e-12f);      // F.normalize eps
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + j * 32 + lane;
+                if (k < D) {
+                    float v = x[k];
+                    if (l2) v = __fdiv_rn(v, nrm);
+                    acc[j] = f ? __fadd_rn(acc[j], v) : v;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j * 32 + lane;
+            if (k < D) out[clip * D + k] = __fdiv_rn(acc[j], static_cast<float>(nf));
+        }
+    }
+}
+
+int launch_clip_features(const float *frames, int64_t N, int32_t F, int32_t D, const int32_t *nframes, int32_t l2,
+                         float *out, cudaStream_t st)
+{
+    if (N == 0) return EOSVR_OK;
+    const int threads = 256;
+    k_clip_features<<<static_cast<unsigned>((N * 32 + threads - 1) / threads), threads, 0, st>>>(frames, N, F, D, nframes, l2, out);
+    EOSVR_CUDA(cudaGetLastError());
+    EOSVR_COUNT_LAUNCH(1);
+    return EOSVR_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// Index-only episode assembly from a device-resident embedding cache (episode_novel_dataloader.py:19-80 without
+// touching pixels or the host): out[i, :] = src[idx[i], :], rows of row_elems floats.  One block per output row.
+// -------------------------------------------------------------------------------------------
+__global__ void k_take_rows(const float *__restrict__ src, int64_t n_src, int64_t row_elems, const int64_t *__restrict__ idx,
+                            float *__restrict__ out)
+{
+    const int64_t i = blockIdx.x;
+    int64_t r = idx[i];
+    r = r < 0 ? 0 : (r >= n_src ? n_src - 1 : r);             // (validated on the host; never read out of bounds)
+    const float *s = src + r * row_elems;
+    float *d = out + i * row_elems;
+    if ((row_elems & 3) == 0) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(s);
+        float4 *d4 = reinterpret_cast<float4 *>(d);
+        for (int64_t k = threadIdx.x; k < row_elems / 4; k += blockDim.x) d4[k] = s4[k];
+    } else {
+        for (int64_t k = threadIdx.x; k < row_elems; k += blockDim.x) d[k] = s[k];
+    }
+}
+
+int launch_take_rows(const float *src, int64_t n_src, int64_t row_elems, const int64_t *idx, int64_t n, float *out, cudaStream_t st)
+{
+    if (n == 0) return EOSVR_OK;
+    k_take_rows<<<static_cast<unsigned>(n), 256, 0, st>>>(src, n_src, row_elems, idx, out);
+    EOSVR_CUDA(cudaGetLastError());
+    EOSVR_COUNT_LAUNCH(1);
+    return EOSVR_OK;
+}
+
 }  // namespace eosvr

@@ -198,6 +198,9 @@ int launch_merge(const uint64_t *gathered, int32_t nshards, int64_t P, uint64_t 
                  float *out_score, int64_t *out_idx, cudaStream_t st);
 int launch_gather_rows(const eosvr_gallery *g, const int64_t *idx, int64_t P, float *out, cudaStream_t st);
 int launch_upcast_bf16(const void *in, int64_t n, float *out, cudaStream_t st);
+int launch_clip_features(const float *frames, int64_t N, int32_t F, int32_t D, const int32_t *nframes, int32_t l2,
+                         float *out, cudaStream_t st);
+int launch_take_rows(const float *src, int64_t n_src, int64_t row_elems, const int64_t *idx, int64_t n, float *out, cudaStream_t st);
 int launch_splice(const float *probes, const float *wrows, int64_t E, int32_t n, int32_t S, int32_t D,
                   int32_t orig_mode, float *out, cudaStream_t st);
 int launch_episode_score(const float *probes, const float *wrows, const void *gal, int32_t gal_dtype, int64_t G, int64_t goff,

@@ -3,7 +3,8 @@
 Same functions, same dict contract (``support_feature [R,D]``, ``support_y [R]``, ``query_feature
 [Q,D]``, ``query_y [Q]``), numpy in / numpy out; the arithmetic runs in libeosvr.so.
 Differences: any number of queries is accepted (the reference breaks for
-Q > 1, classifier.py:57-61); 'SVM' and 'KNN' are not part of this path and raise.
+Q > 1, classifier.py:57-61; the kernels take 8 queries per launch, more are scored in chunks); 'SVM' and
+'KNN' are not part of this path and raise.
 """
 import numpy as np
 import torch
@@ -20,7 +21,13 @@ def _score(data):
     y = _dev(np.asarray(data['support_y'], dtype=np.float32).reshape(-1))
     q = _dev(np.asarray(data['query_feature'], dtype=np.float32).reshape(-1, sup.shape[1]))
     nq = int(np.asarray(data['query_y']).shape[0])              # classifier.py:57 iterates over query_y
-    r = _ev.proto_score(sup[None], y[None], q[None, :nq], max_proto=min(int(sup.shape[0]), 64))
+    if nq > int(q.shape[0]):
+        raise ValueError(f"query_y has {nq} entries but query_feature only {int(q.shape[0])} rows")
+    mp = min(int(sup.shape[0]), 64)
+    parts = [_ev.proto_score(sup[None], y[None], q[None, q0:min(q0 + 8, nq)], max_proto=mp)      # 8 queries per launch
+             for q0 in range(0, nq, 8)]
+    r = {k: torch.cat([p[k] for p in parts], dim=1) for k in ('pred', 'dist', 'prob')}
+    r['nproto'] = parts[0]['nproto']
     return r, sup, y
 
 

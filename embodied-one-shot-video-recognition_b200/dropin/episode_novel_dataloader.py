@@ -44,8 +44,16 @@ class EpisodeDataloader():
                 support_x.append(clips[i])
                 support_x_frames.append(int(self.frames[class_name][i]) if self.frames else int(clips.shape[1]))
                 support_y.append(aim_class_names.index(class_name))
+        self.last_classes = aim_class_names
         return {'support_x': torch.from_numpy(np.stack(support_x)).float(),
                 'support_y': torch.FloatTensor(support_y),
                 'query_x': torch.from_numpy(np.stack(query_x)).float(),
                 'query_y': torch.FloatTensor(query_y),
                 'support_x_frames': support_x_frames}
+
+    def device_sampler(self, seg_len=None, l2=True, seed=None, device=None):
+        """The same episodes as get_episode(), index-only on a device-resident cache (eosvr_b200.DeviceEpisodeSampler):
+        embeddings are uploaded once, an episode batch costs one small index copy and two gather launches."""
+        import eosvr_b200 as _ev
+        return _ev.DeviceEpisodeSampler(self.data, utils.n_way, utils.k_shot, utils.seg_len if seg_len is None else seg_len,
+                                        l2=l2, seed=seed, device=device)

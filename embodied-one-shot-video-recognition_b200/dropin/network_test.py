@@ -121,21 +121,53 @@ class TestNetwork():
         self.acc_file.flush()
 
     def test_network_baseline(self, pre_model=None):
-        """network_test.py:132-167: episodes without augmentation."""
+        """network_test.py:132-167: episodes without augmentation, ``episodes_per_call`` at a time: the clip features of
+        every support clip (truncated to its real frame count, :54-55, :145) and query clip of the batch come from ONE
+        eosvr_clip_features launch each, and all episodes of the batch are scored by ONE eosvr_proto_score launch
+        (or eosvr_cosine_predict for classifier='cosine')."""
         self._open_log(pre_model)
         accs = []
-        for epoch in range(utils.EPISODE_NUMS[self.mode]):
-            data = self.myEpisodeDataloader.get_episode()
-            support_y = data['support_y'].cpu().detach().numpy()
-            query_y = data['query_y'].cpu().detach().numpy()
-            data_result = {'support_feature': self.generate_epoch_features(data['support_x'], self.L2,
-                                                                           data['support_x_frames']),
-                           'support_y': support_y,
-                           'query_feature': self.generate_epoch_features(data['query_x'], self.L2),
-                           'query_y': query_y}
-            predicted_y = self.myClassifier.predict(data_result)
-            self._report(epoch, np.mean(query_y == predicted_y), accs)
+        epoch_nums = utils.EPISODE_NUMS[self.mode]
+        if self.classifier not in ('protonet', 'cosine'):
+            raise ValueError("the batched baseline scores with classifier='protonet' or 'cosine'")
+        for first in range(0, epoch_nums, self.episodes_per_call):
+            sup, supf, sy, qry, qys = [], [], [], [], []
+            for epoch in range(first, min(first + self.episodes_per_call, epoch_nums)):
+                data = self.myEpisodeDataloader.get_episode()
+                sx, qx = torch.as_tensor(data['support_x']), torch.as_tensor(data['query_x'])
+                if qx.shape[0] != len(data['query_y']):
+                    raise ValueError("query_x and query_y disagree on the number of queries")
+                sup.append(self._clip_frames(sx))
+                supf.append(torch.as_tensor(list(data['support_x_frames']), dtype=torch.int32))
+                qry.append(self._clip_frames(qx))
+                sy.append(torch.as_tensor(data['support_y']).float())
+                qys.append(data['query_y'].cpu().detach().numpy())
+            if len({tuple(x.shape) for x in sup}) != 1 or len({tuple(x.shape) for x in qry}) != 1:
+                raise ValueError("the episodes of one call must have equal shapes")
+            E, R, Q = len(sup), int(sup[0].shape[0]), int(qry[0].shape[0])
+            sfeat = _ev.clip_features(torch.cat(sup), torch.cat(supf), bool(self.L2)).view(E, R, -1)
+            qfeat = _ev.clip_features(torch.cat(qry), None, bool(self.L2)).view(E, Q, -1)
+            y = torch.stack(sy).cuda()
+            preds = []
+            for q0 in range(0, Q, 8):                       # the scoring kernels take up to 8 queries per episode
+                qs = qfeat[:, q0:q0 + 8].contiguous()
+                if self.classifier == 'protonet':
+                    preds.append(_ev.proto_score(sfeat, y, qs, min(R, 64))['pred'])
+                else:
+                    preds.append(_ev.cosine_predict(sfeat, qs))
+            pred = torch.cat(preds, dim=1).cpu().numpy()
+            self.last_batch = {'pred': pred}
+            for j, query_y in enumerate(qys):
+                self._report(first + j, np.mean(query_y == pred[j]), accs)
         self._finish(accs)
+
+    def _clip_frames(self, clips):
+        """[clips, frames, D] cached per-frame embeddings on the device (pixels go through the caller's backbone)."""
+        clips = torch.as_tensor(clips)
+        if clips.dim() == 3:
+            return clips.float().cuda()
+        flat = clips.reshape((-1,) + tuple(clips.shape[2:]))
+        return self._frame_embeddings(flat).view(int(clips.shape[0]), int(clips.shape[1]), -1)
 
     def _segment_rows(self, clips):
         """[clips, frames, ...] -> segment embeddings [clips*num_segs, D] (network_test.py:185-189 / :201-205)."""
@@ -168,8 +200,12 @@ class TestNetwork():
                     return 0
                 if data['support_x'].shape[0] != n or data['support_x'].shape[1] != utils.VIDEO_FRAMES:
                     raise ValueError("episode does not match utils.n_way / k_shot / VIDEO_FRAMES")
+                if data['query_x'].shape[0] != len(data['query_y']):
+                    raise ValueError("query_x and query_y disagree on the number of queries")
+                if data['query_x'].shape[0] > 8:
+                    raise ValueError("at most 8 query clips per episode (kernel limit); the reference uses one")
                 probes.append(self._segment_rows(data['support_x']).view(n, S, -1))
-                queries.append(self._mean_rows(self._frame_embeddings(data['query_x'][0]), bool(self.L2))[None])
+                queries.append(_ev.clip_features(self._clip_frames(data['query_x']), None, bool(self.L2)))
                 ys.append(data['support_y'].float())
                 qys.append(data['query_y'].cpu().detach().numpy())
             r = pipe.run(torch.stack(probes), torch.stack(ys).cuda(), torch.stack(queries))

@@ -421,6 +421,44 @@ def segment_features(frames: torch.Tensor, seg_len: int, l2: bool = True, stream
     return out
 
 
+@_stream_scoped
+def clip_features(frames: torch.Tensor, nframes: torch.Tensor | None = None, l2: bool = True, stream=None) -> torch.Tensor:
+    """network_test.py:49-68 for a batch of clips: frames [N, F, D] -> [N, D], the mean over the first nframes[i]
+    frames (all F when None) of the (per-frame L2-normalised) frame features."""
+    frames = _dev_f32(frames, "frames")
+    if frames.dim() != 3:
+        raise ValueError("frames must be [N, F, D]")
+    N, F, D = (int(x) for x in frames.shape)
+    if nframes is not None:
+        nframes = nframes.to(device=frames.device, dtype=torch.int32).contiguous()
+        if tuple(nframes.shape) != (N,):
+            raise ValueError("nframes must be [N]")
+    out = torch.empty(N, D, dtype=torch.float32, device=frames.device)
+    with torch.cuda.device(frames.device):
+        check(lib().eosvr_clip_features(_ptr(frames), N, F, D, _ptr(nframes), int(bool(l2)), _ptr(out), _stream_ptr(stream)),
+              "eosvr_clip_features")
+    return out
+
+
+@_stream_scoped
+def take_rows(src: torch.Tensor, idx: torch.Tensor, out: torch.Tensor | None = None, stream=None) -> torch.Tensor:
+    """out[i] = src[idx[i]] along the first axis (float32 CUDA, int64 indices): index-only episode assembly."""
+    src = _dev_f32(src, "src")
+    idx = idx.to(device=src.device, dtype=torch.int64).contiguous().view(-1)
+    n_src = int(src.shape[0])
+    row = int(src[0].numel()) if n_src else 0
+    if n_src < 1 or row < 1:
+        raise ValueError("src must have at least one non-empty row")
+    if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= n_src):
+        raise IndexError("take_rows: index out of range")
+    if out is None:
+        out = torch.empty((idx.numel(),) + tuple(src.shape[1:]), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        check(lib().eosvr_take_rows(_ptr(src), n_src, row, _ptr(idx), idx.numel(), _ptr(out), _stream_ptr(stream)),
+              "eosvr_take_rows")
+    return out
+
+
 class EpisodePipeline:
     """The loop body of ``test_network_aug_segment`` (network_test.py:195-259) for a batch of episodes on
     cached segment embeddings: match -> winner rows -> augmented support set -> ProtoNet scoring.

@@ -228,6 +228,18 @@ int eosvr_cosine_predict(const float *d_support, const float *d_query, int64_t E
 int eosvr_segment_features(const float *d_frames, int64_t N, int32_t seg_len, int32_t D,
                            int32_t l2, float *d_out, void *stream);
 
+/* ---- callers either side of the path -----------------------------------
+ * eosvr_clip_features: TestNetwork.generate_epoch_features (network_test.py:49-68) for a batch of clips:
+ * d_frames [N, F, D] per-frame embeddings -> d_out [N, D] = mean over the first d_nframes[i] frames (all F
+ * when d_nframes is NULL) of the frame features, per-frame L2-normalised first when l2 != 0 (:63).  The
+ * baseline test truncates every support clip to its real frame count (:54-55, :145, :151).
+ * eosvr_take_rows: d_out[i, :] = d_src[d_idx[i], :] for rows of row_elems floats -- index-only episode
+ * assembly from a device-resident embedding cache (episode_novel_dataloader.py:19-80 without pixels). */
+int eosvr_clip_features(const float *d_frames, int64_t N, int32_t F, int32_t D, const int32_t *d_nframes,
+                        int32_t l2, float *d_out, void *stream);
+int eosvr_take_rows(const float *d_src, int64_t n_src, int64_t row_elems, const int64_t *d_idx, int64_t n,
+                    float *d_out, void *stream);
+
 /* ---- measurement hooks -----------------------------------------------------------------
  * set_timing(on): bracket every kernel the following calls on this workspace launch with CUDA
  * events on the call's stream (per kernel class a ring of the last 128 launches, restarted by

@@ -276,3 +276,76 @@ def test_classifier_and_temporal_goldens_through_dropin(dropin, golden_dir):
         x = torch.from_numpy(d64.astype(np.float32).T.copy())[None, None]
         y = dropin.models.TemporalLayer()(x)
         assert np.array_equal(y[0, 0].cpu().numpy().T, t)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: batched baseline scorer and the device-resident, index-only sampler (8f-4)
+# ---------------------------------------------------------------------------------------------------------------
+def _numpy_clip_feature(frames, nf, l2):
+    """network_test.py:49-68 restated with numpy for one clip: first nf frames, per-frame L2, float32 mean."""
+    x = np.asarray(frames[:nf], dtype=np.float32)
+    if l2:
+        nrm = np.sqrt((x.astype(np.float64) ** 2).sum(axis=1, keepdims=True)).astype(np.float32)
+        x = x / np.maximum(nrm, np.float32(1e-12))
+    acc = x[0].copy()
+    for f in range(1, nf):
+        acc += x[f]
+    return acc / np.float32(nf)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("classifier", ["protonet", "cosine"])
+def test_batched_baseline_vs_oracle_with_truncated_clips(dropin, tmp_path, classifier):
+    """test_network_baseline on 96 episodes, 32 per call, every support clip truncated to its own real frame count
+    (network_test.py:54-55, :145): the logged per-episode accuracies equal the oracle's ProtoNet / cosine decision
+    computed episode by episode from numpy clip features."""
+    import oracle as O
+    cache = _feature_cache(seed=31, classes=9, clips=7, frames=16, D=48)
+    rng = np.random.RandomState(3)
+    frames = {k: rng.randint(3, 17, size=v.shape[0]).tolist() for k, v in cache.items()}
+    dropin.utils.EPISODE_NUMS["val"] = 96
+    mk = lambda: dropin.episode_novel_dataloader.EpisodeDataloader(mode="val", features=cache, seed=77, frames=frames)  # noqa: E731
+    tn = dropin.network_test.TestNetwork(str(tmp_path / "acc.txt"), classifier=classifier, mode="val", episode_dataloader=mk(),
+                                         episodes_per_call=32)
+    n0 = int(__import__("eosvr_b200").lib().eosvr_launch_count())
+    with contextlib.redirect_stdout(io.StringIO()):
+        tn.test_network_baseline()
+    launches = int(__import__("eosvr_b200").lib().eosvr_launch_count()) - n0
+    assert launches == 3 * 3, launches                      # per call: support clip features, query clip features, scoring
+    got = [float(l.split("acc:")[1].split()[0]) for l in open(tmp_path / "acc.txt") if l.startswith("epoch:")]
+    ref_loader, want = mk(), []
+    for _ in range(96):
+        d = ref_loader.get_episode()
+        sup = np.stack([_numpy_clip_feature(d["support_x"][i].numpy(), d["support_x_frames"][i], True)
+                        for i in range(d["support_x"].shape[0])])
+        q = np.stack([_numpy_clip_feature(d["query_x"][i].numpy(), d["query_x"].shape[1], True)
+                      for i in range(d["query_x"].shape[0])])
+        pred = O.lib_protonet(sup, d["support_y"].numpy(), q)[0] if classifier == "protonet" else O.lib_cosine_predict(sup, q)[0]
+        want.append(float(np.mean(d["query_y"].numpy() == pred)))
+    assert got == want
+
+
+@pytest.mark.gpu
+def test_device_sampler_reproduces_the_host_sampler(dropin):
+    """DeviceEpisodeSampler (index-only, embeddings resident in HBM, one gather per tensor) yields exactly the episodes
+    of EpisodeDataloader.get_episode() for the same seed -- segment rows, query features and labels bit-equal to the
+    host path -- and feeds the pipeline to the same predictions."""
+    import eosvr_b200 as ev
+    cache = _feature_cache(seed=41, classes=10, clips=5, frames=16, D=64)
+    host = dropin.episode_novel_dataloader.EpisodeDataloader(mode="val", features=cache, seed=123)
+    dev = dropin.episode_novel_dataloader.EpisodeDataloader(mode="val", features=cache, seed=999).device_sampler(seed=123)
+    n0 = int(ev.lib().eosvr_launch_count())
+    batch = dev.sample(12)
+    assert int(ev.lib().eosvr_launch_count()) - n0 == 2       # one gather for the probes, one for the queries
+    n, S, D = dropin.utils.n_way * dropin.utils.k_shot, 16 // dropin.utils.seg_len, 64
+    assert tuple(batch["probes"].shape) == (12, n, S, D) and batch["probes"].is_cuda
+    for e in range(12):
+        d = host.get_episode()
+        seg = ev.segment_features(d["support_x"].reshape(-1, D).cuda(), dropin.utils.seg_len, True).view(n, S, D)
+        qf = ev.clip_features(d["query_x"].cuda(), None, True)
+        assert torch.equal(batch["probes"][e], seg) and torch.equal(batch["query"][e], qf)
+        assert torch.equal(batch["support_y"][e].cpu(), d["support_y"]) and torch.equal(batch["query_y"][e], d["query_y"])
+    gal = ev.GalleryFeatureCache(torch.from_numpy(synth.segment_features(43, 600, D)).cuda())
+    pipe = ev.EpisodePipeline(gal, dropin.utils.n_way, dropin.utils.k_shot, S, 12)
+    r = pipe.run(batch["probes"], batch["support_y"], batch["query"])
+    assert tuple(r["pred"].shape) == (12, 1)
