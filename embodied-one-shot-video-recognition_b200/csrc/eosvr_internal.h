@@ -179,7 +179,7 @@ MatchPlan make_plan(int64_t P, int32_t rpe);
 // Per-device launch state (the library may drive several GPUs from one process); guarded by one mutex.
 struct DeviceState {
     int num_sms = 0;
-    int max_clusters[2][2] = {{0, 0}, {0, 0}};   // [DIAG][EW == 16]: co-resident CTA pairs of k_match_screen<EW, DIAG>
+    int max_clusters[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // [plain / DIAG / aligned][EW == 16]: co-resident CTA pairs of k_match_screen
     bool rr_attr = false;
     int issuers = 0;                              // MMA issuer warps in use; 0 = not decided yet (self-check pending)
 };

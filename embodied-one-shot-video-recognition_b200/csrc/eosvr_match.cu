@@ -299,6 +299,8 @@ struct ScreenParams {
     int64_t g_stride;       // gallery row stride (1; > 1 in the seed pass)
     int32_t seed_mode;      // 1: only tighten the thresholds, append nothing
     int32_t issuers;        // MMA issuer warps in use: kIssuers, or 1 (the documented single-issuer ordering)
+    int32_t rpe;            // probe rows per episode (the episode-aligned epilogue needs rpe == its chunk width)
+    float w;                // tap weight lam1 / lam2 towards a neighbour of the same episode
     const float *na, *wl, *wr, *epsd;
     const int32_t *rowmap;
     unsigned int *gthr;
@@ -329,6 +331,8 @@ struct StagedCand {
     uint32_t tbits;
 };
 constexpr int kWarpStage = 64;
+constexpr int kStashCols = 6;      // parked columns per epilogue warp (a full stash is worked off on the spot)
+constexpr int kAlign = 20;         // chunk width of the episode-aligned epilogue: 5-way x 4 segments (the metric's episode)
 
 template <int EW>
 struct __align__(16) ScreenSmemTail {
@@ -349,6 +353,11 @@ struct __align__(16) ScreenSmemTail {
     // per-row lists 32 at a time (one global atomicAdd per lane, all in flight together) instead of stalling on
     // one atomic round trip per column
     StagedCand stage[EW][kWarpStage];
+    // episode-aligned epilogue: columns in which some lane fell below its threshold are parked here (the 32 lanes'
+    // values of the column) and worked off AFTER the accumulator has been handed back to the MMA issuers
+    uint32_t sval[EW][kStashCols][32];
+    int32_t scol[EW][kStashCols];       // column within the tile
+    int32_t sgt[EW][kStashCols];        // gallery tile of the entry
 };
 
 constexpr int kABytes = kBM * kBK * 2;              // 16 KiB: this CTA's 128 gallery rows
@@ -423,6 +432,17 @@ __device__ __forceinline__ float pick16(const float (&t)[kChunk], int j)
     }
 }
 
+__device__ __forceinline__ float pick20(const float (&t)[kAlign], int j)
+{
+    switch (j) {
+        case 0: return t[0];   case 1: return t[1];   case 2: return t[2];   case 3: return t[3];
+        case 4: return t[4];   case 5: return t[5];   case 6: return t[6];   case 7: return t[7];
+        case 8: return t[8];   case 9: return t[9];   case 10: return t[10]; case 11: return t[11];
+        case 12: return t[12]; case 13: return t[13]; case 14: return t[14]; case 15: return t[15];
+        case 16: return t[16]; case 17: return t[17]; case 18: return t[18]; default: return t[19];
+    }
+}
+
 // Store candidate (g, tbits) of probe row rm at list position pos; full lists spill to the shared buffer and only
 // if that is full too is the row handed to the exhaustive exact kernel.
 __device__ __forceinline__ void put_candidate(const ScreenParams &p, int32_t rm, unsigned pos, int32_t g, uint32_t tbits)
@@ -464,7 +484,15 @@ __device__ __forceinline__ void flush_staged(const ScreenParams &p, const Staged
 // lane NEXT in every column it has finished with (tcgen05.st, one chunk behind its reads), and every MMA
 // accumulates, so the tensor core delivers a.b - |b|^2/2 and the squared distance is one FFMA per element:
 // x = fma(acc, -2, |a|^2).  The three issuers therefore never order themselves against each other either.
-template <int EW, bool DIAG>
+//
+// AL > 0 selects the EPISODE-ALIGNED epilogue (requires rows-per-episode == AL, no halo, DIAG off): a chunk is the AL
+// columns of one whole episode, so no tap ever crosses a chunk -- no boundary reads between column groups, no lane-
+// quadrant barrier, no per-column tap weights (w inside the episode, nothing at its ends), 240 columns split evenly
+// as 3 episodes per column group.  Columns in which some lane falls below its threshold are only PARKED in shared
+// memory inside the chunk loop (the column's 32 values); tightening the threshold and appending the candidates
+// happens after the accumulator has gone back to the MMA issuers, in time the warp would otherwise spend waiting for
+// the next accumulator -- the tile's release no longer waits for the slowest warp's candidate handling.
+template <int EW, bool DIAG, int AL>
 __global__ void __launch_bounds__(screen_threads(EW), 1)
 k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ScreenParams p)
@@ -657,6 +685,48 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         cursor_next(p, ahead, npairs);                    // from here on: the next tile to use the accumulator `cur` is in
         StagedCand *wstage = tl->stage[warp - 4];
         int wn = 0;                                       // candidates parked by this warp (warp-uniform)
+        int ns = 0;                                       // columns parked by the aligned epilogue (warp-uniform)
+        // Work off the parked columns: per column tighten the threshold with the warp minimum, then stage what is still
+        // below it for the row's candidate list (the generic epilogue's per-column step, off the tile's critical path).
+        auto drain_stash = [&]() {
+            __syncwarp();
+            for (int k = 0; k < ns; ++k) {
+                const int c = tl->scol[warp - 4][k];
+                const int32_t rm = tl->row[c];
+                if (rm < 0) continue;                             // warp-uniform
+                const uint32_t tb = tl->sval[warp - 4][k][lane];
+                const bool uns = tb == kCandUnsafe;
+                const float tj = __uint_as_float(tb);
+                float thr = __uint_as_float(*reinterpret_cast<volatile unsigned int *>(&tl->thr[c]));
+                bool pass = !uns && (tj <= thr);                  // (lanes that were not below the threshold hold +inf)
+                if (__ballot_sync(0xffffffffu, pass)) {
+                    const float mn = __uint_as_float(__reduce_min_sync(0xffffffffu, pass ? tb : 0x7f800000u));
+                    const float nt = fmaf(mn, kSlopMul, tl->mg[c]);
+                    if (nt < thr) {
+                        if (lane == 0) {
+                            atomicMin(&tl->thr[c], __float_as_uint(nt));
+                            atomicMin(p.gthr + rm, __float_as_uint(nt));
+                        }
+                        thr = nt;
+                    }
+                    pass = pass && (tj <= thr);
+                }
+                const bool app = pass || uns;
+                const unsigned ma = __ballot_sync(0xffffffffu, app);
+                if (ma) {
+                    if (app) {
+                        StagedCand sc;
+                        sc.rm = rm;
+                        sc.g = static_cast<int32_t>((static_cast<int64_t>(tl->sgt[warp - 4][k]) * kPairM + row_in_tile) * p.g_stride);
+                        sc.tbits = tb;
+                        wstage[wn + __popc(ma & ((1u << lane) - 1u))] = sc;
+                    }
+                    wn += __popc(ma);
+                    if (wn >= 32) { flush_staged(p, wstage, wn, lane); wn = 0; }
+                }
+            }
+            __syncwarp();
+        };
         int32_t smem_unit = -1;
         while (cur.valid) {
             if (cur.it.u != smem_unit) {
@@ -692,6 +762,135 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const uint32_t trow = tmem_base + static_cast<uint32_t>(acc) * kMaxBN + lane_off;
 
+            if constexpr (AL > 0) {
+                // ===== episode-aligned tile =====
+                const int nep = BN / AL;                              // whole episodes in the tile (padding columns beyond)
+                const int ebeg = nep * grp / EG, eend = nep * (grp + 1) / EG;
+                if (!EOSVR_EXP_ON(p, 1) && eend > ebeg) {
+                    const bool rowok = g < p.G;
+                    const float w = p.w;
+                    uint32_t fv[8];
+                    {
+                        const volatile unsigned int *zp = tl->zeros;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) fv[i] = fill | zp[i];
+                    }
+                    uint32_t v[AL];
+                    tmem_ld_x20(trow + ebeg * AL, v);
+                    tmem_ld_wait_x20(v);
+#pragma unroll 1
+                    for (int e = ebeg; e < eend; ++e) {
+                        const int c0 = e * AL;
+                        float d[AL];
+                        float minx = kBig;
+                        {
+                            const float4 *na4 = reinterpret_cast<const float4 *>(tl->na + c0);
+#pragma unroll
+                            for (int j4 = 0; j4 < AL / 4; ++j4) {
+                                const float4 a = na4[j4];
+                                const float aa[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj) {
+                                    const int j = j4 * 4 + jj;
+                                    const float x = fmaf(__uint_as_float(v[j]), -2.f, aa[jj]);
+                                    minx = fminf(minx, x);
+                                    d[j] = sqrt_approx(fabsf(x));
+                                }
+                            }
+                        }
+                        // the chunk's accumulator columns are in registers: hand them back (fill value of the lane's next
+                        // gallery row) and request the next episode
+                        tmem_st_fill8_x20(trow + c0, fv);
+                        const bool more = e + 1 < eend;
+                        if (more) tmem_ld_x20(trow + c0 + AL, v);
+                        const float4 *th4 = reinterpret_cast<const float4 *>(tl->thr + c0);
+                        bool any0 = false, any1 = false, any2 = false, any3 = false;
+#pragma unroll
+                        for (int j4 = 0; j4 < AL / 4; ++j4) {
+                            const float4 th = th4[j4];
+                            const int j = j4 * 4;
+                            const float t0 = j ? fmaf(w, d[j - 1], fmaf(w, d[j + 1], d[j])) : fmaf(w, d[1], d[0]);
+                            const float t1 = fmaf(w, d[j], fmaf(w, d[j + 2], d[j + 1]));
+                            const float t2 = fmaf(w, d[j + 1], fmaf(w, d[j + 3], d[j + 2]));
+                            const float t3 = (j + 4 < AL) ? fmaf(w, d[j + 2], fmaf(w, d[j + 4], d[j + 3])) : fmaf(w, d[AL - 2], d[AL - 1]);
+                            any0 |= (t0 <= th.x); any1 |= (t1 <= th.y);
+                            any2 |= (t2 <= th.z); any3 |= (t3 <= th.w);
+                        }
+                        const bool guard = minx < xfloor;
+                        const bool hit = (any0 || any1) || (any2 || any3) || guard;
+                        if (__any_sync(0xffffffffu, hit) && !EOSVR_EXP_ON(p, 32)) {
+                            // ---- some lane is below a threshold (or inside the cancellation guard): the taps once more
+                            //      (same arithmetic, same bits), now with a per-lane mask of the columns concerned ----
+                            float t[AL];
+                            unsigned m = 0;
+#pragma unroll
+                            for (int j4 = 0; j4 < AL / 4; ++j4) {
+                                const float4 th = th4[j4];
+                                const float tt[4] = {th.x, th.y, th.z, th.w};
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj) {
+                                    const int j = j4 * 4 + jj;
+                                    float tj = d[j];
+                                    if (j + 1 < AL) tj = fmaf(w, d[j + 1], tj);
+                                    if (j > 0) tj = fmaf(w, d[j - 1], tj);
+                                    t[j] = tj;
+                                    m |= (tj <= tt[jj] ? 1u : 0u) << j;
+                                }
+                            }
+                            if (p.seed_mode) {
+                                // seed pass: thresholds only (see the generic epilogue)
+                                const bool okl = rowok && !guard;
+                                unsigned mine = 0x7f800000u;
+#pragma unroll
+                                for (int j = 0; j < AL; ++j) {
+                                    const unsigned mn = __reduce_min_sync(0xffffffffu, okl ? __float_as_uint(t[j]) : 0x7f800000u);
+                                    if (lane == j) mine = mn;
+                                }
+                                if (lane < AL && mine != 0x7f800000u) {
+                                    const int c = c0 + lane;
+                                    const int32_t rm = tl->row[c];
+                                    if (rm >= 0) {
+                                        const float nt = fmaf(__uint_as_float(mine), kSlopMul, tl->mg[c]);
+                                        if (nt < __uint_as_float(*reinterpret_cast<volatile unsigned int *>(&tl->thr[c]))) {
+                                            atomicMin(&tl->thr[c], __float_as_uint(nt));
+                                            atomicMin(p.gthr + rm, __float_as_uint(nt));
+                                        }
+                                    }
+                                }
+                            } else {
+                                // Inside the cancellation guard (a tap with x~ < 65 E2: the margin in mg[] assumes larger
+                                // taps) nothing is screened: the column of the small tap and its two neighbours are handed
+                                // to the exact re-rank unconditionally ("unsafe").  Only near-duplicates of a probe row
+                                // get here.
+                                unsigned um = 0;
+                                if (guard) {
+                                    unsigned sm = 0;
+#pragma unroll
+                                    for (int j = 0; j < AL; ++j) sm |= (d[j] < dfloor ? 1u : 0u) << j;
+                                    um = (sm | (sm << 1) | (sm >> 1)) & ((1u << AL) - 1u);
+                                }
+                                if (!rowok) { m = 0; um = 0; }
+                                m &= ~um;
+                                unsigned cm = __reduce_or_sync(0xffffffffu, m | um);
+#pragma unroll 1
+                                while (cm) {
+                                    const int jc = __ffs(cm) - 1;                  // warp-uniform
+                                    cm &= cm - 1;
+                                    if (ns == kStashCols) { drain_stash(); ns = 0; }
+                                    const float tj = pick20(t, jc);
+                                    const uint32_t val = ((um >> jc) & 1u) ? kCandUnsafe
+                                                       : (((m >> jc) & 1u) ? __float_as_uint(tj) : 0x7f800000u);
+                                    tl->sval[warp - 4][ns][lane] = val;
+                                    if (lane == 0) { tl->scol[warp - 4][ns] = c0 + jc; tl->sgt[warp - 4][ns] = cur.gt; }
+                                    ++ns;
+                                }
+                            }
+                        }
+                        if (more) tmem_ld_wait_x20(v);
+                    }
+                    tmem_st_wait();
+                }
+            } else
             if (!EOSVR_EXP_ON(p, 1) && cend > cbeg) {
                 const bool rowok = g < p.G;
                 // eight registers holding the fill value: the source of the refill stores (a tcgen05.st wants consecutive
@@ -901,6 +1100,9 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
             if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
             if (pend_thr != 0xFFFFFFFFu) atomicMin(&tl->thr[te], pend_thr);
+            if constexpr (AL > 0) {
+                if (ns) { drain_stash(); ns = 0; }       // before the unit (and with it the per-column arrays) can change
+            }
             if (prof) e_busy += clock64() - t_e0;
             cursor_next(p, cur, npairs);
             cursor_next(p, ahead, npairs);
@@ -1449,7 +1651,7 @@ int launch_merge(const uint64_t *gathered, int32_t nshards, int64_t P, uint64_t 
 // 16 (cycle accounting of the screening kernel) and 64 (phase timing of the re-rank).  The result-destroying
 // timing modes (EOSVR_EXP bits 1, 2, 4, 32) exist only in builds with -DEOSVR_EXPERIMENTS (tools/exp_perf.sh).
 struct Tunables {
-    int order, tpu, seed, ew, issuers, exp;
+    int order, tpu, seed, ew, issuers, exp, aligned;
 };
 static int env_int(const char *name, int dflt)
 {
@@ -1466,6 +1668,7 @@ const Tunables &tunables()
         v.ew = env_int("EOSVR_EW", 0);
         v.issuers = env_int("EOSVR_ISSUERS", 0);
         v.exp = env_int("EOSVR_EXP", 0);
+        v.aligned = env_int("EOSVR_ALIGNED", 1);       // 0: never use the episode-aligned epilogue
 #ifndef EOSVR_EXPERIMENTS
         v.exp &= (16 | 64);
 #endif
@@ -1489,10 +1692,10 @@ static int device_state(DeviceState **out)
     return EOSVR_OK;
 }
 
-template <int EW, bool DIAG>
+template <int EW, bool DIAG, int AL>
 static int launch_screen_t(DeviceState *ds, const CUtensorMap &tmA, const CUtensorMap &tmB, const ScreenParams &sp, cudaStream_t st)
 {
-    auto kern = k_match_screen<EW, DIAG>;
+    auto kern = k_match_screen<EW, DIAG, AL>;
     constexpr size_t smem = screen_smem<EW>();
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1503,7 +1706,7 @@ static int launch_screen_t(DeviceState *ds, const CUtensorMap &tmA, const CUtens
     cfg.blockDim = dim3(screen_threads(EW), 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    int &maxcl = ds->max_clusters[DIAG ? 1 : 0][EW == 16 ? 1 : 0];
+    int &maxcl = ds->max_clusters[AL > 0 ? 2 : (DIAG ? 1 : 0)][EW == 16 ? 1 : 0];
     {
         std::lock_guard<std::mutex> lock(g_dev_mu);
         if (maxcl == 0) {
@@ -1536,7 +1739,7 @@ struct ScreenView {          // the screening copy of the gallery a launch reads
 };
 
 static int launch_screen(DeviceState *ds, const eosvr_gallery *g, const ScreenView &sv, eosvr_workspace *ws, const MatchPlan &pl,
-                         bool seed, const CUtensorMap &tmB, int64_t gallery_tiles, int64_t g_stride, int64_t P,
+                         bool seed, const CUtensorMap &tmB, int64_t gallery_tiles, int64_t g_stride, int64_t P, float w,
                          cudaStream_t st)
 {
     const Tunables &tn = tunables();
@@ -1567,6 +1770,7 @@ static int launch_screen(DeviceState *ds, const eosvr_gallery *g, const ScreenVi
     }
     sp.g_stride = g_stride; sp.seed_mode = seed_mode;
     sp.issuers = ds->issuers > 0 ? ds->issuers : kIssuers;
+    sp.rpe = pl.rpe; sp.w = w;
     sp.na = ws->na; sp.wl = ws->wl; sp.wr = ws->wr; sp.epsd = ws->epsd; sp.rowmap = ws->rowmap;
     sp.gthr = ws->gthr; sp.cand = ws->cand; sp.rowcnt = ws->rowcnt; sp.cand_cap = static_cast<int32_t>(ws->cand_cap);
     sp.ovf = ws->ovf; sp.ovf_cap = static_cast<int32_t>(ws->ovf_cap);
@@ -1580,8 +1784,11 @@ static int launch_screen(DeviceState *ds, const eosvr_gallery *g, const ScreenVi
     const bool diag = sp.dbg != nullptr || (tn.exp & 16) != 0;
     const CUtensorMap &tmA = seed ? *sv.tmapSeed : *sv.tmapA;
     int rc;
-    if (ew == 16) rc = diag ? launch_screen_t<16, true>(ds, tmA, tmB, sp, st) : launch_screen_t<16, false>(ds, tmA, tmB, sp, st);
-    else rc = diag ? launch_screen_t<8, true>(ds, tmA, tmB, sp, st) : launch_screen_t<8, false>(ds, tmA, tmB, sp, st);
+    // episode-aligned epilogue: whole episodes of kAlign rows per tile, no halo, tap weight uniform inside an episode
+    const bool aligned = tn.aligned != 0 && ew == 16 && !diag && pl.rpe == kAlign && pl.halo == 0 && pl.R % kAlign == 0 && P % kAlign == 0;
+    if (aligned) rc = launch_screen_t<16, false, kAlign>(ds, tmA, tmB, sp, st);
+    else if (ew == 16) rc = diag ? launch_screen_t<16, true, 0>(ds, tmA, tmB, sp, st) : launch_screen_t<16, false, 0>(ds, tmA, tmB, sp, st);
+    else rc = diag ? launch_screen_t<8, true, 0>(ds, tmA, tmB, sp, st) : launch_screen_t<8, false, 0>(ds, tmA, tmB, sp, st);
     if (rc) return rc;
     { int trc = timing_end(ws, kid, st); if (trc) return trc; }
     EOSVR_COUNT_LAUNCH(1);
@@ -1664,10 +1871,10 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
         // seed pass over a strided sample of the gallery: tightens every probe row's threshold before the
         // full pass so that concurrent CTAs do not flood the candidate lists (EOSVR_SEED=0 skips it: experiments)
         if (tn.seed && g->seed_tiles > 0 && GT > g->seed_tiles) {
-            rc = launch_screen(ds, g, sv, ws, pl, true, tmB, tn.seed == 1 ? g->seed_tiles : 1, g->seed_stride, P, st);
+            rc = launch_screen(ds, g, sv, ws, pl, true, tmB, tn.seed == 1 ? g->seed_tiles : 1, g->seed_stride, P, lam1 / lam2, st);
             if (rc) return rc;
         }
-        rc = launch_screen(ds, g, sv, ws, pl, false, tmB, GT, 1, P, st);
+        rc = launch_screen(ds, g, sv, ws, pl, false, tmB, GT, 1, P, lam1 / lam2, st);
         if (rc) return rc;
         ws->last_tiles = pl.NT * GT;
 

@@ -196,6 +196,37 @@ __device__ __forceinline__ void tmem_st_fill8_x16(uint32_t taddr, const uint32_t
         ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
         : "memory");
 }
+// 20 consecutive columns (one 5-way x 4-segment episode of the screening epilogue): an x16 and an x4 access.
+__device__ __forceinline__ void tmem_ld_x20(uint32_t taddr, uint32_t (&v)[20])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%20];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%16, %17, %18, %19}, [%20 + 16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_x20(uint32_t (&v)[20])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_fill8_x20(uint32_t taddr, const uint32_t (&v)[8])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n\t"
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0 + 8], {%1, %2, %3, %4, %5, %6, %7, %8};\n\t"
+        "tcgen05.st.sync.aligned.32x32b.x4.b32 [%0 + 16], {%1, %2, %3, %4};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait()
 {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");

@@ -1,5 +1,5 @@
 """Results do not depend on how the screening kernel walks its work units (gallery chunk x probe tile), on the number
-of epilogue warps, or on the number of MMA issuer warps: each setting runs in a fresh process (the knobs are read once
+of epilogue warps, on the number of MMA issuer warps, or on whether the episode-aligned epilogue (20-row episodes) runs: each setting runs in a fresh process (the knobs are read once
 per process) and must reproduce the oracle bit for bit."""
 import os
 import subprocess
@@ -31,7 +31,7 @@ print("OK")
 
 @pytest.mark.parametrize("env", [{"EOSVR_ORDER": "0"}, {"EOSVR_ORDER": "1"}, {"EOSVR_ORDER": "2"}, {"EOSVR_EW": "8"},
                                  {"EOSVR_EW": "16"}, {"EOSVR_ISSUERS": "1"}, {"EOSVR_SEED": "0"}, {"EOSVR_TPU": "3"},
-                                 {"EOSVR_EXP": "63"}])
+                                 {"EOSVR_EXP": "63"}, {"EOSVR_ALIGNED": "0"}])
 def test_knobs_do_not_change_results(env):
     """(EOSVR_EXP=63 asks for the result-destroying timing modes: the shipped library must ignore them.)"""
     e = dict(os.environ)

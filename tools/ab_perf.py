@@ -1,5 +1,5 @@
 """A/B timing of two builds of the library in ONE process-per-build, interleaved (box-to-box variation on the pool is
-+-10 %, so builds are only compared inside one gpurun call):  python tools/ab_perf.py libA.so libB.so [rounds]"""
++-10 %, so builds are only compared inside one gpurun call):  python tools/ab_perf.py libA.so[:ENV=VAL] libB.so[:ENV=VAL] [rounds]"""
 import os
 import subprocess
 import sys
@@ -51,7 +51,12 @@ print("RESULT " + json.dumps(out))
 
 
 def run(lib):
-    env = dict(os.environ, EOSVR_LIB_PATH=os.path.abspath(lib))
+    """lib: path[:ENV=VAL[:ENV=VAL...]] -- the same build can be compared under different knobs"""
+    parts = lib.split(":")
+    env = dict(os.environ, EOSVR_LIB_PATH=os.path.abspath(parts[0]))
+    for kv in parts[1:]:
+        k, v = kv.split("=", 1)
+        env[k] = v
     r = subprocess.run([sys.executable, "-c", CHILD % (ROOT, os.path.join(ROOT, "oracle"))], capture_output=True, text=True, env=env, timeout=900)
     for line in r.stdout.splitlines():
         if line.startswith("RESULT "):
