@@ -405,6 +405,8 @@ def run_workload(cfg, args, dev, world, rank, group, dist, steps, warmup, oracle
     pipe = ev.EpisodePipeline(cache, cfg["n_way"], cfg["k_shot"], cfg["S"], E, group=group, shards=shards, cand_capacity=cand)
     torch.cuda.synchronize()
     m = measure(cfg, pipe, batches, dev, world, steps, warmup, dist, e2e=e2e)
+    if args.profile:             # profiling run: only the steps (no parity kernels in the launch list)
+        return m
 
     # ---- in-run parity -------------------------------------------------------------------------------------------
     parity = {}
@@ -535,10 +537,10 @@ def run_ours(args):
     if world == 1:
         m3 = run_workload(CFG3, args, dev, 1, 0, None, dist, args.steps, args.warmup, oracle_ref=oracle_ref, e2e=not args.profile)
         clocks = sampler.stop() if sampler else None
-        line = line_of(CFG3, m3, 1, args.steps, args.warmup, peaks, peak_src)
         if args.profile:
             print(json.dumps({"profile_run": True, "ms_per_step": m3["ms_step"], "steps": args.steps}), flush=True)
             return
+        line = line_of(CFG3, m3, 1, args.steps, args.warmup, peaks, peak_src)
         line["cpu_baseline"] = cpu
         line["clocks"] = clocks
         del m3

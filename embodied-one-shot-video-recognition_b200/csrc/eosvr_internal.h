@@ -19,11 +19,13 @@ constexpr int kStages = 6;        // TMA -> MMA smem ring (kSub x (16 KiB A + 16
 constexpr int kIssuers = 3;       // MMA issuer warps 1..3 of the pair's leader; stage s belongs to issuer s % kIssuers.
                                   // A tcgen05.commit blocks its thread for ~600 cycles and a UTCHMMA for ~70
                                   // (tools/bench_micro/mma_rate.cu): one thread sustains only ~1/3 of the MMA rate.
-constexpr int kAccStages = 2;     // TMEM accumulator double buffer (2 x 256 columns)
+constexpr int kMaxAccStages = 3;  // TMEM accumulators: 2 x 256 columns, or 3 x 160 when the probe tile has <= 160 columns
 constexpr bool kZeroAcc = true;   // every MMA accumulates; the epilogue zeroes the accumulator behind itself.  false: the
                                   // tile's first stage overwrites and the other issuers wait for its completion (a
                                   // ~600-cycle bubble per tile)
 constexpr int kTmemCols = 512;
+constexpr int kBN3 = 160;         // widest probe tile that leaves room for three accumulator stages (3 x 160 <= 512 columns)
+constexpr int kAlign = 20;        // chunk width of the episode-aligned epilogue: 5-way x 4 segments (the metric's episode)
 // Epilogue warps (template parameter EW of k_match_screen): warps 4 .. 4+EW-1; warp % 4 = TMEM lane quadrant, (warp - 4) / 4 =
 // column group.  8 warps keep up with the tensor pipe when D >= 1024; for shorter rows the epilogue is the critical path and 16
 // warps run it (tools/bench_micro/epi_rate.cu: 3538 -> 2793 cycles per 128 x 240 tile against 3840 cycles of MMA at D = 512).
@@ -179,7 +181,7 @@ MatchPlan make_plan(int64_t P, int32_t rpe);
 // Per-device launch state (the library may drive several GPUs from one process); guarded by one mutex.
 struct DeviceState {
     int num_sms = 0;
-    int max_clusters[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // [plain / DIAG / aligned][EW == 16]: co-resident CTA pairs of k_match_screen
+    int max_clusters[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};   // [plain / DIAG / aligned / aligned DIAG][EW == 16]: co-resident CTA pairs of k_match_screen
     bool rr_attr = false;
     int issuers = 0;                              // MMA issuer warps in use; 0 = not decided yet (self-check pending)
 };

@@ -153,13 +153,24 @@ int launch_gallery_prep_cos(const eosvr_gallery *g, eosvr_screen_copy *c, cudaSt
 // no halo is needed; otherwise each tile carries one halo column on each side so the taps of its
 // first/last emitted row see their neighbours.
 // -------------------------------------------------------------------------------------------
+static bool plan_bn3_enabled()
+{
+    static const bool on = [] { const char *e = getenv("EOSVR_BN3"); return e ? atoi(e) != 0 : false; }();   // experiments: 1 = 160-column tiles, three accumulators
+    return on;
+}
+
 MatchPlan make_plan(int64_t P, int32_t rpe)
 {
     MatchPlan pl;
     pl.P = P;
     pl.rpe = rpe;
     if (rpe <= kMaxBN) {
-        int64_t k = kMaxBN / rpe;
+        // Experiment (EOSVR_BN3=1, off by default): 20-row episodes in tiles of 8 episodes = 160 columns, so that THREE
+        // accumulators fit the 512 TMEM columns.  Measured 10-20 % SLOWER than 240-column tiles with two accumulators
+        // (profiles/r02_ab_three_accumulators_rejected.txt): the single TMA producer thread and the per-tile fixed cost
+        // of the epilogue outweigh the deeper accumulator ring.
+        const int cap = (rpe == kAlign && plan_bn3_enabled()) ? kBN3 : kMaxBN;
+        int64_t k = cap / rpe;
         pl.R = static_cast<int32_t>(k * rpe);
         pl.halo = 0;
     } else {
@@ -299,6 +310,8 @@ struct ScreenParams {
     int64_t g_stride;       // gallery row stride (1; > 1 in the seed pass)
     int32_t seed_mode;      // 1: only tighten the thresholds, append nothing
     int32_t issuers;        // MMA issuer warps in use: kIssuers, or 1 (the documented single-issuer ordering)
+    int32_t acc_stages;     // TMEM accumulator stages: 3 when the tile has <= 160 columns, else 2
+    int32_t acc_stride;     // TMEM columns between accumulator stages
     int32_t rpe;            // probe rows per episode (the episode-aligned epilogue needs rpe == its chunk width)
     float w;                // tap weight lam1 / lam2 towards a neighbour of the same episode
     const float *na, *wl, *wr, *epsd;
@@ -332,7 +345,6 @@ struct StagedCand {
 };
 constexpr int kWarpStage = 64;
 constexpr int kStashCols = 6;      // parked columns per epilogue warp (a full stash is worked off on the spot)
-constexpr int kAlign = 20;         // chunk width of the episode-aligned epilogue: 5-way x 4 segments (the metric's episode)
 
 template <int EW>
 struct __align__(16) ScreenSmemTail {
@@ -345,8 +357,8 @@ struct __align__(16) ScreenSmemTail {
     uint64_t full[kStages];           // stage s is always consumed by issuer s % issuers: a parity wait is only safe
                                       // on a barrier whose every phase the waiter observes
     uint64_t empty[kStages];
-    uint64_t tfull[kAccStages];
-    uint64_t tempty[kAccStages];
+    uint64_t tfull[kMaxAccStages];
+    uint64_t tempty[kMaxAccStages];
     uint32_t tmem_base;
     uint32_t zeros[8];                // zeros the compiler cannot see through (refill-store source registers)
     // candidate staging: every epilogue warp parks its candidates in shared memory and hands them to the
@@ -522,7 +534,7 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
         for (int s = 0; s < kStages; ++s) { mbar_init(&tl->full[s], 1); mbar_init(&tl->empty[s], 1); }
-        for (int s = 0; s < kAccStages; ++s) {
+        for (int s = 0; s < kMaxAccStages; ++s) {
             mbar_init(&tl->tfull[s], p.issuers);         // one commit per MMA issuer warp
             mbar_init(&tl->tempty[s], 2 * EW);
         }
@@ -589,7 +601,9 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp >= 1 && warp <= p.issuers && rank == 0) {
         // ===== MMA issuers: p.issuers warps of the pair's leader drive the tensor cores of both SMs, taking the
-        //       pipeline stages round-robin (stage s -> issuer s % issuers) into the same accumulator.  Every MMA
+        //       pipeline stages round-robin (stage s -> issuer s % issuers) into the same accumulator.  (One commit per
+        //       PAIR of stages -- fewer of the ~900-cycle commits per issuing thread -- measured 1-2 % slower on every
+        //       shape, profiles/r02_ab_three_accumulators_rejected.txt.)  Every MMA
         //       accumulates onto the values the epilogue left behind, so the issuers need no ordering among
         //       themselves.  Every issuer observes every phase of tempty. =====
         if (kRepartition) reg_release<kLightRegs>();
@@ -607,7 +621,7 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (prof) { const long long t0 = clock64(); mbar_wait(&tl->tempty[acc], accphase); w_acc += clock64() - t0; }
                 else mbar_wait(&tl->tempty[acc], accphase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * kMaxBN;
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.acc_stride);
                 for (int ks = 0; ks < KS; ++ks, ++seq) {
                     if (static_cast<int>(seq % nis) != w) continue;
                     const int stage = static_cast<int>(seq % kStages);
@@ -633,7 +647,7 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 if (lane == 0) mma_commit_2sm(&tl->tfull[acc], pair_mask);   // this warp's share of the tile is done
                 __syncwarp();
-                if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
+                if (++acc == p.acc_stages) { acc = 0; accphase ^= 1; }
             }
         }
         if (prof && lane == 0 && w == 0) atomicAdd(&p.ctr->cyc_mma_wait_acc, w_acc);
@@ -655,7 +669,6 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int64_t row_in_tile = static_cast<int64_t>(rank) * kBM + q * 32 + lane;
         int acc = 0; uint32_t accphase = 0;
         const uint32_t tempty_leader0 = mapa(smem_u32(&tl->tempty[0]), 0);
-        const uint32_t tempty_leader1 = mapa(smem_u32(&tl->tempty[1]), 0);
         unsigned long long e_busy = 0, e_wait = 0, e_pre = 0, e_loop = 0;
 
         // accumulator fill value for tile c: -|b|^2/2 of this lane's gallery row (0 when there is no such tile)
@@ -667,22 +680,29 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         cur.u = pair;
         cursor_seek(p, cur, npairs);
         TileCursor ahead = cur;
-        cursor_next(p, ahead, npairs);
         {
-            // initial fill: accumulator 0 for the pair's first tile, accumulator 1 for its second; every column group
-            // takes its share of the 2 x 256 columns and every warp then reports both accumulators (a barrier
-            // completes only when all 2*EW warps of the pair have arrived)
-            const uint32_t f0 = fill_bits(cur), f1 = fill_bits(ahead);
-            constexpr int kShare = kAccStages * kMaxBN / EG;
+            // initial fill: accumulator s for the pair's tile s; every column group takes its share of the 512 columns
+            // and every warp then reports all accumulators (a barrier completes only when all 2*EW warps of the pair
+            // have arrived)
+            const uint32_t f0 = fill_bits(ahead);
+            cursor_next(p, ahead, npairs);
+            const uint32_t f1 = fill_bits(ahead);
+            cursor_next(p, ahead, npairs);
+            uint32_t f2 = 0u;
+            if (p.acc_stages > 2) { f2 = fill_bits(ahead); cursor_next(p, ahead, npairs); }
+            constexpr int kShare = kTmemCols / EG;
 #pragma unroll 1
-            for (int c = grp * kShare; c < (grp + 1) * kShare; c += kChunk)
-                tmem_st_fill_x16(tmem_base + lane_off + c, c < kMaxBN ? f0 : f1);
+            for (int c = grp * kShare; c < (grp + 1) * kShare; c += kChunk) {
+                const int sidx = c / p.acc_stride;
+                tmem_st_fill_x16(tmem_base + lane_off + c, sidx == 0 ? f0 : (sidx == 1 ? f1 : f2));
+            }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { mbar_arrive_cluster(tempty_leader0); mbar_arrive_cluster(tempty_leader1); }
+            if (lane == 0)
+                for (int sidx = 0; sidx < p.acc_stages; ++sidx) mbar_arrive_cluster(tempty_leader0 + sidx * 8u);
         }
-        cursor_next(p, ahead, npairs);                    // from here on: the next tile to use the accumulator `cur` is in
+        // from here on `ahead` is the next tile to use the accumulator `cur` is in (acc_stages tiles later)
         StagedCand *wstage = tl->stage[warp - 4];
         int wn = 0;                                       // candidates parked by this warp (warp-uniform)
         int ns = 0;                                       // columns parked by the aligned epilogue (warp-uniform)
@@ -760,7 +780,8 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (prof) { const long long t0 = clock64(); mbar_wait(&tl->tfull[acc], accphase); t_e0 = clock64(); e_wait += t_e0 - t0; }
             else mbar_wait(&tl->tfull[acc], accphase);
             tc_fence_after();
-            const uint32_t trow = tmem_base + static_cast<uint32_t>(acc) * kMaxBN + lane_off;
+            const uint32_t trow = tmem_base + static_cast<uint32_t>(acc * p.acc_stride) + lane_off;
+            bool released = false;                        // aligned epilogue: the accumulator was handed back inside the tile
 
             if constexpr (AL > 0) {
                 // ===== episode-aligned tile =====
@@ -778,6 +799,8 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint32_t v[AL];
                     tmem_ld_x20(trow + ebeg * AL, v);
                     tmem_ld_wait_x20(v);
+                    long long t_e1 = 0;
+                    if (prof) { t_e1 = clock64(); e_pre += t_e1 - t_e0; }
 #pragma unroll 1
                     for (int e = ebeg; e < eend; ++e) {
                         const int c0 = e * AL;
@@ -802,7 +825,18 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         // gallery row) and request the next episode
                         tmem_st_fill8_x20(trow + c0, fv);
                         const bool more = e + 1 < eend;
-                        if (more) tmem_ld_x20(trow + c0 + AL, v);
+                        if (more) {
+                            tmem_ld_x20(trow + c0 + AL, v);
+                        } else {
+                            // The warp's last TMEM read of the tile is in registers and its columns are refilled: the
+                            // accumulator goes back to the MMA issuers NOW; the taps, the compare and the candidate
+                            // handling of this last episode run while the tensor pipe is already on the tile after next.
+                            tmem_st_wait();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(tempty_leader0 + static_cast<uint32_t>(acc) * 8u);
+                            released = true;
+                        }
                         const float4 *th4 = reinterpret_cast<const float4 *>(tl->thr + c0);
                         bool any0 = false, any1 = false, any2 = false, any3 = false;
 #pragma unroll
@@ -888,7 +922,7 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                         if (more) tmem_ld_wait_x20(v);
                     }
-                    tmem_st_wait();
+                    if (prof) e_loop += clock64() - t_e1;
                 }
             } else
             if (!EOSVR_EXP_ON(p, 1) && cend > cbeg) {
@@ -1095,10 +1129,12 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else if (!EOSVR_EXP_ON(p, 256)) {
                 named_bar_sync(2 + q, 32 * EG);           // (a column group is empty when the tile has fewer chunks than groups)
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
-            if (++acc == kAccStages) { acc = 0; accphase ^= 1; }
+            if (!released) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_leader0 + static_cast<uint32_t>(acc) * 8u);
+            }
+            if (++acc == p.acc_stages) { acc = 0; accphase ^= 1; }
             if (pend_thr != 0xFFFFFFFFu) atomicMin(&tl->thr[te], pend_thr);
             if constexpr (AL > 0) {
                 if (ns) { drain_stash(); ns = 0; }       // before the unit (and with it the per-column arrays) can change
@@ -1706,7 +1742,7 @@ static int launch_screen_t(DeviceState *ds, const CUtensorMap &tmA, const CUtens
     cfg.blockDim = dim3(screen_threads(EW), 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    int &maxcl = ds->max_clusters[AL > 0 ? 2 : (DIAG ? 1 : 0)][EW == 16 ? 1 : 0];
+    int &maxcl = ds->max_clusters[(AL > 0 ? 2 : 0) + (DIAG ? 1 : 0)][EW == 16 ? 1 : 0];
     {
         std::lock_guard<std::mutex> lock(g_dev_mu);
         if (maxcl == 0) {
@@ -1771,6 +1807,8 @@ static int launch_screen(DeviceState *ds, const eosvr_gallery *g, const ScreenVi
     sp.g_stride = g_stride; sp.seed_mode = seed_mode;
     sp.issuers = ds->issuers > 0 ? ds->issuers : kIssuers;
     sp.rpe = pl.rpe; sp.w = w;
+    sp.acc_stages = pl.BN <= kBN3 ? 3 : 2;
+    sp.acc_stride = pl.BN <= kBN3 ? kBN3 : kMaxBN;
     sp.na = ws->na; sp.wl = ws->wl; sp.wr = ws->wr; sp.epsd = ws->epsd; sp.rowmap = ws->rowmap;
     sp.gthr = ws->gthr; sp.cand = ws->cand; sp.rowcnt = ws->rowcnt; sp.cand_cap = static_cast<int32_t>(ws->cand_cap);
     sp.ovf = ws->ovf; sp.ovf_cap = static_cast<int32_t>(ws->ovf_cap);
@@ -1785,8 +1823,10 @@ static int launch_screen(DeviceState *ds, const eosvr_gallery *g, const ScreenVi
     const CUtensorMap &tmA = seed ? *sv.tmapSeed : *sv.tmapA;
     int rc;
     // episode-aligned epilogue: whole episodes of kAlign rows per tile, no halo, tap weight uniform inside an episode
-    const bool aligned = tn.aligned != 0 && ew == 16 && !diag && pl.rpe == kAlign && pl.halo == 0 && pl.R % kAlign == 0 && P % kAlign == 0;
-    if (aligned) rc = launch_screen_t<16, false, kAlign>(ds, tmA, tmB, sp, st);
+    // (the screening-value dump of the tests runs the generic epilogue; cycle accounting exists for both)
+    const bool aligned = tn.aligned != 0 && ew == 16 && sp.dbg == nullptr && pl.rpe == kAlign && pl.halo == 0 && pl.R % kAlign == 0 &&
+                         P % kAlign == 0;
+    if (aligned) rc = diag ? launch_screen_t<16, true, kAlign>(ds, tmA, tmB, sp, st) : launch_screen_t<16, false, kAlign>(ds, tmA, tmB, sp, st);
     else if (ew == 16) rc = diag ? launch_screen_t<16, true, 0>(ds, tmA, tmB, sp, st) : launch_screen_t<16, false, 0>(ds, tmA, tmB, sp, st);
     else rc = diag ? launch_screen_t<8, true, 0>(ds, tmA, tmB, sp, st) : launch_screen_t<8, false, 0>(ds, tmA, tmB, sp, st);
     if (rc) return rc;

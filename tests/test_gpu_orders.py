@@ -31,7 +31,7 @@ print("OK")
 
 @pytest.mark.parametrize("env", [{"EOSVR_ORDER": "0"}, {"EOSVR_ORDER": "1"}, {"EOSVR_ORDER": "2"}, {"EOSVR_EW": "8"},
                                  {"EOSVR_EW": "16"}, {"EOSVR_ISSUERS": "1"}, {"EOSVR_SEED": "0"}, {"EOSVR_TPU": "3"},
-                                 {"EOSVR_EXP": "63"}, {"EOSVR_ALIGNED": "0"}])
+                                 {"EOSVR_EXP": "63"}, {"EOSVR_ALIGNED": "0"}, {"EOSVR_BN3": "1"}, {"EOSVR_BN3": "1", "EOSVR_ALIGNED": "0"}])
 def test_knobs_do_not_change_results(env):
     """(EOSVR_EXP=63 asks for the result-destroying timing modes: the shipped library must ignore them.)"""
     e = dict(os.environ)

@@ -66,8 +66,8 @@ def run(lib):
 
 
 if __name__ == "__main__":
-    libs = sys.argv[1:3]
-    rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    libs = [a for a in sys.argv[1:] if not a.isdigit()]
+    rounds = next((int(a) for a in sys.argv[1:] if a.isdigit()), 2)
     res = {l: [] for l in libs}
     for _ in range(rounds):
         for l in libs:
