@@ -58,7 +58,15 @@ def test_temporal_golden(golden_dir):
         np.testing.assert_allclose(cd, d64, rtol=1e-13)
         assert np.array_equal(cd.astype(np.float32), d64.astype(np.float32))
         assert np.array_equal(O.lib_temporal_smooth(d64), t)
-        assert np.array_equal(O.c_temporal_smooth(d64), t)               # FMA chain == conv2d, bit-exact
+        assert np.array_equal(O.c_temporal_smooth(d64), t)               # FMA chain == the recorded conv2d, bit-exact
+        # This host's own conv2d: bit-equal where oneDNN picks the fused kernel (the recording host, the GPU
+        # boxes); on a host whose kernel rounds the last product separately it is 1-2 ulp away and the
+        # lib_* functions return the pinned chain instead (oracle.conv2d_kind()).
+        raw = O.lib_temporal_smooth(d64, pinned=False)
+        if O.conv2d_kind() == "fma-chain":
+            assert np.array_equal(raw, t)
+        else:
+            np.testing.assert_allclose(raw, t, rtol=2.4e-7)
         idx, val = O.c_match(A, B)
         assert np.array_equal(idx, np.argsort(t, axis=1, kind="stable")[:, 0])
         assert np.array_equal(val, t[np.arange(t.shape[0]), idx])
