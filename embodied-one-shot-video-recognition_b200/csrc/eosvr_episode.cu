@@ -40,6 +40,34 @@ static void *stream_scratch(cudaStream_t st, size_t bytes)
     return slot.first;
 }
 
+
+// classifier.py:63 is scipy's cdist(query, prototypes) on float32 rows: promoted to float64 and, per pair, ONE
+// sequential pass  s = 0; for k: e = q[k] - p[k]; s = s + e*e  (product rounded, then the sum; no FMA), sqrt(s),
+// then the float32 cast of :66.  A float64 sum in another order flips the float32 rounding of about one distance in
+// 5 million, so the chain is not parallelised: ONE THREAD evaluates one (query, prototype) pair, and the prototypes
+// (float32, numpy's order) go through a scratch array in global memory (read back with ld.global.cg: with a split
+// feature axis other blocks wrote them).
+__device__ __forceinline__ void seq1(double &s, float q, float p)
+{
+    const double e = __dsub_rn(static_cast<double>(q), static_cast<double>(p));
+    s = __dadd_rn(s, __dmul_rn(e, e));
+}
+__device__ __forceinline__ float seq_dist(const float *__restrict__ q, const float *proto, int D)
+{
+    double s = 0.0;
+    if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(proto)) & 15) == 0) {
+        const float4 *q4 = reinterpret_cast<const float4 *>(q), *p4 = reinterpret_cast<const float4 *>(proto);
+#pragma unroll 2
+        for (int k = 0; k < (D >> 2); ++k) {
+            const float4 a = q4[k], b = __ldcg(p4 + k);
+            seq1(s, a.x, b.x); seq1(s, a.y, b.y); seq1(s, a.z, b.z); seq1(s, a.w, b.w);
+        }
+    } else {
+        for (int k = 0; k < D; ++k) seq1(s, q[k], __ldcg(proto + k));
+    }
+    return static_cast<float>(sqrt(s));
+}
+
 // grid: (E*n, 1+S); block: 128 threads striding D.
 // out[e, i*(1+S) + j, :]:  j = 0 "original" row, j = 1+s the clip with segment s replaced.
 __global__ void k_splice(const float *__restrict__ probes, const float *__restrict__ wrows,
@@ -89,20 +117,20 @@ constexpr int kMaxQ = 8;
 
 __global__ void __launch_bounds__(kProtoThreads)
 k_proto_score(const float *__restrict__ sup, const float *__restrict__ sup_y, const float *__restrict__ query,
-              int R, int Q, int D, int max_proto, float *__restrict__ dist, float *__restrict__ prob,
-              int64_t *__restrict__ pred, int32_t *__restrict__ nproto_out)
+              int R, int Q, int D, int max_proto, float *protos, int pstride, float *__restrict__ dist,
+              float *__restrict__ prob, int64_t *__restrict__ pred, int32_t *__restrict__ nproto_out)
 {
     __shared__ int16_t s_cls[kMaxRows];
     __shared__ float s_pid[kMaxProto];
     __shared__ int s_np;
-    __shared__ double s_red[kProtoThreads / 32][kMaxQ];
     __shared__ float s_d[kMaxQ][kMaxProto];
 
     const int64_t e = blockIdx.x;
     const float *S0 = sup + e * R * D;
     const float *Y = sup_y + e * R;
     const float *Qp = query + e * Q * D;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *PR = protos + e * pstride * D;              // this episode's prototypes [np, D]
+    const int tid = threadIdx.x;
 
     if (tid == 0) {
         // classifier.py:21-29: classes keyed by label value, first-appearance order
@@ -120,9 +148,6 @@ k_proto_score(const float *__restrict__ sup, const float *__restrict__ sup_y, co
     const int np = s_np;
 
     for (int c = 0; c < np; ++c) {
-        double part[kMaxQ];
-#pragma unroll
-        for (int q = 0; q < kMaxQ; ++q) part[q] = 0.0;
         for (int k = tid; k < D; k += kProtoThreads) {
             // classifier.py:34-35: float32 mean over the class rows, sequential, true division
             float acc = 0.f; int cnt = 0;
@@ -132,30 +157,16 @@ k_proto_score(const float *__restrict__ sup, const float *__restrict__ sup_y, co
                 acc = cnt ? __fadd_rn(acc, v) : v;
                 ++cnt;
             }
-            const float pk = __fdiv_rn(acc, static_cast<float>(cnt));
-            // classifier.py:63: cdist in double, direct differences
-#pragma unroll
-            for (int q = 0; q < kMaxQ; ++q) {
-                if (q < Q) {
-                    const double df = static_cast<double>(Qp[static_cast<int64_t>(q) * D + k]) - static_cast<double>(pk);
-                    part[q] += df * df;
-                }
-            }
+            PR[static_cast<int64_t>(c) * D + k] = __fdiv_rn(acc, static_cast<float>(cnt));
         }
-#pragma unroll
-        for (int q = 0; q < kMaxQ; ++q) {
-            double v = part[q];
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) s_red[warp][q] = v;
-        }
-        __syncthreads();
-        if (tid < Q) {
-            double v = 0.0;
-            for (int w = 0; w < kProtoThreads / 32; ++w) v += s_red[w][tid];
-            s_d[tid][c] = static_cast<float>(sqrt(v));       // classifier.py:66 float32 cast
-        }
-        __syncthreads();
     }
+    __syncthreads();
+    // classifier.py:63,:66: cdist in double (scipy's order, one thread per pair), float32 cast
+    for (int t = tid; t < Q * np; t += kProtoThreads) {
+        const int q = t / np, c = t - q * np;
+        s_d[q][c] = seq_dist(Qp + static_cast<int64_t>(q) * D, PR + static_cast<int64_t>(c) * D, D);
+    }
+    __syncthreads();
 
     if (tid < Q) {
         const int q = tid;
@@ -184,7 +195,10 @@ int launch_proto_score(const float *sup, const float *sup_y, const float *query,
                   kMaxRows, kMaxQ, kMaxProto, R, Q, max_proto);
         return EOSVR_EINVAL;
     }
-    k_proto_score<<<static_cast<unsigned>(E), kProtoThreads, 0, st>>>(sup, sup_y, query, R, Q, D, max_proto,
+    const int pstride = R < max_proto ? R : max_proto;      // prototypes per episode, at most
+    float *protos = static_cast<float *>(stream_scratch(st, static_cast<size_t>(E) * pstride * D * sizeof(float)));
+    if (!protos) { set_error("proto_score: scratch allocation failed"); return EOSVR_ENOMEM; }
+    k_proto_score<<<static_cast<unsigned>(E), kProtoThreads, 0, st>>>(sup, sup_y, query, R, Q, D, max_proto, protos, pstride,
                                                                      dist, prob, pred, nproto);
     EOSVR_CUDA(cudaGetLastError());
     EOSVR_COUNT_LAUNCH(1);
@@ -206,7 +220,7 @@ __global__ void __launch_bounds__(kProtoThreads)
 k_episode_score(const float *__restrict__ probes, const float *__restrict__ wrows, const void *__restrict__ gal,
                 int gdt, int64_t G, int64_t goff, const int64_t *__restrict__ idx, const float *__restrict__ sup_y,
                 const float *__restrict__ query, int n, int S_rt, int Q, int D, int orig_mode, int max_proto,
-                float *__restrict__ dist, float *__restrict__ prob, int64_t *__restrict__ pred,
+                float *protos, int pstride, float *__restrict__ dist, float *__restrict__ prob, int64_t *__restrict__ pred,
                 int32_t *__restrict__ nproto_out)
 {
     __shared__ int16_t s_cls[kMaxClips];
@@ -214,7 +228,6 @@ k_episode_score(const float *__restrict__ probes, const float *__restrict__ wrow
     __shared__ int16_t s_start[kMaxProto + 1];
     __shared__ float s_pid[kMaxProto];
     __shared__ int s_np;
-    __shared__ double s_red[kProtoThreads / 32][kMaxQ];
     __shared__ float s_d[kMaxQ][kMaxProto];
 
     const int S = S_T > 0 ? S_T : S_rt;
@@ -222,7 +235,8 @@ k_episode_score(const float *__restrict__ probes, const float *__restrict__ wrow
     const float *Pe = probes + e * n * S * D;             // the episode's n*S segment rows
     const float *Y = sup_y + e * n;
     const float *Qp = query + e * Q * D;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *PR = protos + e * pstride * D;                 // this episode's prototypes [np, D]
+    const int tid = threadIdx.x;
 
     if (tid == 0) {
         int np = 0;
@@ -246,9 +260,6 @@ k_episode_score(const float *__restrict__ probes, const float *__restrict__ wrow
     const float fS = static_cast<float>(S);
 
     for (int c = 0; c < np; ++c) {
-        double part[kMaxQ];
-#pragma unroll
-        for (int q = 0; q < kMaxQ; ++q) part[q] = 0.0;
         const int i0 = s_start[c], i1 = s_start[c + 1];
         for (int k = tid; k < D; k += kProtoThreads) {
             float acc = 0.f;
@@ -307,29 +318,16 @@ k_episode_score(const float *__restrict__ probes, const float *__restrict__ wrow
                     }
                 }
             }
-            const float pk = __fdiv_rn(acc, static_cast<float>(cnt));
-#pragma unroll
-            for (int q = 0; q < kMaxQ; ++q) {
-                if (q < Q) {
-                    const double df = static_cast<double>(Qp[static_cast<int64_t>(q) * D + k]) - static_cast<double>(pk);
-                    part[q] += df * df;
-                }
-            }
+            PR[static_cast<int64_t>(c) * D + k] = __fdiv_rn(acc, static_cast<float>(cnt));
         }
-#pragma unroll
-        for (int q = 0; q < kMaxQ; ++q) {
-            double v = part[q];
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) s_red[warp][q] = v;
-        }
-        __syncthreads();
-        if (tid < Q) {
-            double v = 0.0;
-            for (int w = 0; w < kProtoThreads / 32; ++w) v += s_red[w][tid];
-            s_d[tid][c] = static_cast<float>(sqrt(v));
-        }
-        __syncthreads();
     }
+    __syncthreads();
+    // classifier.py:63,:66: cdist in double (scipy's order, one thread per pair), float32 cast
+    for (int t = tid; t < Q * np; t += kProtoThreads) {
+        const int q = t / np, c = t - q * np;
+        s_d[q][c] = seq_dist(Qp + static_cast<int64_t>(q) * D, PR + static_cast<int64_t>(c) * D, D);
+    }
+    __syncthreads();
 
     if (tid < Q) {
         const int q = tid;
@@ -349,11 +347,11 @@ k_episode_score(const float *__restrict__ probes, const float *__restrict__ wrow
 
 // -------------------------------------------------------------------------------------------
 // Split variant of the fused kernel for D % 4 == 0 and S in {2,4,8}: grid (E, nsplit), every block
-// folds one slice of the feature axis with float4 loads and writes its float64 partial sums of squared
-// query-prototype differences; k_episode_final adds the slices in a fixed order (deterministic) and
-// finishes sqrt / softmax / arg-max.  Same float32 evaluation order per feature as k_episode_score, so
-// prototypes are bit-equal; only the float64 summation order over features differs (as it already does
-// from scipy's).  One block per episode left most of the 148 SMs idle at E = 256.
+// folds one slice of the feature axis with float4 loads and writes its slice of the episode's float32
+// prototypes; the LAST block of the episode to finish evaluates the query-prototype distances (scipy's
+// sequential order, one thread per pair) and finishes softmax / arg-max.  Same float32 evaluation order per
+// feature as k_episode_score, so everything is bit-equal.  One block per episode left most of the 148 SMs
+// idle at E = 256.
 // -------------------------------------------------------------------------------------------
 constexpr int kEpThreads = 128;
 
@@ -363,7 +361,7 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
                   int gdt, int64_t G, int64_t goff, const void *const *__restrict__ shard_bases,
                   const int64_t *__restrict__ shard_begin, int nshards, const int64_t *__restrict__ idx,
                   const float *__restrict__ sup_y, const float *__restrict__ query, int n, int Q, int D, int orig_mode,
-                  int max_proto, int nsplit, double *partial, unsigned int *done, float *__restrict__ dist,
+                  int max_proto, int nsplit, float *protos, int pstride, unsigned int *done, float *__restrict__ dist,
                   float *__restrict__ prob, int64_t *__restrict__ pred, int32_t *__restrict__ nproto_out)
 {
     // where each winner row of the episode lives: the exchanged rows, the local gallery, or -- gallery sharded
@@ -376,7 +374,7 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
     __shared__ int16_t s_start[kMaxProto + 1];
     __shared__ float s_pid[kMaxProto];
     __shared__ int s_np;
-    __shared__ double s_red[kEpThreads / 32][kMaxQ];
+    __shared__ float s_d[kMaxQ][kMaxProto];
     __shared__ int s_last;
 
     const int64_t e = blockIdx.x;
@@ -384,8 +382,9 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
     const int D4 = D >> 2;
     const float4 *Pe = reinterpret_cast<const float4 *>(probes + e * n * S_T * D);
     const float *Y = sup_y + e * n;
-    const float4 *Qp = reinterpret_cast<const float4 *>(query + e * Q * D);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *Qp = query + e * Q * D;
+    float *PR = protos + e * pstride * D;                 // this episode's prototypes [np, D]
+    const int tid = threadIdx.x;
 
     for (int t = tid; t < n * S_T; t += kEpThreads) {
         const int64_t slot = e * n * S_T + t;
@@ -427,9 +426,6 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
     const int k0 = sp * per, k1 = min(D4, k0 + per);
 
     for (int c = 0; c < np; ++c) {
-        double part[kMaxQ];
-#pragma unroll
-        for (int q = 0; q < kMaxQ; ++q) part[q] = 0.0;
         const int i0 = s_start[c], i1 = s_start[c + 1];
         for (int k = k0 + tid; k < k1; k += kEpThreads) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -479,37 +475,15 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
                 }
             }
             const float fc = static_cast<float>(cnt);
-#pragma unroll
-            for (int q = 0; q < kMaxQ; ++q) {
-                if (q < Q) {
-                    const float4 qv = Qp[static_cast<int64_t>(q) * D4 + k];
-                    const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) {
-                        const double df = static_cast<double>(qq[x]) - static_cast<double>(__fdiv_rn(acc[x], fc));
-                        part[q] += df * df;
-                    }
-                }
-            }
+            reinterpret_cast<float4 *>(PR + static_cast<int64_t>(c) * D)[k] =
+                make_float4(__fdiv_rn(acc[0], fc), __fdiv_rn(acc[1], fc), __fdiv_rn(acc[2], fc), __fdiv_rn(acc[3], fc));
         }
-#pragma unroll
-        for (int q = 0; q < kMaxQ; ++q) {
-            double v = part[q];
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) s_red[warp][q] = v;
-        }
-        __syncthreads();
-        if (tid < Q) {
-            double v = 0.0;
-            for (int w = 0; w < kEpThreads / 32; ++w) v += s_red[w][tid];
-            partial[((e * nsplit + sp) * max_proto + c) * kMaxQ + tid] = v;
-        }
-        __syncthreads();
     }
-    // The last block of the episode to get here adds the slices in a FIXED order (deterministic) and finishes
-    // sqrt / softmax / arg-max (classifier.py:63-67,:85); its ticket orders it after the other blocks' partial sums.
+    // The last block of the episode to get here evaluates the distances and finishes softmax / arg-max
+    // (classifier.py:63-67,:85); its ticket orders it after the other blocks' prototype slices.
     if (nsplit > 1) {
-        __threadfence();
+        __threadfence();                                  // every thread: its prototype stores before ...
+        __syncthreads();                                  // ... thread 0 takes the block's ticket
         if (tid == 0) {
             const unsigned int ticket = atomicAdd(done + e, 1u);
             s_last = ticket == static_cast<unsigned int>(nsplit - 1);
@@ -518,15 +492,20 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
         if (!s_last) return;
         __threadfence();
     }
+    else __syncthreads();                                 // one slice: this block's own prototype stores
     if (tid == 0 && nproto_out) nproto_out[e] = np;
+    // classifier.py:63,:66: cdist in double (scipy's order, one thread per pair), float32 cast
+    for (int t = tid; t < Q * np; t += kEpThreads) {
+        const int q = t / np, c = t - q * np;
+        s_d[q][c] = seq_dist(Qp + static_cast<int64_t>(q) * D, PR + static_cast<int64_t>(c) * D, D);
+    }
+    __syncthreads();
     if (tid >= Q) return;
     const int q = tid;
     float d[kMaxProto];
     float mx = 0.f; int best = 0;
     for (int c = 0; c < np; ++c) {
-        double v = 0.0;
-        for (int s2 = 0; s2 < nsplit; ++s2) v += __ldcg(partial + ((e * nsplit + s2) * max_proto + c) * kMaxQ + q);
-        d[c] = static_cast<float>(sqrt(v));                  // classifier.py:66 float32 cast
+        d[c] = s_d[q][c];
         if (c == 0) mx = -d[0];
         else { if (-d[c] > mx) mx = -d[c]; if (d[c] < d[best]) best = c; }
     }
@@ -555,23 +534,24 @@ int launch_episode_score(const float *probes, const float *wrows, const void *ga
         set_error("episode_score: need 1<=n<=%d, S>=1, 1<=Q<=%d, 1<=max_proto<=%d", kMaxClips, kMaxQ, kMaxProto);
         return EOSVR_EINVAL;
     }
+    const int pstride = n < max_proto ? n : max_proto;      // prototypes per episode, at most
     if ((D & 3) == 0 && (S == 2 || S == 4 || S == 8) && D >= 256) {
         int nsplit = D / 512;                 // >= 128 float4 columns per block
         if (nsplit < 1) nsplit = 1;
         if (nsplit > 8) nsplit = 8;
-        // scratch: [ticket counters E x u32] [partial sums]
-        const size_t pbytes = static_cast<size_t>(E) * nsplit * max_proto * kMaxQ * sizeof(double);
+        // scratch: [ticket counters E x u32] [float32 prototypes E x pstride x D]
+        const size_t pbytes = static_cast<size_t>(E) * pstride * D * sizeof(float);
         const size_t nbytes = (static_cast<size_t>(E) * sizeof(unsigned int) + 255) / 256 * 256;
         char *scratch = static_cast<char *>(stream_scratch(st, nbytes + pbytes));
         if (!scratch) { set_error("episode_score: scratch allocation of %zu bytes failed", nbytes + pbytes); return EOSVR_ENOMEM; }
         unsigned int *done = reinterpret_cast<unsigned int *>(scratch);
         if (nsplit > 1) EOSVR_CUDA(cudaMemsetAsync(done, 0, static_cast<size_t>(E) * sizeof(unsigned int), st));   // ticket counters
-        double *partial = reinterpret_cast<double *>(scratch + nbytes);
+        float *protos = reinterpret_cast<float *>(scratch + nbytes);
         dim3 pgrid(static_cast<unsigned>(E), static_cast<unsigned>(nsplit));
 #define EOSVR_EPP_LAUNCH(ST)                                                                                      \
         k_episode_partial<ST><<<pgrid, kEpThreads, 0, st>>>(probes, wrows, gal, gal_dtype, G, goff, shard_bases, shard_begin,     \
                                                            nshards, idx, sup_y, query, n, Q, D, orig_mode, max_proto, \
-                                                           nsplit, partial, done, dist, prob, pred, nproto)
+                                                           nsplit, protos, pstride, done, dist, prob, pred, nproto)
         { int trc = timing_begin(timing_ws, EOSVR_KERNEL_EPISODE, st); if (trc) return trc; }
         if (S == 2) EOSVR_EPP_LAUNCH(2); else if (S == 4) EOSVR_EPP_LAUNCH(4); else EOSVR_EPP_LAUNCH(8);
 #undef EOSVR_EPP_LAUNCH
@@ -581,9 +561,11 @@ int launch_episode_score(const float *probes, const float *wrows, const void *ga
         return EOSVR_OK;
     }
     const unsigned grid = static_cast<unsigned>(E);
+    float *protos = static_cast<float *>(stream_scratch(st, static_cast<size_t>(E) * pstride * D * sizeof(float)));
+    if (!protos) { set_error("episode_score: scratch allocation failed"); return EOSVR_ENOMEM; }
 #define EOSVR_EP_LAUNCH(ST)                                                                                    \
     k_episode_score<ST><<<grid, kProtoThreads, 0, st>>>(probes, wrows, gal, gal_dtype, G, goff, idx, sup_y, query, n, S, Q, D, \
-                                                        orig_mode, max_proto, dist, prob, pred, nproto)
+                                                        orig_mode, max_proto, protos, pstride, dist, prob, pred, nproto)
     switch (S) {
         case 2: EOSVR_EP_LAUNCH(2); break;
         case 4: EOSVR_EP_LAUNCH(4); break;

@@ -155,6 +155,35 @@ def test_candidate_overflow_paths():
     assert np.array_equal(idx2.cpu().numpy(), oid2) and np.array_equal(score2.cpu().numpy(), oval2)
 
 
+@pytest.mark.parametrize("D", [64, 512, 2048])
+def test_order_sensitive_pairs(golden_dir, D):
+    """Pairs constructed so that the float64 sum of squared differences sits within a few ulps of a float32
+    rounding boundary (oracle/make_order_cases.py; scipy's value recorded): any summation order but scipy's
+    sequential one rounds most of them to the neighbouring float32.  The matcher (screened and exhaustive) and
+    the prototype scorer must return scipy's float32 bit for bit."""
+    fx = np.load(os.path.join(golden_dir, "golden_order_sensitive.npz"))
+    A, B, want = fx[f"A{D}"], fx[f"B{D}"], fx[f"d64_{D}"].astype(np.float32)
+    n = A.shape[0]
+    gal = np.concatenate([B, synth.gallery(900 + D, 700, D, centroid_seed=3)])
+    r = _match_both(A, gal, 1)                      # one row per episode: no taps, the score IS float32(distance)
+    assert np.array_equal(r["idx"], np.arange(n)) and np.array_equal(r["idx_exact"], np.arange(n))
+    assert np.array_equal(r["score"], want), int((r["score"] != want).sum())
+    assert np.array_equal(r["score_exact"], want), int((r["score_exact"] != want).sum())
+    oid, oval = O.c_match(A, gal, 4)                # with taps: every tap is one of the recorded distances or near one
+    r4 = _match_both(A, gal, 4)
+    assert np.array_equal(r4["idx"], oid) and np.array_equal(r4["score"], oval)
+    assert np.array_equal(r4["idx_exact"], oid) and np.array_equal(r4["score_exact"], oval)
+    # classifier.py:63: one support row per class => the prototype is the row, dist[q, c] = float32(cdist(query q, row c))
+    for s0 in range(0, n, 8):
+        sup, q = B[s0:s0 + 8][None], A[s0:s0 + 8][None]
+        y = np.arange(8, dtype=np.float32)[None]
+        ps = ev.proto_score(_cuda(sup), _cuda(y), _cuda(q), max_proto=8)
+        got = ps["dist"][0].cpu().numpy()
+        assert np.array_equal(np.diagonal(got), want[s0:s0 + 8])
+        _, _, d32, _, _ = O.lib_protonet(sup[0], y[0], q[0])
+        assert np.array_equal(got, d32)
+
+
 def test_screening_error_within_margin():
     """The tensor-core screening values must lie within the rigorous error margin used for the candidate
     test; checked on every element of a small case through the debug dump."""
@@ -171,6 +200,35 @@ def test_screening_error_within_margin():
         err = np.abs(dbg.cpu().numpy() - t)
         assert not np.isnan(err).any()
         assert err.max() < bound, (fmt, err.max())
+
+
+@pytest.mark.parametrize("D", [512, 2048])
+def test_tensor_core_accumulation_term(D):
+    """The accumulation term of the screening error bound (DESIGN.md "Error bound": 2 * 2^-22 * (Dp/16 + 1) *
+    (|a16||b16| + max|b|^2 / 2), the tensor core's undocumented float32 accumulation order) on adversarial data:
+    all-positive features (no cancellation, the partial sums are as large as they get) that are exact in float16,
+    so the rounding-residual terms of the bound vanish and the accumulation term stands alone."""
+    rng = np.random.RandomState(500 + D)
+    A = (rng.randint(0, 64, size=(40, D)) / 1024.0).astype(np.float32)
+    gal = (rng.randint(0, 64, size=(1500, D)) / 1024.0).astype(np.float32)
+    assert np.array_equal(A.astype(np.float16).astype(np.float32), A)
+    cache = ev.GalleryFeatureCache(_cuda(gal))
+    ws = ev.MatchWorkspace(A.shape[0], D)
+    dbg = ws.set_debug_dump(A.shape[0], gal.shape[0])
+    idx, score = ev.match_segments(cache, ws, _cuda(A), 1)          # one row per episode: the dump holds sqrt(|x~|)
+    torch.cuda.synchronize()
+    oid, oval = O.c_match(A, gal, 1)
+    assert np.array_equal(idx.cpu().numpy(), oid) and np.array_equal(score.cpu().numpy(), oval)
+    xt = dbg.cpu().numpy().astype(np.float64) ** 2
+    A64, B64 = A.astype(np.float64), gal.astype(np.float64)
+    na, nb = (A64 * A64).sum(1), (B64 * B64).sum(1)
+    x = na[:, None] + nb[None, :] - 2.0 * (A64 @ B64.T)             # exact to ~1e-15: the inputs are 6-bit integers / 1024
+    ulp, Dp, B2 = 2.0 ** -22, (D + 63) // 64 * 64, nb.max()
+    bound = 1.01 * (2 * ulp * (Dp / 16 + 1) * (np.sqrt(na * B2) + 0.5 * B2) + 2 * ulp * (na + B2))
+    err = np.abs(xt - x) - 1e-6 * x                                  # sqrt.approx and the float32 dump: 2^-21 relative
+    worst = (err / bound[:, None]).max()
+    assert worst < 1.0, worst
+    print(f"accumulation term D={D}: worst observed error / bound = {worst:.3f}")
 
 
 def test_empty_and_errors():
@@ -562,7 +620,8 @@ def test_native_bf16_storage(D, G):
 
 def test_episode_batch_one_call_equals_two_calls():
     """eosvr_episode_batch (one ABI call, caller-provided outputs) == eosvr_match + eosvr_episode_score, for both
-    metrics, and it launches 6 kernels (probe prep, seed pass, screening, re-rank, finish, fused splice + ProtoNet)."""
+    metrics, and it launches 7 kernels (probe prep, seed pass, screening, re-rank, exact jobs, finish, fused splice +
+    ProtoNet)."""
     E, n_way, S, D, G = 40, 5, 4, 512, 30000
     ep = synth.episode_batch(81, E, n_way, 1, S, D)
     cache = ev.GalleryFeatureCache(_cuda(synth.gallery(82, G, D, centroid_seed=81)))
@@ -573,7 +632,7 @@ def test_episode_batch_one_call_equals_two_calls():
         n0 = int(ev.lib().eosvr_launch_count())
         r = pipe.run(p, y, q, reuse_outputs=True)
         launches = int(ev.lib().eosvr_launch_count()) - n0
-        assert launches == 6, launches
+        assert launches == 7, launches
         idx, score = ev.match_segments(cache, pipe.ws, p.reshape(-1, D), n_way * S, metric=metric)
         two = ev.episode_score(p.reshape(-1, D), y, q, n_way, S, gallery=cache, idx=idx, max_proto=n_way)
         assert torch.equal(r["idx"].reshape(-1), idx) and torch.equal(r["score"].reshape(-1), score)

@@ -55,8 +55,7 @@ def test_temporal_golden(golden_dir):
         A, B, d64, t = fx[f"t{c}_A"], fx[f"t{c}_B"], fx[f"t{c}_d64"], fx[f"t{c}_t"]
         assert np.array_equal(O.lib_cdist(A, B), d64)
         cd = O.c_cdist(A, B)
-        np.testing.assert_allclose(cd, d64, rtol=1e-13)
-        assert np.array_equal(cd.astype(np.float32), d64.astype(np.float32))
+        assert np.array_equal(cd, d64)                                   # float64, bit for bit: scipy's summation order
         assert np.array_equal(O.lib_temporal_smooth(d64), t)
         assert np.array_equal(O.c_temporal_smooth(d64), t)               # FMA chain == the recorded conv2d, bit-exact
         # This host's own conv2d: bit-equal where oneDNN picks the fused kernel (the recording host, the GPU
@@ -178,3 +177,21 @@ def test_cosine_match_oracle_vs_sklearn():
     Bn[11] = 10.0                                # keep the zero row out of the Euclidean race
     e_idx, _ = O.c_match(An, Bn, 1, 0.0, 1.0)
     assert (e_idx[keep & clear] == idx[keep & clear]).all()
+
+
+@pytest.mark.parametrize("D", [64, 512, 2048])
+def test_order_sensitive_pairs(golden_dir, D):
+    """Constructed pairs whose float64 sum sits within a few ulps of a float32 rounding boundary
+    (oracle/make_order_cases.py): scipy's cdist and the C restatement agree on them in float64 bit for bit
+    (sequential sum, product rounded before the add), while other summation orders round to another float32."""
+    fx = _load(golden_dir, "golden_order_sensitive.npz")
+    A, B, d64 = fx[f"A{D}"], fx[f"B{D}"], fx[f"d64_{D}"]
+    n = A.shape[0]
+    assert np.array_equal(np.diagonal(O.lib_cdist(A, B)), d64)
+    assert np.array_equal(np.diagonal(O.c_cdist(A, B)), d64)
+    assert int(fx[f"wrong_pairwise_{D}"]) > n // 2 and int(fx[f"wrong_lanes32_{D}"]) > n // 2
+    # the pair is the nearest neighbour of its probe row, so a matcher run on (A, B) reports exactly these distances
+    idx, val = O.c_match(A, B, rows_per_episode=1)
+    assert np.array_equal(idx, np.arange(n)) and np.array_equal(val, d64.astype(np.float32))
+    pred, prob, d32, order, protos = O.lib_protonet(B[:8], np.arange(8, dtype=np.float32), A[:8])
+    assert np.array_equal(np.diagonal(d32), d64[:8].astype(np.float32))
