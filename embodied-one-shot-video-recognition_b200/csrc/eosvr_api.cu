@@ -280,11 +280,6 @@ int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capac
     if (ws->ovf_cap < (1ll << 20)) ws->ovf_cap = 1ll << 20;
     if (ws->ovf_cap > (1ll << 24)) ws->ovf_cap = 1ll << 24;
     const size_t o_ov = carve(static_cast<size_t>(ws->ovf_cap) * sizeof(OvfCand));
-    // exact jobs: the re-rank emits about one per probe row (the winner and its exact ties) and every surviving
-    // spill-over entry is one; a full list sends the row to the exhaustive evaluation
-    ws->job_cap = 4 * ws->maxP + ws->ovf_cap;
-    if (ws->job_cap > (1ll << 30)) ws->job_cap = 1ll << 30;
-    const size_t o_jb = carve(static_cast<size_t>(ws->job_cap) * 8);
     if (cudaMalloc(&ws->slab, off) != cudaSuccess) {
         cudaGetLastError();
         set_error("workspace_create: device allocation of %zu bytes failed", off);
@@ -303,7 +298,6 @@ int eosvr_workspace_create(int64_t max_probe_rows, int32_t D, int64_t cand_capac
     ws->counters = reinterpret_cast<Counters *>(b + o_ct);
     ws->idx_scratch = reinterpret_cast<int64_t *>(b + o_ix);
     ws->ovf = reinterpret_cast<OvfCand *>(b + o_ov);
-    ws->jobs = b + o_jb;
     *out = ws;
     return EOSVR_OK;
 }

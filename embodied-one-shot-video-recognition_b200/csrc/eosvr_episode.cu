@@ -43,29 +43,68 @@ static void *stream_scratch(cudaStream_t st, size_t bytes)
 
 // classifier.py:63 is scipy's cdist(query, prototypes) on float32 rows: promoted to float64 and, per pair, ONE
 // sequential pass  s = 0; for k: e = q[k] - p[k]; s = s + e*e  (product rounded, then the sum; no FMA), sqrt(s),
-// then the float32 cast of :66.  A float64 sum in another order flips the float32 rounding of about one distance in
-// 5 million, so the chain is not parallelised: ONE THREAD evaluates one (query, prototype) pair, and the prototypes
-// (float32, numpy's order) go through a scratch array in global memory (read back with ld.global.cg: with a split
-// feature axis other blocks wrote them).
-__device__ __forceinline__ void seq1(double &s, float q, float p)
+// then the float32 cast of :66.  A float64 sum in another order flips the float32 rounding of about one distance
+// in 10^6, and the sequential chain cannot be parallelised, so the distance is FILTERED: the kernels sum in any
+// order (threads stride k, FMA, tree reduction); that sum S and scipy's are both within gamma_(D+1) of the exact
+// sum of the same squared differences, |S_scipy - S| <= (2 D + 8) 2^-53 S; if float32(sqrt(.)) is the same at both
+// ends of that interval (directed roundings; sqrt and the cast are monotone and correctly rounded) it IS scipy's
+// float32.  Otherwise the pair is parked and a warp evaluates scipy's chain itself from the episode's prototypes in
+// a scratch array (the lanes form 32 consecutive products in parallel, the running sum takes them in order).
+__device__ __forceinline__ bool dist_f32_decided(double S, int D, float &out)
 {
-    const double e = __dsub_rn(static_cast<double>(q), static_cast<double>(p));
-    s = __dadd_rn(s, __dmul_rn(e, e));
+    const double delta = (2.0 * D + 8.0) * 1.1102230246251565e-16;        // (2 D + 8) 2^-53
+    const float lo = static_cast<float>(sqrt(__dmul_rd(S, 1.0 - delta)));
+    const float hi = static_cast<float>(sqrt(__dmul_ru(S, 1.0 + delta)));
+    out = lo;
+    return lo == hi;
 }
-__device__ __forceinline__ float seq_dist(const float *__restrict__ q, const float *proto, int D)
+// proto is read with ld.global.cg (with a split feature axis other blocks wrote it); all lanes return the value
+__device__ __forceinline__ float warp_seq_dist(const float *__restrict__ q, const float *proto, int D, int lane)
 {
     double s = 0.0;
-    if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(proto)) & 15) == 0) {
-        const float4 *q4 = reinterpret_cast<const float4 *>(q), *p4 = reinterpret_cast<const float4 *>(proto);
-#pragma unroll 2
-        for (int k = 0; k < (D >> 2); ++k) {
-            const float4 a = q4[k], b = __ldcg(p4 + k);
-            seq1(s, a.x, b.x); seq1(s, a.y, b.y); seq1(s, a.z, b.z); seq1(s, a.w, b.w);
+    for (int k0 = 0; k0 < D; k0 += 32) {
+        const int k = k0 + lane;
+        double pr = 0.0;                                   // a lane beyond D adds +0.0: the sum is unchanged
+        if (k < D) {
+            const double e = __dsub_rn(static_cast<double>(q[k]), static_cast<double>(__ldcg(proto + k)));
+            pr = __dmul_rn(e, e);
         }
-    } else {
-        for (int k = 0; k < D; ++k) seq1(s, q[k], __ldcg(proto + k));
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) s = __dadd_rn(s, __shfl_sync(0xffffffffu, pr, i));
     }
     return static_cast<float>(sqrt(s));
+}
+// Parked pairs of one episode (block-wide): decide-or-park, then resolve.  s_amb holds q * 256 + c.
+constexpr int kMaxAmb = 32;
+__device__ __forceinline__ void dist_decide(double S, int D, int q, int c, float (*s_d)[64], int *s_namb, int *s_amb)
+{
+    float d;
+    if (dist_f32_decided(S, D, d)) { s_d[q][c] = d; return; }
+    const int i = atomicAdd(s_namb, 1);
+    if (i < kMaxAmb) s_amb[i] = q * 256 + c;
+    s_d[q][c] = __int_as_float(0x7fc00000);                // resolved below (or by the caller if the list overflowed)
+}
+// after a __syncthreads(): the block's warps resolve the parked pairs; a list overflow (never seen: it takes > 32
+// boundary hits in one episode) resolves every pair of the episode.  Ends with a __syncthreads().
+__device__ __forceinline__ void dist_resolve(const float *__restrict__ Qp, const float *PR, int D, int Q, int np,
+                                             float (*s_d)[64], const int *s_namb, const int *s_amb, int nthreads)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = nthreads >> 5;
+    const int n = *s_namb;
+    if (n > kMaxAmb) {
+        for (int t = warp; t < Q * np; t += nw) {
+            const int q = t / np, c = t - q * np;
+            const float d = warp_seq_dist(Qp + static_cast<int64_t>(q) * D, PR + static_cast<int64_t>(c) * D, D, lane);
+            if (lane == 0) s_d[q][c] = d;
+        }
+    } else {
+        for (int i = warp; i < n; i += nw) {
+            const int q = s_amb[i] >> 8, c = s_amb[i] & 255;
+            const float d = warp_seq_dist(Qp + static_cast<int64_t>(q) * D, PR + static_cast<int64_t>(c) * D, D, lane);
+            if (lane == 0) s_d[q][c] = d;
+        }
+    }
+    __syncthreads();
 }
 
 // grid: (E*n, 1+S); block: 128 threads striding D.
@@ -122,17 +161,19 @@ k_proto_score(const float *__restrict__ sup, const float *__restrict__ sup_y, co
 {
     __shared__ int16_t s_cls[kMaxRows];
     __shared__ float s_pid[kMaxProto];
-    __shared__ int s_np;
+    __shared__ int s_np, s_namb, s_amb[kMaxAmb];
+    __shared__ double s_red[kProtoThreads / 32][kMaxQ];
     __shared__ float s_d[kMaxQ][kMaxProto];
 
     const int64_t e = blockIdx.x;
     const float *S0 = sup + e * R * D;
     const float *Y = sup_y + e * R;
     const float *Qp = query + e * Q * D;
-    float *PR = protos + e * pstride * D;              // this episode's prototypes [np, D]
-    const int tid = threadIdx.x;
+    float *PR = protos + e * pstride * D;              // this episode's prototypes [np, D] (read by the rare sequential pass)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
+        s_namb = 0;
         // classifier.py:21-29: classes keyed by label value, first-appearance order
         int np = 0;
         for (int r = 0; r < R; ++r) {
@@ -148,6 +189,9 @@ k_proto_score(const float *__restrict__ sup, const float *__restrict__ sup_y, co
     const int np = s_np;
 
     for (int c = 0; c < np; ++c) {
+        double part[kMaxQ];
+#pragma unroll
+        for (int q = 0; q < kMaxQ; ++q) part[q] = 0.0;
         for (int k = tid; k < D; k += kProtoThreads) {
             // classifier.py:34-35: float32 mean over the class rows, sequential, true division
             float acc = 0.f; int cnt = 0;
@@ -157,16 +201,32 @@ k_proto_score(const float *__restrict__ sup, const float *__restrict__ sup_y, co
                 acc = cnt ? __fadd_rn(acc, v) : v;
                 ++cnt;
             }
-            PR[static_cast<int64_t>(c) * D + k] = __fdiv_rn(acc, static_cast<float>(cnt));
+            const float pk = __fdiv_rn(acc, static_cast<float>(cnt));
+            PR[static_cast<int64_t>(c) * D + k] = pk;
+            // classifier.py:63: cdist in double, direct differences (summation order: see dist_f32_decided)
+#pragma unroll
+            for (int q = 0; q < kMaxQ; ++q) {
+                if (q < Q) {
+                    const double df = static_cast<double>(Qp[static_cast<int64_t>(q) * D + k]) - static_cast<double>(pk);
+                    part[q] += df * df;
+                }
+            }
         }
+#pragma unroll
+        for (int q = 0; q < kMaxQ; ++q) {
+            double v = part[q];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_red[warp][q] = v;
+        }
+        __syncthreads();
+        if (tid < Q) {
+            double v = 0.0;
+            for (int w = 0; w < kProtoThreads / 32; ++w) v += s_red[w][tid];
+            dist_decide(v, D, tid, c, s_d, &s_namb, s_amb);  // classifier.py:66 float32 cast
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    // classifier.py:63,:66: cdist in double (scipy's order, one thread per pair), float32 cast
-    for (int t = tid; t < Q * np; t += kProtoThreads) {
-        const int q = t / np, c = t - q * np;
-        s_d[q][c] = seq_dist(Qp + static_cast<int64_t>(q) * D, PR + static_cast<int64_t>(c) * D, D);
-    }
-    __syncthreads();
+    dist_resolve(Qp, PR, D, Q, np, s_d, &s_namb, s_amb, kProtoThreads);
 
     if (tid < Q) {
         const int q = tid;
@@ -227,7 +287,8 @@ k_episode_score(const float *__restrict__ probes, const float *__restrict__ wrow
     __shared__ int16_t s_order[kMaxClips];      // clips grouped by class, original order inside a class
     __shared__ int16_t s_start[kMaxProto + 1];
     __shared__ float s_pid[kMaxProto];
-    __shared__ int s_np;
+    __shared__ int s_np, s_namb, s_amb[kMaxAmb];
+    __shared__ double s_red[kProtoThreads / 32][kMaxQ];
     __shared__ float s_d[kMaxQ][kMaxProto];
 
     const int S = S_T > 0 ? S_T : S_rt;
@@ -236,9 +297,10 @@ k_episode_score(const float *__restrict__ probes, const float *__restrict__ wrow
     const float *Y = sup_y + e * n;
     const float *Qp = query + e * Q * D;
     float *PR = protos + e * pstride * D;                 // this episode's prototypes [np, D]
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
+        s_namb = 0;
         int np = 0;
         for (int i = 0; i < n; ++i) {                     // classifier.py:21-29 (every row of clip i carries Y[i])
             const float y = Y[i];
@@ -260,6 +322,9 @@ k_episode_score(const float *__restrict__ probes, const float *__restrict__ wrow
     const float fS = static_cast<float>(S);
 
     for (int c = 0; c < np; ++c) {
+        double part[kMaxQ];
+#pragma unroll
+        for (int q = 0; q < kMaxQ; ++q) part[q] = 0.0;
         const int i0 = s_start[c], i1 = s_start[c + 1];
         for (int k = tid; k < D; k += kProtoThreads) {
             float acc = 0.f;
@@ -318,16 +383,31 @@ k_episode_score(const float *__restrict__ probes, const float *__restrict__ wrow
                     }
                 }
             }
-            PR[static_cast<int64_t>(c) * D + k] = __fdiv_rn(acc, static_cast<float>(cnt));
+            const float pk = __fdiv_rn(acc, static_cast<float>(cnt));
+            PR[static_cast<int64_t>(c) * D + k] = pk;
+#pragma unroll
+            for (int q = 0; q < kMaxQ; ++q) {
+                if (q < Q) {
+                    const double df = static_cast<double>(Qp[static_cast<int64_t>(q) * D + k]) - static_cast<double>(pk);
+                    part[q] += df * df;
+                }
+            }
         }
+#pragma unroll
+        for (int q = 0; q < kMaxQ; ++q) {
+            double v = part[q];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_red[warp][q] = v;
+        }
+        __syncthreads();
+        if (tid < Q) {
+            double v = 0.0;
+            for (int w = 0; w < kProtoThreads / 32; ++w) v += s_red[w][tid];
+            dist_decide(v, D, tid, c, s_d, &s_namb, s_amb);
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    // classifier.py:63,:66: cdist in double (scipy's order, one thread per pair), float32 cast
-    for (int t = tid; t < Q * np; t += kProtoThreads) {
-        const int q = t / np, c = t - q * np;
-        s_d[q][c] = seq_dist(Qp + static_cast<int64_t>(q) * D, PR + static_cast<int64_t>(c) * D, D);
-    }
-    __syncthreads();
+    dist_resolve(Qp, PR, D, Q, np, s_d, &s_namb, s_amb, kProtoThreads);
 
     if (tid < Q) {
         const int q = tid;
@@ -347,11 +427,11 @@ k_episode_score(const float *__restrict__ probes, const float *__restrict__ wrow
 
 // -------------------------------------------------------------------------------------------
 // Split variant of the fused kernel for D % 4 == 0 and S in {2,4,8}: grid (E, nsplit), every block
-// folds one slice of the feature axis with float4 loads and writes its slice of the episode's float32
-// prototypes; the LAST block of the episode to finish evaluates the query-prototype distances (scipy's
-// sequential order, one thread per pair) and finishes softmax / arg-max.  Same float32 evaluation order per
-// feature as k_episode_score, so everything is bit-equal.  One block per episode left most of the 148 SMs
-// idle at E = 256.
+// folds one slice of the feature axis with float4 loads and writes its float64 partial sums of squared
+// query-prototype differences (and its slice of the float32 prototypes, for the rare sequential pass); the last
+// block of the episode adds the slices in a fixed order (deterministic), decides the float32 distances
+// (dist_f32_decided) and finishes softmax / arg-max.  Same float32 evaluation order per feature as
+// k_episode_score, so everything is bit-equal.  One block per episode left most of the 148 SMs idle at E = 256.
 // -------------------------------------------------------------------------------------------
 constexpr int kEpThreads = 128;
 
@@ -361,8 +441,8 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
                   int gdt, int64_t G, int64_t goff, const void *const *__restrict__ shard_bases,
                   const int64_t *__restrict__ shard_begin, int nshards, const int64_t *__restrict__ idx,
                   const float *__restrict__ sup_y, const float *__restrict__ query, int n, int Q, int D, int orig_mode,
-                  int max_proto, int nsplit, float *protos, int pstride, unsigned int *done, float *__restrict__ dist,
-                  float *__restrict__ prob, int64_t *__restrict__ pred, int32_t *__restrict__ nproto_out)
+                  int max_proto, int nsplit, double *partial, float *protos, int pstride, unsigned int *done,
+                  float *__restrict__ dist, float *__restrict__ prob, int64_t *__restrict__ pred, int32_t *__restrict__ nproto_out)
 {
     // where each winner row of the episode lives: the exchanged rows, the local gallery, or -- gallery sharded
     // over the GPUs of the box -- the owning GPU's memory, read in place over NVLink (peer loads)
@@ -373,7 +453,8 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
     __shared__ int16_t s_order[kMaxClips];
     __shared__ int16_t s_start[kMaxProto + 1];
     __shared__ float s_pid[kMaxProto];
-    __shared__ int s_np;
+    __shared__ int s_np, s_namb, s_amb[kMaxAmb];
+    __shared__ double s_red[kEpThreads / 32][kMaxQ];
     __shared__ float s_d[kMaxQ][kMaxProto];
     __shared__ int s_last;
 
@@ -382,9 +463,8 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
     const int D4 = D >> 2;
     const float4 *Pe = reinterpret_cast<const float4 *>(probes + e * n * S_T * D);
     const float *Y = sup_y + e * n;
-    const float *Qp = query + e * Q * D;
-    float *PR = protos + e * pstride * D;                 // this episode's prototypes [np, D]
-    const int tid = threadIdx.x;
+    const float4 *Qp = reinterpret_cast<const float4 *>(query + e * Q * D);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int t = tid; t < n * S_T; t += kEpThreads) {
         const int64_t slot = e * n * S_T + t;
@@ -402,7 +482,9 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
         s_wrow4[t] = row4;
     }
     const int wdt = wrows ? EOSVR_F32 : gdt;
+    float *PR = protos + e * pstride * D;                 // this episode's prototypes [np, D] (read by the rare sequential pass)
     if (tid == 0) {
+        s_namb = 0;
         int np = 0;
         for (int i = 0; i < n; ++i) {                     // classifier.py:21-29 (every row of clip i carries Y[i])
             const float y = Y[i];
@@ -426,6 +508,9 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
     const int k0 = sp * per, k1 = min(D4, k0 + per);
 
     for (int c = 0; c < np; ++c) {
+        double part[kMaxQ];
+#pragma unroll
+        for (int q = 0; q < kMaxQ; ++q) part[q] = 0.0;
         const int i0 = s_start[c], i1 = s_start[c + 1];
         for (int k = k0 + tid; k < k1; k += kEpThreads) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -475,12 +560,39 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
                 }
             }
             const float fc = static_cast<float>(cnt);
-            reinterpret_cast<float4 *>(PR + static_cast<int64_t>(c) * D)[k] =
-                make_float4(__fdiv_rn(acc[0], fc), __fdiv_rn(acc[1], fc), __fdiv_rn(acc[2], fc), __fdiv_rn(acc[3], fc));
+            const float pk[4] = {__fdiv_rn(acc[0], fc), __fdiv_rn(acc[1], fc), __fdiv_rn(acc[2], fc), __fdiv_rn(acc[3], fc)};
+            reinterpret_cast<float4 *>(PR + static_cast<int64_t>(c) * D)[k] = make_float4(pk[0], pk[1], pk[2], pk[3]);
+#pragma unroll
+            for (int q = 0; q < kMaxQ; ++q) {
+                if (q < Q) {
+                    const float4 qv = Qp[static_cast<int64_t>(q) * D4 + k];
+                    const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const double df = static_cast<double>(qq[x]) - static_cast<double>(pk[x]);
+                        part[q] += df * df;
+                    }
+                }
+            }
         }
+#pragma unroll
+        for (int q = 0; q < kMaxQ; ++q) {
+            double v = part[q];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) s_red[warp][q] = v;
+        }
+        __syncthreads();
+        if (tid < Q) {
+            double v = 0.0;
+            for (int w = 0; w < kEpThreads / 32; ++w) v += s_red[w][tid];
+            partial[((e * nsplit + sp) * max_proto + c) * kMaxQ + tid] = v;
+        }
+        __syncthreads();
     }
-    // The last block of the episode to get here evaluates the distances and finishes softmax / arg-max
-    // (classifier.py:63-67,:85); its ticket orders it after the other blocks' prototype slices.
+    // The last block of the episode to get here adds the slices in a FIXED order (deterministic), decides the float32
+    // distances (dist_f32_decided; the rare undecided pair is evaluated in scipy's order from the prototype scratch) and
+    // finishes softmax / arg-max (classifier.py:63-67,:85); its ticket orders it after the other blocks' partial sums
+    // and prototype slices.
     if (nsplit > 1) {
         __threadfence();                                  // every thread: its prototype stores before ...
         __syncthreads();                                  // ... thread 0 takes the block's ticket
@@ -492,29 +604,25 @@ k_episode_partial(const float *__restrict__ probes, const float *__restrict__ wr
         if (!s_last) return;
         __threadfence();
     }
-    else __syncthreads();                                 // one slice: this block's own prototype stores
     if (tid == 0 && nproto_out) nproto_out[e] = np;
-    // classifier.py:63,:66: cdist in double (scipy's order, one thread per pair), float32 cast
     for (int t = tid; t < Q * np; t += kEpThreads) {
         const int q = t / np, c = t - q * np;
-        s_d[q][c] = seq_dist(Qp + static_cast<int64_t>(q) * D, PR + static_cast<int64_t>(c) * D, D);
+        double v = 0.0;
+        for (int s2 = 0; s2 < nsplit; ++s2) v += __ldcg(partial + ((e * nsplit + s2) * max_proto + c) * kMaxQ + q);
+        dist_decide(v, D, q, c, s_d, &s_namb, s_amb);         // classifier.py:66 float32 cast
     }
     __syncthreads();
+    dist_resolve(query + e * Q * D, PR, D, Q, np, s_d, &s_namb, s_amb, kEpThreads);
     if (tid >= Q) return;
     const int q = tid;
-    float d[kMaxProto];
-    float mx = 0.f; int best = 0;
-    for (int c = 0; c < np; ++c) {
-        d[c] = s_d[q][c];
-        if (c == 0) mx = -d[0];
-        else { if (-d[c] > mx) mx = -d[c]; if (d[c] < d[best]) best = c; }
-    }
+    float mx = -s_d[q][0]; int best = 0;
+    for (int c = 1; c < np; ++c) { if (-s_d[q][c] > mx) mx = -s_d[q][c]; if (s_d[q][c] < s_d[q][best]) best = c; }
     float sum = 0.f;
-    for (int c = 0; c < np; ++c) sum += expf(-d[c] - mx);
+    for (int c = 0; c < np; ++c) sum += expf(-s_d[q][c] - mx);
     for (int c = 0; c < max_proto; ++c) {
         const int64_t o = (e * Q + q) * max_proto + c;
-        if (dist) dist[o] = c < np ? d[c] : INFINITY;
-        if (prob) prob[o] = c < np ? expf(-d[c] - mx) / sum : 0.f;
+        if (dist) dist[o] = c < np ? s_d[q][c] : INFINITY;
+        if (prob) prob[o] = c < np ? expf(-s_d[q][c] - mx) / sum : 0.f;
     }
     if (pred) pred[e * Q + q] = best;
 }
@@ -539,19 +647,21 @@ int launch_episode_score(const float *probes, const float *wrows, const void *ga
         int nsplit = D / 512;                 // >= 128 float4 columns per block
         if (nsplit < 1) nsplit = 1;
         if (nsplit > 8) nsplit = 8;
-        // scratch: [ticket counters E x u32] [float32 prototypes E x pstride x D]
-        const size_t pbytes = static_cast<size_t>(E) * pstride * D * sizeof(float);
+        // scratch: [ticket counters E x u32] [partial sums] [float32 prototypes E x pstride x D]
+        const size_t pbytes = (static_cast<size_t>(E) * nsplit * max_proto * kMaxQ * sizeof(double) + 255) / 256 * 256;
         const size_t nbytes = (static_cast<size_t>(E) * sizeof(unsigned int) + 255) / 256 * 256;
-        char *scratch = static_cast<char *>(stream_scratch(st, nbytes + pbytes));
-        if (!scratch) { set_error("episode_score: scratch allocation of %zu bytes failed", nbytes + pbytes); return EOSVR_ENOMEM; }
+        const size_t rbytes = static_cast<size_t>(E) * pstride * D * sizeof(float);
+        char *scratch = static_cast<char *>(stream_scratch(st, nbytes + pbytes + rbytes));
+        if (!scratch) { set_error("episode_score: scratch allocation of %zu bytes failed", nbytes + pbytes + rbytes); return EOSVR_ENOMEM; }
+        float *protos = reinterpret_cast<float *>(scratch + nbytes + pbytes);
         unsigned int *done = reinterpret_cast<unsigned int *>(scratch);
         if (nsplit > 1) EOSVR_CUDA(cudaMemsetAsync(done, 0, static_cast<size_t>(E) * sizeof(unsigned int), st));   // ticket counters
-        float *protos = reinterpret_cast<float *>(scratch + nbytes);
+        double *partial = reinterpret_cast<double *>(scratch + nbytes);
         dim3 pgrid(static_cast<unsigned>(E), static_cast<unsigned>(nsplit));
 #define EOSVR_EPP_LAUNCH(ST)                                                                                      \
         k_episode_partial<ST><<<pgrid, kEpThreads, 0, st>>>(probes, wrows, gal, gal_dtype, G, goff, shard_bases, shard_begin,     \
                                                            nshards, idx, sup_y, query, n, Q, D, orig_mode, max_proto, \
-                                                           nsplit, protos, pstride, done, dist, prob, pred, nproto)
+                                                           nsplit, partial, protos, pstride, done, dist, prob, pred, nproto)
         { int trc = timing_begin(timing_ws, EOSVR_KERNEL_EPISODE, st); if (trc) return trc; }
         if (S == 2) EOSVR_EPP_LAUNCH(2); else if (S == 4) EOSVR_EPP_LAUNCH(4); else EOSVR_EPP_LAUNCH(8);
 #undef EOSVR_EPP_LAUNCH

@@ -97,7 +97,7 @@ struct Counters {
     unsigned int xfloor_bits;        // max over columns of the cancellation guard (x domain)
     unsigned int ovf_count;          // entries appended to the shared spill-over buffer
     unsigned int done_blocks;        // k_finish: blocks that have finished the exhaustive evaluation (last one unpacks)
-    unsigned int job_count;          // pairs handed to k_exact_jobs (may exceed the list's capacity)
+    unsigned int pad0;
     // cycle accounting of the screening kernel (EOSVR_EXP bit 16; measurement only), summed over CTAs
     unsigned long long cyc_epi_busy, cyc_epi_wait, cyc_mma_wait_full, cyc_mma_wait_acc, cyc_prod_wait, cyc_total;
     unsigned long long cyc_epi_pre, cyc_epi_loop;   // epilogue busy time split: before / inside the chunk loop of a tile
@@ -151,8 +151,6 @@ struct eosvr_workspace {
     eosvr::Cand *cand;       // [maxP, cand_cap]
     eosvr::OvfCand *ovf;     // [ovf_cap] shared spill-over of full row lists
     int64_t ovf_cap;
-    void *jobs;              // [job_cap] (probe row, gallery row) pairs for k_exact_jobs (8 B each)
-    int64_t job_cap;
     eosvr::Counters *counters;
     float *dbg;              // optional [P,G] dump of screening values (tests)
     int64_t dbg_elems;

@@ -1158,32 +1158,87 @@ k_match_screen(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // -------------------------------------------------------------------------------------------
-// Exact evaluation (the reference's arithmetic, in the reference's ORDER): network_test.py:208 is scipy's
+// Exact evaluation (the reference's arithmetic, with the reference's ROUNDING): network_test.py:208 is scipy's
 // cdist(..., 'euclidean') on float32 rows -- promoted to float64, then, per pair, ONE sequential pass
 //   s = 0;  for k = 0 .. D-1:  e = a[k] - b[k];  s = s + e*e        (product rounded, then the sum: no FMA)
 // and sqrt(s) (scipy/spatial/src/distance_metrics.h, transform_reduce_2d_: the 4-way unrolling is over ROWS, the
-// reduction along a row is sequential; verified bit for bit in float64 by the CPU tests).  Then :109
-// (float32 cast) and models.py:42-56 as the float32 FMA chain
+// reduction along a row is sequential; checked bit for bit in float64 by the CPU tests).  Then :109 (float32 cast)
+// and models.py:42-56 as the float32 FMA chain
 //   acc = lam1*d[p-1];  acc = fma(lam2, d[p], acc);  acc = fma(lam1, d[p+1], acc)
-// with zero padding at episode ends.  A float64 sum in another order differs from scipy's in the last bits and
-// flips the float32 rounding of about one distance in 5 million, so the chain is NOT parallelised: ONE THREAD
-// evaluates one (probe row, gallery row) pair -- the three taps are three independent chains in that thread --
-// and parallelism comes from the pairs (thread per job in k_exact_jobs, lane per gallery row in k_finish).
-// __dsub_rn / __dmul_rn / __dadd_rn keep the compiler from contracting e*e + s into an FMA.
+// with zero padding at episode ends.
+//
+// A float64 sum in another order differs from scipy's in its last bits, and about one distance in 10^6 then rounds
+// to the neighbouring float32.  The sequential chain cannot be parallelised, so the evaluation is FILTERED:
+//   (1) fast sum S in any order (lanes stride k, FMA, tree reduction).  Both S and scipy's sum are within
+//       gamma_(D+1) of the exact sum of the (identical) squared differences, so |S_scipy - S| <= delta * S with
+//       delta = (2 D + 8) 2^-53;
+//   (2) if float32(sqrt(S (1 - delta))) == float32(sqrt(S (1 + delta))) (directed roundings; sqrt and the cast are
+//       monotone and correctly rounded), scipy's float32 is that value -- decided;
+//   (3) otherwise (a rounding boundary of float32 lies inside the interval: ~1e-6 of the distances) the warp
+//       evaluates scipy's sequential chain itself: the lanes form the products of 32 consecutive k in parallel and
+//       the running sums take them in order through shuffles (warp_seq3).
+// tests/golden/golden_order_sensitive.npz holds pairs constructed to fall into (3).
 // -------------------------------------------------------------------------------------------
-__device__ __forceinline__ void seq3(double &s0, double &s1, double &s2, float b, float q0, float q1, float q2)
+__device__ __forceinline__ double seq_delta(int D) { return (2.0 * D + 8.0) * 1.1102230246251565e-16; }   // (2D+8) 2^-53
+
+// float32(sqrt(s_scipy)) if it is determined by S and delta (see above); false: ambiguous
+__device__ __forceinline__ bool sqrt_f32_decided(double S, double delta, float &out)
 {
-    const double bd = static_cast<double>(b);
-    const double e0 = __dsub_rn(static_cast<double>(q0), bd);
-    const double e1 = __dsub_rn(static_cast<double>(q1), bd);
-    const double e2 = __dsub_rn(static_cast<double>(q2), bd);
-    s0 = __dadd_rn(s0, __dmul_rn(e0, e0));
-    s1 = __dadd_rn(s1, __dmul_rn(e1, e1));
-    s2 = __dadd_rn(s2, __dmul_rn(e2, e2));
+    const float lo = static_cast<float>(sqrt(__dmul_rd(S, 1.0 - delta)));
+    const float hi = static_cast<float>(sqrt(__dmul_ru(S, 1.0 + delta)));
+    out = lo;
+    return lo == hi;
+}
+
+// scipy's sequential float64 sums of squared differences of gallery row b0 against up to three probe rows,
+// warp-cooperative: lane l forms the products of element k0 + l, the running sums add them in the order of k
+// (a lane beyond D contributes +0.0, which leaves a non-negative sum unchanged).  All lanes return the sums.
+__device__ __forceinline__ void warp_seq3(const float *a0, const float *a1, const float *a2, const void *__restrict__ gal,
+                                          int gdt, int64_t b0, int D, int lane, double &s0, double &s1, double &s2)
+{
+    s0 = s1 = s2 = 0.0;
+    for (int k0 = 0; k0 < D; k0 += 32) {
+        const int k = k0 + lane;
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+        if (k < D) {
+            const double bv = ld_feat(gal, gdt, b0 + k);
+            const double e0 = __dsub_rn(static_cast<double>(a0[k]), bv);
+            const double e1 = __dsub_rn(static_cast<double>(a1[k]), bv);
+            const double e2 = __dsub_rn(static_cast<double>(a2[k]), bv);
+            p0 = __dmul_rn(e0, e0); p1 = __dmul_rn(e1, e1); p2 = __dmul_rn(e2, e2);
+        }
+#pragma unroll 2
+        for (int i = 0; i < 32; ++i) {
+            s0 = __dadd_rn(s0, __shfl_sync(0xffffffffu, p0, i));
+            s1 = __dadd_rn(s1, __shfl_sync(0xffffffffu, p1, i));
+            s2 = __dadd_rn(s2, __shfl_sync(0xffffffffu, p2, i));
+        }
+    }
+}
+
+// The three float32 distances of the taps from fast sums y0..y2 (any order), falling back to scipy's order where
+// the float32 rounding is not decided by them.  Warp-cooperative (all lanes hold the same y); a0/a1/a2 may live in
+// shared or global memory.
+__device__ __forceinline__ void taps_f32(double y0, double y1, double y2, bool hl, bool hr, const float *a0, const float *a1,
+                                         const float *a2, const void *__restrict__ gal, int gdt, int64_t b0, int D, int lane,
+                                         float &d0, float &d1, float &d2)
+{
+    const double delta = seq_delta(D);
+    bool ok = sqrt_f32_decided(y1, delta, d1);
+    d0 = 0.f; d2 = 0.f;
+    if (hl) ok = sqrt_f32_decided(y0, delta, d0) && ok;
+    if (hr) ok = sqrt_f32_decided(y2, delta, d2) && ok;
+    if (!ok) {                                               // warp-uniform
+        double s0, s1, s2;
+        warp_seq3(a0, a1, a2, gal, gdt, b0, D, lane, s0, s1, s2);
+        d0 = hl ? static_cast<float>(sqrt(s0)) : 0.f;
+        d1 = static_cast<float>(sqrt(s1));
+        d2 = hr ? static_cast<float>(sqrt(s2)) : 0.f;
+    }
 }
 
 __device__ __forceinline__ float exact_t(const float *__restrict__ probes, int64_t P, int D, int rpe,
-                                         int64_t p, const void *__restrict__ gal, int gdt, int64_t g, float lam1, float lam2)
+                                         int64_t p, const void *__restrict__ gal, int gdt, int64_t b0, float lam1, float lam2, int lane)
 {
     const int r = static_cast<int>(p % rpe);
     const bool hl = r > 0, hr = (r + 1 < rpe) && (p + 1 < P);
@@ -1191,35 +1246,21 @@ __device__ __forceinline__ float exact_t(const float *__restrict__ probes, int64
     const float *a0 = hl ? a1 - D : a1;
     const float *a2 = hr ? a1 + D : a1;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    if ((D & 3) == 0) {
-        const float4 *a04 = reinterpret_cast<const float4 *>(a0), *a14 = reinterpret_cast<const float4 *>(a1),
-                     *a24 = reinterpret_cast<const float4 *>(a2);
-        const int64_t g4 = g * (D >> 2);
-#pragma unroll 2
-        for (int k = 0; k < (D >> 2); ++k) {
-            const float4 b = ld_feat4(gal, gdt, g4 + k);
-            const float4 q0 = a04[k], q1 = a14[k], q2 = a24[k];
-            seq3(s0, s1, s2, b.x, q0.x, q1.x, q2.x);
-            seq3(s0, s1, s2, b.y, q0.y, q1.y, q2.y);
-            seq3(s0, s1, s2, b.z, q0.z, q1.z, q2.z);
-            seq3(s0, s1, s2, b.w, q0.w, q1.w, q2.w);
-        }
-    } else {
-        const int64_t b0 = g * D;
-        for (int k = 0; k < D; ++k) seq3(s0, s1, s2, ld_feat(gal, gdt, b0 + k), a0[k], a1[k], a2[k]);
+    for (int k = lane; k < D; k += 32) {
+        const double bv = ld_feat(gal, gdt, b0 + k);
+        const double e0 = static_cast<double>(a0[k]) - bv;
+        const double e1 = static_cast<double>(a1[k]) - bv;
+        const double e2 = static_cast<double>(a2[k]) - bv;
+        s0 += e0 * e0; s1 += e1 * e1; s2 += e2 * e2;
     }
-    const float d0 = hl ? static_cast<float>(sqrt(s0)) : 0.f;
-    const float d1 = static_cast<float>(sqrt(s1));
-    const float d2 = hr ? static_cast<float>(sqrt(s2)) : 0.f;
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    float d0, d1, d2;
+    taps_f32(s0, s1, s2, hl, hr, a0, a1, a2, gal, gdt, b0, D, lane, d0, d1, d2);
     float acc = __fmul_rn(lam1, d0);
     acc = __fmaf_rn(lam2, d1, acc);
     acc = __fmaf_rn(lam1, d2, acc);
     return acc;
 }
-
-struct ExactJob {            // one (probe row, local gallery row) pair to be evaluated exactly
-    int32_t row, g;
-};
 
 struct RerankParams {
     const float *probes;
@@ -1238,110 +1279,119 @@ struct RerankParams {
     int32_t *rowflag;
     const OvfCand *ovf;
     int32_t ovf_cap;
-    ExactJob *jobs;          // pairs handed to k_exact_jobs
-    int32_t job_cap;
     const float *epsd, *wl, *wr;   // per plan column (column_margin)
     int32_t planR, planBN, planHalo;
     int32_t prof;            // EOSVR_EXP bit 64: phase timing of k_rerank_rows into the cycle counters
     int32_t rows_per_block;  // consecutive probe rows per k_rerank_rows block (1..kRrRowsPerBlock)
 };
 
-// Cosine metric, exactly: float64 dot / (|a| |b|) on the original rows (0 for a zero row), rounded to
-// float32; returned negated (score domain).  Sequential order (the definition the tests check against:
-// dot, |a|^2 and |b|^2 each one sequential pass): three chains, products rounded before they are added.
-__device__ __forceinline__ float exact_negcos(const float *__restrict__ a, const void *__restrict__ gal, int gdt, int64_t g, int D)
+// The definition's sequential chains of the cosine (rare path of exact_negcos), warp-cooperative like warp_seq3.
+__device__ __forceinline__ float warp_seq_negcos(const float *a, const void *__restrict__ gal, int gdt, int64_t b0, int D, int lane)
 {
     double dot = 0.0, na = 0.0, nb = 0.0;
-    const int64_t b0 = g * D;
-    for (int k = 0; k < D; ++k) {
+    for (int k0 = 0; k0 < D; k0 += 32) {
+        const int k = k0 + lane;
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+        if (k < D) {
+            const double x = a[k], y = ld_feat(gal, gdt, b0 + k);
+            p0 = __dmul_rn(x, y); p1 = __dmul_rn(x, x); p2 = __dmul_rn(y, y);
+        }
+#pragma unroll 2
+        for (int i = 0; i < 32; ++i) {
+            dot = __dadd_rn(dot, __shfl_sync(0xffffffffu, p0, i));
+            na = __dadd_rn(na, __shfl_sync(0xffffffffu, p1, i));
+            nb = __dadd_rn(nb, __shfl_sync(0xffffffffu, p2, i));
+        }
+    }
+    return 0.f - static_cast<float>(__ddiv_rn(dot, __dmul_rn(sqrt(na), sqrt(nb))));
+}
+
+// Cosine metric, exactly: float64 dot / (|a| |b|) on the original rows (0 for a zero row), rounded to
+// float32; returned negated (score domain).  The definition sums dot, |a|^2 and |b|^2 each in ONE sequential
+// float64 pass (products rounded before they are added); filtered like the distances: both the fast value c and the
+// sequential one are within (2 D + 7) 2^-53 of the true cosine (Cauchy-Schwarz on the dot product's rounding
+// errors, |c| <= 1), so a float32 rounding that is the same at c -+ (4 D + 32) 2^-53 is the answer, and otherwise the
+// warp evaluates the sequential chains.  Warp-cooperative; all lanes return the value.
+__device__ __forceinline__ float exact_negcos(const float *__restrict__ a, const void *__restrict__ gal, int gdt, int64_t b0,
+                                              int D, int lane)
+{
+    double dot = 0.0, na = 0.0, nb = 0.0;
+    for (int k = lane; k < D; k += 32) {
         const double x = a[k], y = ld_feat(gal, gdt, b0 + k);
-        dot = __dadd_rn(dot, __dmul_rn(x, y));
-        na = __dadd_rn(na, __dmul_rn(x, x));
-        nb = __dadd_rn(nb, __dmul_rn(y, y));
+        dot += x * y; na += x * x; nb += y * y;
     }
-    const double den = __dmul_rn(sqrt(na), sqrt(nb));
-    return 0.f - (den > 0.0 ? static_cast<float>(dot / den) : 0.f);   // 0 - c: never -0 (packed order)
+    dot = warp_sum(dot); na = warp_sum(na); nb = warp_sum(nb);
+    const double den = sqrt(na) * sqrt(nb);
+    if (!(den > 0.0)) return 0.f;                            // a zero row (the same in any summation order)
+    const double c = dot / den, dc = (4.0 * D + 32.0) * 1.1102230246251565e-16;
+    const float lo = static_cast<float>(__dadd_rd(c, -dc)), hi = static_cast<float>(__dadd_ru(c, dc));
+    if (lo == hi) return 0.f - lo;                           // 0 - c: never -0 (packed order)
+    return warp_seq_negcos(a, gal, gdt, b0, D, lane);
 }
 
-// One thread, one pair.
-__device__ __forceinline__ float exact_score(const RerankParams &p, int64_t row, int64_t g)
+__device__ __forceinline__ float exact_score(const RerankParams &p, int64_t row, int64_t g, int lane)
 {
-    if (p.metric == EOSVR_METRIC_COSINE) return exact_negcos(p.probes + row * p.D, p.gal, p.gal_dtype, g, p.D);
-    return exact_t(p.probes, p.P, p.D, p.rpe, row, p.gal, p.gal_dtype, g, p.lam1, p.lam2);
+    if (p.metric == EOSVR_METRIC_COSINE) return exact_negcos(p.probes + row * p.D, p.gal, p.gal_dtype, g * p.D, p.D, lane);
+    return exact_t(p.probes, p.P, p.D, p.rpe, row, p.gal, p.gal_dtype, g * p.D, p.lam1, p.lam2, lane);
 }
 
-// Hand a pair to k_exact_jobs.  A full job list sends the row to the exhaustive evaluation in k_finish (correct,
-// slow; the list holds 4 jobs per probe row plus the whole spill-over buffer, the re-rank emits ~1 per row).
-__device__ __forceinline__ void push_job(const RerankParams &p, int32_t row, int32_t g)
-{
-    const unsigned pos = atomicAdd(&p.ctr->job_count, 1u);
-    if (pos < static_cast<unsigned>(p.job_cap)) {
-        ExactJob j;
-        j.row = row; j.g = g;
-        p.jobs[pos] = j;
-    } else {
-        p.rowflag[row] = 1;
-        p.ctr->overflow = 1u;
-    }
-}
-
-// Spill-over candidates (row lists that filled up): one thread per entry, grid-strided over the threads of the
-// calling kernel; the survivors of the row's FINAL threshold become exact jobs.  Nothing to do when the buffer is
-// empty (the normal case).
-__device__ __forceinline__ void rerank_spilled(const RerankParams &p, int64_t thread_id, int64_t n_threads)
+// Spill-over candidates (row lists that filled up): one warp per entry, grid-strided over the warps of the
+// calling kernel.  Nothing to do when the buffer is empty (the normal case).
+__device__ __forceinline__ void rerank_spilled(const RerankParams &p, int64_t warp_id, int64_t n_warps, int lane)
 {
     const unsigned cnt = p.ctr->ovf_count;
     if (cnt == 0) return;
     const int64_t n = cnt < static_cast<unsigned>(p.ovf_cap) ? cnt : p.ovf_cap;
-    for (int64_t i = thread_id; i < n; i += n_threads) {
-        const OvfCand c = p.ovf[i];
+    unsigned long long done = 0;
+    for (int64_t w = warp_id; w < n; w += n_warps) {
+        const OvfCand c = p.ovf[w];
         if (c.tbits != kCandUnsafe && __uint_as_float(c.tbits) > __uint_as_float(p.gthr[c.p])) continue;
-        push_job(p, c.p, c.g);
+        const float t = exact_score(p, c.p, c.g, lane);
+        if (lane == 0) { atomicMin(p.best + c.p, pack_score_idx(t, static_cast<uint32_t>(p.offset + c.g))); ++done; }
     }
+    if (lane == 0 && done) atomicAdd(&p.ctr->n_exact, done);
 }
 
-// Exact evaluation of the listed pairs, one thread per pair, merged by packed 64-bit atomicMin.
-constexpr int kJobThreads = 32;
-__global__ void __launch_bounds__(kJobThreads)
-k_exact_jobs(const RerankParams p)
-{
-    const unsigned cnt = p.ctr->job_count;
-    const int64_t n = cnt < static_cast<unsigned>(p.job_cap) ? cnt : p.job_cap;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&p.ctr->n_exact, static_cast<unsigned long long>(n));
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kJobThreads + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * kJobThreads) {
-        const ExactJob j = p.jobs[i];
-        const float t = exact_score(p, j.row, j.g);
-        atomicMin(p.best + j.row, pack_score_idx(t, static_cast<uint32_t>(p.offset + j.g)));
-    }
-}
-
-// Generic re-rank (feature dimensions k_rerank_rows does not take): one warp per probe row, every candidate still
-// below the row's FINAL threshold becomes an exact job.
+// One warp per probe row: keep the candidates still below the row's FINAL threshold, evaluate them
+// exactly, and keep the smallest packed (score, index).  The three probe rows stay in L1 across the
+// row's candidates.
 __global__ void k_rerank(const RerankParams p)
 {
     const int lane = threadIdx.x & 31;
     const int64_t nw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-    unsigned long long appended = 0, uns = 0;
+    unsigned long long appended = 0, done = 0, uns = 0;
     for (int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < p.P; row += nw) {
         const unsigned cnt = p.rowcnt[row];
         const int n = cnt < static_cast<unsigned>(p.cand_cap) ? static_cast<int>(cnt) : p.cand_cap;
         appended += cnt;
         const float thr = __uint_as_float(p.gthr[row]);
         const Cand *list = p.cand + row * p.cand_cap;
+        unsigned long long loc = ~0ull;
         for (int b0 = 0; b0 < n; b0 += 32) {
             Cand c;
             c.g = 0; c.tbits = 0x7f800000u;
             if (b0 + lane < n) c = list[b0 + lane];
             const bool keep = (b0 + lane < n) && (c.tbits == kCandUnsafe || __uint_as_float(c.tbits) <= thr);
-            if (keep) push_job(p, static_cast<int32_t>(row), c.g);
-            uns += __popc(__ballot_sync(0xffffffffu, keep && c.tbits == kCandUnsafe));
+            unsigned m = __ballot_sync(0xffffffffu, keep);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int32_t g = __shfl_sync(0xffffffffu, c.g, src);
+                const uint32_t tb = __shfl_sync(0xffffffffu, c.tbits, src);
+                const float t = exact_score(p, row, g, lane);
+                const unsigned long long v = pack_score_idx(t, static_cast<uint32_t>(p.offset + g));
+                loc = v < loc ? v : loc;
+                ++done; uns += (tb == kCandUnsafe);
+            }
         }
+        if (lane == 0 && loc != ~0ull) atomicMin(p.best + row, loc);
     }
     if (lane == 0) {
         if (appended) atomicAdd(&p.ctr->cand_count, appended);
+        if (done) atomicAdd(&p.ctr->n_exact, done);
         if (uns) atomicAdd(&p.ctr->n_unsafe, uns);
     }
-    rerank_spilled(p, static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x, static_cast<int64_t>(gridDim.x) * blockDim.x);
+    rerank_spilled(p, (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, nw, lane);
 }
 
 // Block-per-row re-rank, warp-per-candidate.  The three probe rows the taps need are staged in shared memory
@@ -1351,12 +1401,18 @@ __global__ void k_rerank(const RerankParams p)
 //       differences (relative error of the smoothed value < kF32Rel, orders of magnitude tighter than the 16-bit
 //       screening) and tightening the shared bound; a warp stops as soon as the next screening value cannot win;
 //   (2) the candidates within 2*kF32Rel of the best float32 value -- the winner and its exact ties, normally ONE
-//       candidate -- become exact jobs: k_exact_jobs evaluates them exactly as the reference does (float64 direct
-//       differences summed in scipy's sequential order -> float32 -> float32 FMA chain), one thread per pair, and
-//       merges by packed 64-bit atomicMin.
+//       candidate -- are evaluated exactly as the reference does (float64 direct differences, scipy's rounding by
+//       the filter of taps_f32 -> float32 -> float32 FMA chain) and merged by packed 64-bit atomicMin.
 // No block-wide barrier sits between candidates, the gallery-row loads of the warps overlap, and float64 work
 // (conversions run at 16/clk/SM) is spent only where it decides the answer.
 constexpr int kRrThreads = 128;
+#ifndef EOSVR_RR_MINBLOCKS
+#define EOSVR_RR_MINBLOCKS 6
+#endif
+// resident blocks per SM the compiler must allow: the kernel is bound by the latency of a row's dependent steps, so
+// occupancy is what it needs (cfg-3 / cfg-2: 128 registers = 4 blocks 0.198 / 0.444 ms; 80 registers = 6 blocks 0.165 / 0.394 ms;
+// 64 registers = 8 blocks spills and loses: 0.186 ms on cfg-3 -- profiles/r02_ab_rerank_occupancy.txt)
+constexpr int kRrMinBlocks = EOSVR_RR_MINBLOCKS;
 constexpr float kF32Rel = 32.0f / 16777216.0f;   // 32 ulp: |t32 - t_reference| <= kF32Rel * t
 
 constexpr float kF32AbsCos = 64.0f / 16777216.0f;   // |cos32 - cos_reference| <= 64 ulp(1) absolute
@@ -1376,7 +1432,7 @@ __device__ __forceinline__ float o2f(unsigned int b)
 constexpr int kRrRowsPerBlock = 8;   // consecutive probe rows per block: neighbours are staged once (sliding window)
 
 template <bool COS>
-__global__ void __launch_bounds__(kRrThreads)
+__global__ void __launch_bounds__(kRrThreads, kRrMinBlocks)
 k_rerank_rows(const RerankParams p)
 {
     extern __shared__ float4 s_probe4[];          // ring of 4 probe rows [4][D/4]: row q lives in slot q % 4  (COS: 2 rows)
@@ -1387,9 +1443,10 @@ k_rerank_rows(const RerankParams p)
     __shared__ int s_next, s_n32;
     __shared__ unsigned int s_cnt[kRrRowsPerBlock];
     __shared__ float s_thr[kRrRowsPerBlock], s_eps[kRrRowsPerBlock];
+    __shared__ double s_part64[kRrThreads / 32][3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int D4 = p.D >> 2;
-    unsigned long long appended = 0, unsafe_n = 0;
+    const int D = p.D, D4 = p.D >> 2;
+    unsigned long long appended = 0, done = 0, unsafe_n = 0;
     const float inv_lam2 = 1.0f / p.lam2;
     const float4 *probes4 = reinterpret_cast<const float4 *>(p.probes);
     const int rpb = p.rows_per_block;
@@ -1440,6 +1497,7 @@ k_rerank_rows(const RerankParams p)
         const float thr = s_thr[row - r0];
         const float eps1 = s_eps[row - r0];
         const Cand *list = p.cand + row * p.cand_cap;
+        unsigned long long loc = ~0ull;
         if (tid == 0) { s_bound = __float_as_uint(thr); s_best32 = f2o(INFINITY); }
         __syncthreads();
         RR_MARK(c_setup);
@@ -1544,16 +1602,77 @@ k_rerank_rows(const RerankParams p)
             }
             __syncthreads();
             RR_MARK(c_p1);
-            // ---- (2) everything within the float32 error of the best float32 value -- the winner and its exact
-            //      ties, normally ONE candidate -- goes to k_exact_jobs, which evaluates it in the reference's order ----
+            // ---- (2) exact evaluation of everything within the float32 error of the best float32 value ----
             const int n32 = s_n32;
             const float best32 = o2f(s_best32);
             const float cut = COS ? best32 + 2.0f * kF32AbsCos : best32 * (1.0f + 2.0f * kF32Rel);
-            for (int j = tid; j < n32; j += kRrThreads)
-                if (s_t[j] <= cut) push_job(p, static_cast<int32_t>(row), s_g[j]);
+            for (int j = 0; j < n32; ++j) {                              // normally ONE candidate: the whole block on it
+                if (!(s_t[j] <= cut)) continue;                          // block-uniform
+                const int32_t g = s_g[j];
+                const int64_t gp = static_cast<int64_t>(g) * D4;
+                const int gdt = p.gal_dtype;
+                double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+                if (COS) {
+                    for (int k = tid; k < D4; k += kRrThreads) {
+                        const float4 b = ld_feat4(p.gal, gdt, gp + k);
+                        const float4 q = sp1[k];
+                        const double bb[4] = {b.x, b.y, b.z, b.w}, qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { y0 += qq[e] * bb[e]; y1 += bb[e] * bb[e]; y2 += qq[e] * qq[e]; }
+                    }
+                } else {
+                    for (int k = tid; k < D4; k += kRrThreads) {
+                        const float4 b = ld_feat4(p.gal, gdt, gp + k);
+                        const float4 q0 = sp0[k], q1 = sp1[k], q2 = sp2[k];
+                        const double bb[4] = {b.x, b.y, b.z, b.w};
+                        const float qq0[4] = {q0.x, q0.y, q0.z, q0.w}, qq1[4] = {q1.x, q1.y, q1.z, q1.w},
+                                    qq2[4] = {q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const double e0 = static_cast<double>(qq0[e]) - bb[e];
+                            const double e1 = static_cast<double>(qq1[e]) - bb[e];
+                            const double e2 = static_cast<double>(qq2[e]) - bb[e];
+                            y0 += e0 * e0; y1 += e1 * e1; y2 += e2 * e2;
+                        }
+                    }
+                }
+                y0 = warp_sum(y0); y1 = warp_sum(y1); y2 = warp_sum(y2);
+                if (lane == 0) { s_part64[warp][0] = y0; s_part64[warp][1] = y1; s_part64[warp][2] = y2; }
+                __syncthreads();
+                if (warp == 0) {                                         // the whole warp: the fallback is warp-cooperative
+                    y0 = y1 = y2 = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kRrThreads / 32; ++w) { y0 += s_part64[w][0]; y1 += s_part64[w][1]; y2 += s_part64[w][2]; }
+                    float acc;
+                    if (COS) {
+                        // the float32 rounding of the fast value is the definition's unless a rounding boundary lies
+                        // within its error: then the warp evaluates the sequential chains (exact_negcos)
+                        const double den = sqrt(y2) * sqrt(y1);
+                        const double c = den > 0.0 ? y0 / den : 0.0, dc = (4.0 * p.D + 32.0) * 1.1102230246251565e-16;
+                        const float lo = static_cast<float>(__dadd_rd(c, -dc)), hi = static_cast<float>(__dadd_ru(c, dc));
+                        acc = 0.f - lo;
+                        if (den > 0.0 && lo != hi)
+                            acc = exact_negcos(reinterpret_cast<const float *>(sp1), p.gal, gdt, static_cast<int64_t>(g) * p.D, p.D, lane);
+                    } else {
+                        float d0, d1, d2;
+                        taps_f32(y0, y1, y2, hl, hr, reinterpret_cast<const float *>(sp0), reinterpret_cast<const float *>(sp1),
+                                 reinterpret_cast<const float *>(sp2), p.gal, gdt, static_cast<int64_t>(g) * p.D, p.D, lane, d0, d1, d2);
+                        acc = __fmul_rn(p.lam1, d0);
+                        acc = __fmaf_rn(p.lam2, d1, acc);
+                        acc = __fmaf_rn(p.lam1, d2, acc);
+                    }
+                    if (lane == 0) {
+                        const unsigned long long v = pack_score_idx(acc, static_cast<uint32_t>(p.offset + g));
+                        loc = v < loc ? v : loc;
+                        ++done;
+                    }
+                }
+                __syncthreads();
+            }
             __syncthreads();
             RR_MARK(c_p2);
         }
+        if (tid == 0 && loc != ~0ull) atomicMin(p.best + row, loc);
       }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
@@ -1562,10 +1681,14 @@ k_rerank_rows(const RerankParams p)
         atomicAdd(&p.ctr->cyc_mma_wait_full, c_p1); atomicAdd(&p.ctr->cyc_mma_wait_acc, c_p2);
     }
 #undef RR_MARK
-    if (tid == 0 && appended) atomicAdd(&p.ctr->cand_count, appended);
+    if (tid == 0) {
+        if (appended) atomicAdd(&p.ctr->cand_count, appended);
+        if (done) atomicAdd(&p.ctr->n_exact, done);
+    }
     unsafe_n = static_cast<unsigned long long>(warp_sum(static_cast<double>(unsafe_n)));
     if (lane == 0 && unsafe_n) atomicAdd(&p.ctr->n_unsafe, unsafe_n);
-    rerank_spilled(p, static_cast<int64_t>(blockIdx.x) * kRrThreads + tid, static_cast<int64_t>(gridDim.x) * kRrThreads);
+    rerank_spilled(p, static_cast<int64_t>(blockIdx.x) * (kRrThreads / 32) + warp,
+                   static_cast<int64_t>(gridDim.x) * (kRrThreads / 32), lane);
 }
 
 __device__ __forceinline__ void finalize_row(const unsigned long long *best, int64_t i, int negate,
@@ -1582,7 +1705,7 @@ __device__ __forceinline__ void finalize_row(const unsigned long long *best, int
 // are first resolved by exhaustive exact evaluation: every block derives the same ordered list of flagged rows,
 // the grid shares the (row, strip of gallery rows) work items, and the LAST block to finish unpacks the winners
 // (its atomic ticket orders it after every other block's atomicMin).
-constexpr int kStrip = 32;         // gallery rows per warp work item in the exhaustive evaluation (one per lane)
+constexpr int kStrip = 8;          // gallery rows per warp work item in the exhaustive evaluation
 constexpr int kFinThreads = 256;
 constexpr int kMaxFlagList = 2048;
 
@@ -1622,19 +1745,17 @@ k_finish(const RerankParams p, int negate, uint64_t *out_packed, float *out_scor
         if (s_n <= kMaxFlagList) { nrows = s_n; listed = true; }
         if (blockIdx.x == 0 && tid == 0) p.ctr->n_flag_rows = static_cast<unsigned>(s_n);
     } else if (blockIdx.x == 0 && tid == 0) p.ctr->n_flag_rows = static_cast<unsigned>(p.P);
-    // one warp per (row, strip of 32 gallery rows): a lane evaluates ONE pair sequentially (the reference's order)
     const int64_t nstrips = (p.G + kStrip - 1) / kStrip;
     const int64_t nw = static_cast<int64_t>(gridDim.x) * (kFinThreads / 32);
     for (int64_t w = static_cast<int64_t>(blockIdx.x) * (kFinThreads / 32) + warp; w < nrows * nstrips; w += nw) {
         const int64_t row = listed ? s_list[w / nstrips] : w / nstrips;
         if (!listed && mode == 1 && p.rowflag[row] == 0) continue;
-        const int64_t g = (w % nstrips) * kStrip + lane;
+        const int64_t g0 = (w % nstrips) * kStrip, g1 = min(g0 + kStrip, p.G);
         unsigned long long loc = ~0ull;
-        if (g < p.G) loc = pack_score_idx(exact_score(p, row, g), static_cast<uint32_t>(p.offset + g));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, loc, o);
-            loc = other < loc ? other : loc;
+        for (int64_t g = g0; g < g1; ++g) {
+            const float t = exact_score(p, row, g, lane);
+            const unsigned long long v = pack_score_idx(t, static_cast<uint32_t>(p.offset + g));
+            loc = v < loc ? v : loc;
         }
         if (lane == 0) atomicMin(p.best + row, loc);
     }
@@ -1873,7 +1994,6 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
     rp.ctr = ws->counters; rp.gthr = ws->gthr;
     rp.best = ws->best; rp.rowflag = ws->rowflag;
     rp.ovf = ws->ovf; rp.ovf_cap = static_cast<int32_t>(ws->ovf_cap);
-    rp.jobs = reinterpret_cast<ExactJob *>(ws->jobs); rp.job_cap = static_cast<int32_t>(ws->job_cap);
     rp.epsd = ws->epsd; rp.wl = ws->wl; rp.wr = ws->wr; rp.planR = pl.R; rp.planBN = pl.BN; rp.planHalo = pl.halo;
     rp.prof = (tn.exp & 64) ? 1 : 0;
     rp.rows_per_block = 1;
@@ -1939,16 +2059,9 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
         }
         else k_rerank<<<num_sms * 8, 256, 0, st>>>(rp);
         EOSVR_CUDA(cudaGetLastError());
-        // the exact jobs of the re-rank (about one per probe row; grid-strided, so a longer list only takes longer)
-        {
-            const int64_t jb = (2 * P + kJobThreads - 1) / kJobThreads;
-            const unsigned jgrid = static_cast<unsigned>(jb < static_cast<int64_t>(num_sms) * 32 ? jb : num_sms * 32);
-            k_exact_jobs<<<jgrid, kJobThreads, 0, st>>>(rp);
-            EOSVR_CUDA(cudaGetLastError());
-        }
         rc = timing_end(ws, EOSVR_KERNEL_RERANK, st);
         if (rc) return rc;
-        EOSVR_COUNT_LAUNCH(2);
+        EOSVR_COUNT_LAUNCH(1);
     }
     rc = timing_begin(ws, EOSVR_KERNEL_FINISH, st);
     if (rc) return rc;

@@ -159,8 +159,9 @@ def test_candidate_overflow_paths():
 def test_order_sensitive_pairs(golden_dir, D):
     """Pairs constructed so that the float64 sum of squared differences sits within a few ulps of a float32
     rounding boundary (oracle/make_order_cases.py; scipy's value recorded): any summation order but scipy's
-    sequential one rounds most of them to the neighbouring float32.  The matcher (screened and exhaustive) and
-    the prototype scorer must return scipy's float32 bit for bit."""
+    sequential one rounds most of them to the neighbouring float32, so these pairs take the kernels' rare path
+    (fast sum undecided -> the warp evaluates scipy's sequential chain).  The matcher (screened and exhaustive)
+    and the prototype scorer must return scipy's float32 bit for bit."""
     fx = np.load(os.path.join(golden_dir, "golden_order_sensitive.npz"))
     A, B, want = fx[f"A{D}"], fx[f"B{D}"], fx[f"d64_{D}"].astype(np.float32)
     n = A.shape[0]
@@ -209,8 +210,9 @@ def test_tensor_core_accumulation_term(D):
     all-positive features (no cancellation, the partial sums are as large as they get) that are exact in float16,
     so the rounding-residual terms of the bound vanish and the accumulation term stands alone."""
     rng = np.random.RandomState(500 + D)
-    A = (rng.randint(0, 64, size=(40, D)) / 1024.0).astype(np.float32)
-    gal = (rng.randint(0, 64, size=(1500, D)) / 1024.0).astype(np.float32)
+    scale = 1.6 / np.sqrt(D)                                          # row norms ~1: the regime of the real features
+    A = rng.uniform(0.25 * scale, scale, size=(40, D)).astype(np.float16).astype(np.float32)      # full 11-bit mantissas
+    gal = rng.uniform(0.25 * scale, scale, size=(1500, D)).astype(np.float16).astype(np.float32)
     assert np.array_equal(A.astype(np.float16).astype(np.float32), A)
     cache = ev.GalleryFeatureCache(_cuda(gal))
     ws = ev.MatchWorkspace(A.shape[0], D)
@@ -222,13 +224,14 @@ def test_tensor_core_accumulation_term(D):
     xt = dbg.cpu().numpy().astype(np.float64) ** 2
     A64, B64 = A.astype(np.float64), gal.astype(np.float64)
     na, nb = (A64 * A64).sum(1), (B64 * B64).sum(1)
-    x = na[:, None] + nb[None, :] - 2.0 * (A64 @ B64.T)             # exact to ~1e-15: the inputs are 6-bit integers / 1024
+    x = na[:, None] + nb[None, :] - 2.0 * (A64 @ B64.T)             # float64: ~1e-15, eight orders below the bound
     ulp, Dp, B2 = 2.0 ** -22, (D + 63) // 64 * 64, nb.max()
     bound = 1.01 * (2 * ulp * (Dp / 16 + 1) * (np.sqrt(na * B2) + 0.5 * B2) + 2 * ulp * (na + B2))
-    err = np.abs(xt - x) - 1e-6 * x                                  # sqrt.approx and the float32 dump: 2^-21 relative
+    raw = np.abs(xt - x)
+    err = raw - 1e-6 * np.abs(xt)                                    # sqrt.approx and the float32 dump: 2^-21 relative
     worst = (err / bound[:, None]).max()
-    assert worst < 1.0, worst
-    print(f"accumulation term D={D}: worst observed error / bound = {worst:.3f}")
+    assert raw.max() > 0 and worst < 1.0, (raw.max(), worst)
+    print(f"accumulation term D={D}: worst observed error / bound = {worst:.3f} (largest error {raw.max():.3e}, bound {bound.min():.3e})")
 
 
 def test_empty_and_errors():
@@ -620,8 +623,7 @@ def test_native_bf16_storage(D, G):
 
 def test_episode_batch_one_call_equals_two_calls():
     """eosvr_episode_batch (one ABI call, caller-provided outputs) == eosvr_match + eosvr_episode_score, for both
-    metrics, and it launches 7 kernels (probe prep, seed pass, screening, re-rank, exact jobs, finish, fused splice +
-    ProtoNet)."""
+    metrics, and it launches 6 kernels (probe prep, seed pass, screening, re-rank, finish, fused splice + ProtoNet)."""
     E, n_way, S, D, G = 40, 5, 4, 512, 30000
     ep = synth.episode_batch(81, E, n_way, 1, S, D)
     cache = ev.GalleryFeatureCache(_cuda(synth.gallery(82, G, D, centroid_seed=81)))
@@ -632,7 +634,7 @@ def test_episode_batch_one_call_equals_two_calls():
         n0 = int(ev.lib().eosvr_launch_count())
         r = pipe.run(p, y, q, reuse_outputs=True)
         launches = int(ev.lib().eosvr_launch_count()) - n0
-        assert launches == 7, launches
+        assert launches == 6, launches
         idx, score = ev.match_segments(cache, pipe.ws, p.reshape(-1, D), n_way * S, metric=metric)
         two = ev.episode_score(p.reshape(-1, D), y, q, n_way, S, gallery=cache, idx=idx, max_proto=n_way)
         assert torch.equal(r["idx"].reshape(-1), idx) and torch.equal(r["score"].reshape(-1), score)
