@@ -245,8 +245,10 @@ def kernel_table(cfg, kernel_ms, stats, G_local, peaks):
         "probe_prep": ("hbm", P * D * 4 + P * D * 2),
         "seed": ("tensor", None),
         "screen": ("tensor", 2.0 * P * G_local * D),
-        # bytes: every probe row once (+ its two neighbours from the staged ring) + one gallery row per float32 evaluation
-        "rerank": ("hbm", P * D * 4 + max(stats.get("candidates", 0), exact) * D * 4),
+        # bytes: every probe row once (+ its two neighbours from the staged ring) + the candidate lists + one gallery row
+        # per float32 evaluation (counted by the kernel: candidates above the tightening bound are never read) and per
+        # exact evaluation.  The kernel is bound by the latency of a row's dependent steps, not by these bytes.
+        "rerank": ("hbm", P * D * 4 + stats.get("candidates", 0) * 8 + (stats.get("f32_evals", 0) + exact) * D * 4),
         "finish": ("hbm", P * (8 + 8 + 4 + 8)),
         # bytes: probe rows + winner rows + queries read (2 n S D 4 + Q D 4 per episode)
         "episode": ("hbm", E * (2 * n * S * D * 4 + D * 4)),

@@ -52,6 +52,7 @@ SIGNATURES = {
     "eosvr_match": (_c.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _vp]),
     "eosvr_match_exact": (_c.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _vp]),
     "eosvr_match_stats": (_c.c_int, [_vp, _vp, _c.POINTER(_i64)]),
+    "eosvr_match_stats_ex": (_c.c_int, [_vp, _vp, _c.POINTER(_i64), _c.c_int32]),
     "eosvr_workspace_debug_cycles": (_c.c_int, [_vp, _vp, _c.POINTER(_i64)]),
     "eosvr_merge_top1": (_c.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "eosvr_gather_rows": (_c.c_int, [_vp, _vp, _i64, _vp, _vp]),

@@ -430,6 +430,19 @@ int eosvr_match_stats(eosvr_workspace_t *ws, void *stream, int64_t out[8])
     return EOSVR_OK;
 }
 
+int eosvr_match_stats_ex(eosvr_workspace_t *ws, void *stream, int64_t *out, int32_t n)
+{
+    if (!ws || !out || n < 0) { set_error("match_stats_ex: bad argument"); return EOSVR_EINVAL; }
+    Counters c;
+    EOSVR_CUDA(cudaMemcpyAsync(&c, ws->counters, sizeof(c), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    EOSVR_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    const int64_t v[9] = {static_cast<int64_t>(c.cand_count), static_cast<int64_t>(c.n_exact), c.n_flag_rows,
+                          ws->cand_cap * ws->maxP, ws->last_tiles, ws->last_bn, static_cast<int64_t>(c.n_unsafe),
+                          c.ovf_count, static_cast<int64_t>(c.n_eval32)};
+    for (int i = 0; i < n; ++i) out[i] = i < 9 ? v[i] : 0;
+    return EOSVR_OK;
+}
+
 int eosvr_workspace_debug_cycles(eosvr_workspace_t *ws, void *stream, int64_t out[8])
 {
     if (!ws || !out) { set_error("debug_cycles: NULL argument"); return EOSVR_EINVAL; }

@@ -101,6 +101,7 @@ struct Counters {
     // cycle accounting of the screening kernel (EOSVR_EXP bit 16; measurement only), summed over CTAs
     unsigned long long cyc_epi_busy, cyc_epi_wait, cyc_mma_wait_full, cyc_mma_wait_acc, cyc_prod_wait, cyc_total;
     unsigned long long cyc_epi_pre, cyc_epi_loop;   // epilogue busy time split: before / inside the chunk loop of a tile
+    unsigned long long n_eval32;     // candidates the re-rank evaluated in float32 (one gallery row read each)
 };
 
 }  // namespace eosvr

@@ -1246,12 +1246,31 @@ __device__ __forceinline__ float exact_t(const float *__restrict__ probes, int64
     const float *a0 = hl ? a1 - D : a1;
     const float *a2 = hr ? a1 + D : a1;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int k = lane; k < D; k += 32) {
-        const double bv = ld_feat(gal, gdt, b0 + k);
-        const double e0 = static_cast<double>(a0[k]) - bv;
-        const double e1 = static_cast<double>(a1[k]) - bv;
-        const double e2 = static_cast<double>(a2[k]) - bv;
-        s0 += e0 * e0; s1 += e1 * e1; s2 += e2 * e2;
+    if ((D & 3) == 0) {                                  // 16-byte loads (every row starts 16-byte aligned then)
+        const float4 *a04 = reinterpret_cast<const float4 *>(a0), *a14 = reinterpret_cast<const float4 *>(a1),
+                     *a24 = reinterpret_cast<const float4 *>(a2);
+        const int64_t b04 = b0 >> 2;
+        for (int k = lane; k < (D >> 2); k += 32) {
+            const float4 b = ld_feat4(gal, gdt, b04 + k);
+            const float4 q0 = a04[k], q1 = a14[k], q2 = a24[k];
+            const double bb[4] = {b.x, b.y, b.z, b.w};
+            const float qq0[4] = {q0.x, q0.y, q0.z, q0.w}, qq1[4] = {q1.x, q1.y, q1.z, q1.w}, qq2[4] = {q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const double e0 = static_cast<double>(qq0[e]) - bb[e];
+                const double e1 = static_cast<double>(qq1[e]) - bb[e];
+                const double e2 = static_cast<double>(qq2[e]) - bb[e];
+                s0 += e0 * e0; s1 += e1 * e1; s2 += e2 * e2;
+            }
+        }
+    } else {
+        for (int k = lane; k < D; k += 32) {
+            const double bv = ld_feat(gal, gdt, b0 + k);
+            const double e0 = static_cast<double>(a0[k]) - bv;
+            const double e1 = static_cast<double>(a1[k]) - bv;
+            const double e2 = static_cast<double>(a2[k]) - bv;
+            s0 += e0 * e0; s1 += e1 * e1; s2 += e2 * e2;
+        }
     }
     s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
     float d0, d1, d2;
@@ -1446,7 +1465,7 @@ k_rerank_rows(const RerankParams p)
     __shared__ double s_part64[kRrThreads / 32][3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = p.D, D4 = p.D >> 2;
-    unsigned long long appended = 0, done = 0, unsafe_n = 0;
+    unsigned long long appended = 0, done = 0, unsafe_n = 0, ev32 = 0;   // ev32: per lane-0 thread
     const float inv_lam2 = 1.0f / p.lam2;
     const float4 *probes4 = reinterpret_cast<const float4 *>(p.probes);
     const int rpb = p.rows_per_block;
@@ -1595,6 +1614,7 @@ k_rerank_rows(const RerankParams p)
                         nb = fmaf(acc * (1.0f + kF32Rel) * inv_lam2, 1.00002f, eps1);
                     }
                     const int i32 = atomicAdd(&s_n32, 1);
+                    ++ev32;
                     s_g[i32] = g; s_t[i32] = acc;
                     atomicMin(&s_best32, f2o(acc));
                     atomicMin(&s_bound, __float_as_uint(nb));
@@ -1687,8 +1707,190 @@ k_rerank_rows(const RerankParams p)
     }
     unsafe_n = static_cast<unsigned long long>(warp_sum(static_cast<double>(unsafe_n)));
     if (lane == 0 && unsafe_n) atomicAdd(&p.ctr->n_unsafe, unsafe_n);
+    if (lane == 0 && ev32) atomicAdd(&p.ctr->n_eval32, ev32);
     rerank_spilled(p, static_cast<int64_t>(blockIdx.x) * (kRrThreads / 32) + warp,
                    static_cast<int64_t>(gridDim.x) * (kRrThreads / 32), lane);
+}
+
+// -------------------------------------------------------------------------------------------
+// Warp-per-row re-rank (the default for 512-element rows; EOSVR_RR=0 / 1 forces one kernel or the other): the same
+// two steps with the same arithmetic as k_rerank_rows, but a probe row belongs to ONE warp, so nothing in a row's chain
+// of dependent steps waits at a block barrier; one resident wave of warps, each taking several rows.
+//   * candidates are read 32 at a time; the lanes keep what is still below the row's final threshold and the warp
+//     takes them in ascending order of their screening value (one REDUX per pick);
+//   * float32 evaluation of a candidate: the lanes stride the row exactly like k_rerank_rows (same per-lane FMA
+//     order, same butterfly: the kF32Rel bound is the same); the gallery row of the NEXT candidate in order is
+//     requested before the current one is reduced (the pick order does not depend on the results, only the stop does);
+//   * the probe rows come from global memory (L1 hits after the first candidate; neighbouring rows belong to the
+//     neighbouring warps of the block);
+//   * candidates within 2 kF32Rel of the best float32 value are evaluated exactly (exact_score: filtered float64).
+// -------------------------------------------------------------------------------------------
+constexpr int kRwWarps = 4;
+#ifndef EOSVR_RW_MINBLOCKS
+#define EOSVR_RW_MINBLOCKS 5
+#endif
+// BF: bfloat16 gallery rows; D512: the rows have exactly 512 elements (the metric's shape: every loop is static, the
+// loads are immediate offsets from one row pointer -- integer bookkeeping was half of the generic kernel's instructions)
+template <bool BF>
+__device__ __forceinline__ float4 ld_row4(const void *rowp, int k)
+{
+    if (!BF) return reinterpret_cast<const float4 *>(rowp)[k];
+    const uint2 u = reinterpret_cast<const uint2 *>(rowp)[k];
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u),
+                       __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+}
+
+template <bool COS, bool BF, bool D512>
+__global__ void __launch_bounds__(32 * kRwWarps, EOSVR_RW_MINBLOCKS)
+k_rerank_warp(const RerankParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * kRwWarps + (threadIdx.x >> 5);
+    const int64_t nw = static_cast<int64_t>(gridDim.x) * kRwWarps;
+    const int D4 = D512 ? 128 : (p.D >> 2);
+    const size_t row_bytes = static_cast<size_t>(D4) * (BF ? 8 : 16);
+    const char *galb = static_cast<const char *>(p.gal);
+    const float inv_lam2 = 1.0f / p.lam2;
+    const float4 *probes4 = reinterpret_cast<const float4 *>(p.probes);
+    unsigned long long appended = 0, done = 0, unsafe_n = 0, ev32 = 0;
+
+    // the row's counters and its first 32 candidates are requested one row ahead (the three loads are independent: the
+    // candidate slot is read whether or not it is filled), so a row does not start with two dependent round trips
+    unsigned cnt_n = 0, thr_n = 0;
+    Cand cand_n;
+    cand_n.g = 0; cand_n.tbits = 0x7f800000u;
+    if (warp0 < p.P) { cnt_n = p.rowcnt[warp0]; thr_n = p.gthr[warp0]; cand_n = p.cand[warp0 * p.cand_cap + lane]; }
+    for (int64_t row = warp0; row < p.P; row += nw) {
+        const unsigned cnt = cnt_n;
+        const unsigned thr_bits = thr_n;
+        const Cand first = cand_n;
+        if (row + nw < p.P) { cnt_n = p.rowcnt[row + nw]; thr_n = p.gthr[row + nw]; cand_n = p.cand[(row + nw) * p.cand_cap + lane]; }
+        const int n = cnt < static_cast<unsigned>(p.cand_cap) ? static_cast<int>(cnt) : p.cand_cap;
+        appended += cnt;
+        if (n == 0) continue;
+        const int r = static_cast<int>(row % p.rpe);
+        const bool hl = !COS && r > 0, hr = !COS && (r + 1 < p.rpe) && (row + 1 < p.P);
+        const float4 *a1 = probes4 + row * D4;
+        const float4 *a0 = hl ? a1 - D4 : a1;
+        const float4 *a2 = hr ? a1 + D4 : a1;
+        const float eps1 = 0.5f * column_margin(p.epsd, p.wl, p.wr, (row / p.planR) * p.planBN + p.planHalo + (row % p.planR));
+        float bound = __uint_as_float(thr_bits);                    // candidates above it cannot win (tightens)
+        float best32 = INFINITY;
+        unsigned long long loc = ~0ull;
+        const Cand *list = p.cand + row * p.cand_cap;
+
+        for (int b0 = 0; b0 < n; b0 += 32) {
+            Cand c;
+            c.g = 0; c.tbits = 0x7f800000u;
+            const bool in = b0 + lane < n;
+            if (in) c = b0 == 0 ? first : list[b0 + lane];
+            const bool isuns = in && c.tbits == kCandUnsafe;
+            // order key: unsafe candidates first (0), then the screening value's bits (t~ >= 0: float order == uint order)
+            unsigned key = isuns ? 0u : c.tbits;
+            bool keep = in && (isuns || __uint_as_float(c.tbits) <= bound);
+            unsafe_n += __popc(__ballot_sync(0xffffffffu, isuns));
+            // this lane's slot of the evaluated list of the batch
+            int32_t eg = 0; float et = INFINITY;
+            int nev = 0;
+            // pick the first candidate and request its row
+            unsigned kmin = __reduce_min_sync(0xffffffffu, keep ? key : 0xFFFFFFFFu);
+            int src = __ffs(__ballot_sync(0xffffffffu, keep && key == kmin)) - 1;
+            float4 gb[4];                                            // this lane's float4 groups k = lane + 32 i, i < 4, of the row
+            int32_t g = 0;
+            auto request = [&](int32_t gg) {
+                const void *rp = galb + static_cast<size_t>(gg) * row_bytes;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (D512 || lane + 32 * i < D4) gb[i] = ld_row4<BF>(rp, lane + 32 * i);
+            };
+            if (src >= 0) { g = __shfl_sync(0xffffffffu, c.g, src); request(g); }
+            while (src >= 0) {
+                // the picked candidate is lane src's; it leaves the set
+                const float tv = __uint_as_float(kmin);
+                if (lane == src) keep = false;
+                if (kmin != 0u && tv > bound) break;                 // ascending order: nothing later can win either
+                // ---- float32 evaluation (k_rerank_rows's arithmetic) ----
+                const int32_t gcur = g;
+                float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+                float4 cb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cb[i] = gb[i];
+                // next pick, its row requested before this one is reduced
+                kmin = __reduce_min_sync(0xffffffffu, keep ? key : 0xFFFFFFFFu);
+                src = __ffs(__ballot_sync(0xffffffffu, keep && key == kmin)) - 1;
+                if (src >= 0) { g = __shfl_sync(0xffffffffu, c.g, src); request(g); }
+                auto accum = [&](const float4 b, int k) {
+                    if (COS) {
+                        const float4 q = a1[k];
+                        x0 = fmaf(q.x, b.x, x0); x0 = fmaf(q.y, b.y, x0); x0 = fmaf(q.z, b.z, x0); x0 = fmaf(q.w, b.w, x0);
+                        x1 = fmaf(b.x, b.x, x1); x1 = fmaf(b.y, b.y, x1); x1 = fmaf(b.z, b.z, x1); x1 = fmaf(b.w, b.w, x1);
+                        x2 = fmaf(q.x, q.x, x2); x2 = fmaf(q.y, q.y, x2); x2 = fmaf(q.z, q.z, x2); x2 = fmaf(q.w, q.w, x2);
+                    } else {
+                        const float4 q0 = a0[k], q1 = a1[k], q2 = a2[k];
+                        float e;
+                        e = q0.x - b.x; x0 = fmaf(e, e, x0); e = q0.y - b.y; x0 = fmaf(e, e, x0);
+                        e = q0.z - b.z; x0 = fmaf(e, e, x0); e = q0.w - b.w; x0 = fmaf(e, e, x0);
+                        e = q1.x - b.x; x1 = fmaf(e, e, x1); e = q1.y - b.y; x1 = fmaf(e, e, x1);
+                        e = q1.z - b.z; x1 = fmaf(e, e, x1); e = q1.w - b.w; x1 = fmaf(e, e, x1);
+                        e = q2.x - b.x; x2 = fmaf(e, e, x2); e = q2.y - b.y; x2 = fmaf(e, e, x2);
+                        e = q2.z - b.z; x2 = fmaf(e, e, x2); e = q2.w - b.w; x2 = fmaf(e, e, x2);
+                    }
+                };
+                // (per lane the groups are taken in ascending k, as in k_rerank_rows: first the four requested ahead)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (D512 || lane + 32 * i < D4) accum(cb[i], lane + 32 * i);
+                if (!D512) {
+                    const void *rp = galb + static_cast<size_t>(gcur) * row_bytes;
+                    for (int k = lane + 128; k < D4; k += 32) accum(ld_row4<BF>(rp, k), k);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    x0 += __shfl_xor_sync(0xffffffffu, x0, o);
+                    x1 += __shfl_xor_sync(0xffffffffu, x1, o);
+                    x2 += __shfl_xor_sync(0xffffffffu, x2, o);
+                }
+                float acc, nb;
+                if (COS) {
+                    const float den = sqrtf(x2) * sqrtf(x1);
+                    acc = 0.f - (den > 0.f ? x0 / den : 0.f);
+                    nb = fmaf(sqrtf(fmaxf(2.0f + 2.0f * (acc + 2.0f * kF32AbsCos), 0.f)), 1.000001f, eps1);
+                } else {
+                    const float d0 = hl ? sqrtf(x0) : 0.f;
+                    const float d1 = sqrtf(x1);
+                    const float d2 = hr ? sqrtf(x2) : 0.f;
+                    acc = __fmul_rn(p.lam1, d0);
+                    acc = __fmaf_rn(p.lam2, d1, acc);
+                    acc = __fmaf_rn(p.lam1, d2, acc);
+                    nb = fmaf(acc * (1.0f + kF32Rel) * inv_lam2, 1.00002f, eps1);
+                }
+                if (lane == nev) { eg = gcur; et = acc; }
+                ++nev; ++ev32;
+                best32 = fminf(best32, acc);
+                bound = fminf(bound, nb);
+            }
+            // ---- exact evaluation of what is within the float32 error of the best float32 value ----
+            const float cut = COS ? best32 + 2.0f * kF32AbsCos : best32 * (1.0f + 2.0f * kF32Rel);
+            unsigned m2 = __ballot_sync(0xffffffffu, lane < nev && et <= cut);
+            while (m2) {
+                const int j = __ffs(m2) - 1;
+                m2 &= m2 - 1;
+                const int32_t gj = __shfl_sync(0xffffffffu, eg, j);
+                const float t = exact_score(p, row, gj, lane);
+                const unsigned long long v = pack_score_idx(t, static_cast<uint32_t>(p.offset + gj));
+                loc = v < loc ? v : loc;
+                ++done;
+            }
+        }
+        if (lane == 0 && loc != ~0ull) atomicMin(p.best + row, loc);
+    }
+    if (lane == 0) {
+        if (appended) atomicAdd(&p.ctr->cand_count, appended);
+        if (done) atomicAdd(&p.ctr->n_exact, done);
+        if (unsafe_n) atomicAdd(&p.ctr->n_unsafe, unsafe_n);
+        if (ev32) atomicAdd(&p.ctr->n_eval32, ev32);
+    }
+    rerank_spilled(p, warp0, nw, lane);
 }
 
 __device__ __forceinline__ void finalize_row(const unsigned long long *best, int64_t i, int negate,
@@ -1804,7 +2006,7 @@ int launch_merge(const uint64_t *gathered, int32_t nshards, int64_t P, uint64_t 
 // 16 (cycle accounting of the screening kernel) and 64 (phase timing of the re-rank).  The result-destroying
 // timing modes (EOSVR_EXP bits 1, 2, 4, 32) exist only in builds with -DEOSVR_EXPERIMENTS (tools/exp_perf.sh).
 struct Tunables {
-    int order, tpu, seed, ew, issuers, exp, aligned;
+    int order, tpu, seed, ew, issuers, exp, aligned, rr;
 };
 static int env_int(const char *name, int dflt)
 {
@@ -1822,6 +2024,7 @@ const Tunables &tunables()
         v.issuers = env_int("EOSVR_ISSUERS", 0);
         v.exp = env_int("EOSVR_EXP", 0);
         v.aligned = env_int("EOSVR_ALIGNED", 1);       // 0: never use the episode-aligned epilogue
+        v.rr = env_int("EOSVR_RR", -1);                // re-rank kernel: 0 block-per-rows, 1 warp-per-row, -1 chosen per call
 #ifndef EOSVR_EXPERIMENTS
         v.exp &= (16 | 64);
 #endif
@@ -2054,7 +2257,22 @@ int launch_match(eosvr_gallery *g, eosvr_workspace *ws, const float *probes, int
                     ds->rr_attr = true;
                 }
             }
-            if (cosm) k_rerank_rows<true><<<rr_grid, kRrThreads, rr_smem, st>>>(rp);
+            // warp-per-row where its static specialisation applies (512-element rows: cfg-3 / cfg-4 0.165 -> 0.098 ms);
+            // the block-per-rows kernel elsewhere (at D = 2048 the warp kernel is 1.6x slower: four warps share a
+            // candidate's 8 KiB row there) -- profiles/r02_ab_rerank_warp.txt
+            if (tn.rr == 1 || (tn.rr < 0 && g->D == 512)) {
+                // one resident wave: a warp takes several rows and requests a row's counters and candidates a row ahead
+                const int64_t wb = (P + kRwWarps - 1) / kRwWarps;
+                const unsigned wgrid = static_cast<unsigned>(wb < static_cast<int64_t>(num_sms) * EOSVR_RW_MINBLOCKS ? wb : num_sms * EOSVR_RW_MINBLOCKS);
+                const bool bf = g->dtype == EOSVR_BF16, d512 = g->D == 512;
+#define EOSVR_RW(C, B, X) k_rerank_warp<C, B, X><<<wgrid, 32 * kRwWarps, 0, st>>>(rp)
+                if (cosm) { if (bf) { if (d512) EOSVR_RW(true, true, true); else EOSVR_RW(true, true, false); }
+                            else { if (d512) EOSVR_RW(true, false, true); else EOSVR_RW(true, false, false); } }
+                else { if (bf) { if (d512) EOSVR_RW(false, true, true); else EOSVR_RW(false, true, false); }
+                       else { if (d512) EOSVR_RW(false, false, true); else EOSVR_RW(false, false, false); } }
+#undef EOSVR_RW
+            }
+            else if (cosm) k_rerank_rows<true><<<rr_grid, kRrThreads, rr_smem, st>>>(rp);
             else k_rerank_rows<false><<<rr_grid, kRrThreads, rr_smem, st>>>(rp);
         }
         else k_rerank<<<num_sms * 8, 256, 0, st>>>(rp);

@@ -25,14 +25,21 @@ for cfg in (bench.CFG3, bench.CFG2):
     for i in range(n): pipe.run(*ins[i %% 3], reuse_outputs=True)
     e.record(); torch.cuda.synchronize()
     km = {k: pipe.ws.kernel_ms(k) for k in ("screen", "rerank", "episode", "probe_prep")}
-    out[cfg["name"]] = dict(step=s.elapsed_time(e) / n, **{k: v[0] / max(v[1], 1) for k, v in km.items()})
+    st = pipe.ws.stats()
+    out[cfg["name"]] = dict(step=s.elapsed_time(e) / n, **{k: v[0] / max(v[1], 1) for k, v in km.items()},
+                            f32_per_row=st.get("f32_evals", 0) / (cfg["E"] * bench.rpe(cfg)), cand_per_row=st["candidates"] / (cfg["E"] * bench.rpe(cfg)))
     del cache, pipe, ins
 print("RESULT " + json.dumps(out))
 """
 
 
 def run(lib):
-    env = dict(os.environ, EOSVR_LIB_PATH=os.path.abspath(lib))
+    """lib: path[:ENV=VAL[:ENV=VAL...]] -- the same build can be compared under different knobs"""
+    parts = lib.split(":")
+    env = dict(os.environ, EOSVR_LIB_PATH=os.path.abspath(parts[0]))
+    for kv in parts[1:]:
+        k, v = kv.split("=", 1)
+        env[k] = v
     r = subprocess.run([sys.executable, "-c", CHILD % (ROOT, os.path.join(ROOT, "oracle"))], capture_output=True, text=True, env=env, timeout=900)
     for line in r.stdout.splitlines():
         if line.startswith("RESULT "):
@@ -50,4 +57,4 @@ if __name__ == "__main__":
     for cfg in res[libs[0]][0]:
         for l in libs:
             best = {k: min(r[cfg][k] for r in res[l]) for k in res[l][0][cfg]}
-            print(f"{cfg} {os.path.basename(l):24s} " + "  ".join(f"{k} {v:7.4f}" for k, v in best.items()), flush=True)
+            print(f"{cfg} {os.path.basename(l):34s} " + "  ".join(f"{k} {v:7.4f}" for k, v in best.items()), flush=True)
