@@ -436,10 +436,10 @@ int eosvr_match_stats_ex(eosvr_workspace_t *ws, void *stream, int64_t *out, int3
     Counters c;
     EOSVR_CUDA(cudaMemcpyAsync(&c, ws->counters, sizeof(c), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
     EOSVR_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
-    const int64_t v[9] = {static_cast<int64_t>(c.cand_count), static_cast<int64_t>(c.n_exact), c.n_flag_rows,
-                          ws->cand_cap * ws->maxP, ws->last_tiles, ws->last_bn, static_cast<int64_t>(c.n_unsafe),
-                          c.ovf_count, static_cast<int64_t>(c.n_eval32)};
-    for (int i = 0; i < n; ++i) out[i] = i < 9 ? v[i] : 0;
+    const int64_t v[10] = {static_cast<int64_t>(c.cand_count), static_cast<int64_t>(c.n_exact), c.n_flag_rows,
+                           ws->cand_cap * ws->maxP, ws->last_tiles, ws->last_bn, static_cast<int64_t>(c.n_unsafe),
+                           c.ovf_count, static_cast<int64_t>(c.n_eval32), static_cast<int64_t>(c.n_seq)};
+    for (int i = 0; i < n; ++i) out[i] = i < 10 ? v[i] : 0;
     return EOSVR_OK;
 }
 

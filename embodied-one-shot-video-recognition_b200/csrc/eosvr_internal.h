@@ -102,6 +102,7 @@ struct Counters {
     unsigned long long cyc_epi_busy, cyc_epi_wait, cyc_mma_wait_full, cyc_mma_wait_acc, cyc_prod_wait, cyc_total;
     unsigned long long cyc_epi_pre, cyc_epi_loop;   // epilogue busy time split: before / inside the chunk loop of a tile
     unsigned long long n_eval32;     // candidates the re-rank evaluated in float32 (one gallery row read each)
+    unsigned long long n_seq;        // exact evaluations the fast float64 sum could not decide (sequential chain taken)
 };
 
 }  // namespace eosvr

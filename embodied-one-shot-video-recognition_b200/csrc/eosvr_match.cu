@@ -1221,7 +1221,7 @@ __device__ __forceinline__ void warp_seq3(const float *a0, const float *a1, cons
 // shared or global memory.
 __device__ __forceinline__ void taps_f32(double y0, double y1, double y2, bool hl, bool hr, const float *a0, const float *a1,
                                          const float *a2, const void *__restrict__ gal, int gdt, int64_t b0, int D, int lane,
-                                         float &d0, float &d1, float &d2)
+                                         float &d0, float &d1, float &d2, unsigned long long *n_seq)
 {
     const double delta = seq_delta(D);
     bool ok = sqrt_f32_decided(y1, delta, d1);
@@ -1229,6 +1229,7 @@ __device__ __forceinline__ void taps_f32(double y0, double y1, double y2, bool h
     if (hl) ok = sqrt_f32_decided(y0, delta, d0) && ok;
     if (hr) ok = sqrt_f32_decided(y2, delta, d2) && ok;
     if (!ok) {                                               // warp-uniform
+        if (lane == 0 && n_seq) atomicAdd(n_seq, 1ull);      // (statistics: the tests check that the constructed pairs get here)
         double s0, s1, s2;
         warp_seq3(a0, a1, a2, gal, gdt, b0, D, lane, s0, s1, s2);
         d0 = hl ? static_cast<float>(sqrt(s0)) : 0.f;
@@ -1238,7 +1239,8 @@ __device__ __forceinline__ void taps_f32(double y0, double y1, double y2, bool h
 }
 
 __device__ __forceinline__ float exact_t(const float *__restrict__ probes, int64_t P, int D, int rpe,
-                                         int64_t p, const void *__restrict__ gal, int gdt, int64_t b0, float lam1, float lam2, int lane)
+                                         int64_t p, const void *__restrict__ gal, int gdt, int64_t b0, float lam1, float lam2, int lane,
+                                         unsigned long long *n_seq = nullptr)
 {
     const int r = static_cast<int>(p % rpe);
     const bool hl = r > 0, hr = (r + 1 < rpe) && (p + 1 < P);
@@ -1274,7 +1276,7 @@ __device__ __forceinline__ float exact_t(const float *__restrict__ probes, int64
     }
     s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
     float d0, d1, d2;
-    taps_f32(s0, s1, s2, hl, hr, a0, a1, a2, gal, gdt, b0, D, lane, d0, d1, d2);
+    taps_f32(s0, s1, s2, hl, hr, a0, a1, a2, gal, gdt, b0, D, lane, d0, d1, d2, n_seq);
     float acc = __fmul_rn(lam1, d0);
     acc = __fmaf_rn(lam2, d1, acc);
     acc = __fmaf_rn(lam1, d2, acc);
@@ -1332,7 +1334,7 @@ __device__ __forceinline__ float warp_seq_negcos(const float *a, const void *__r
 // errors, |c| <= 1), so a float32 rounding that is the same at c -+ (4 D + 32) 2^-53 is the answer, and otherwise the
 // warp evaluates the sequential chains.  Warp-cooperative; all lanes return the value.
 __device__ __forceinline__ float exact_negcos(const float *__restrict__ a, const void *__restrict__ gal, int gdt, int64_t b0,
-                                              int D, int lane)
+                                              int D, int lane, unsigned long long *n_seq = nullptr)
 {
     double dot = 0.0, na = 0.0, nb = 0.0;
     for (int k = lane; k < D; k += 32) {
@@ -1345,13 +1347,14 @@ __device__ __forceinline__ float exact_negcos(const float *__restrict__ a, const
     const double c = dot / den, dc = (4.0 * D + 32.0) * 1.1102230246251565e-16;
     const float lo = static_cast<float>(__dadd_rd(c, -dc)), hi = static_cast<float>(__dadd_ru(c, dc));
     if (lo == hi) return 0.f - lo;                           // 0 - c: never -0 (packed order)
+    if (lane == 0 && n_seq) atomicAdd(n_seq, 1ull);
     return warp_seq_negcos(a, gal, gdt, b0, D, lane);
 }
 
 __device__ __forceinline__ float exact_score(const RerankParams &p, int64_t row, int64_t g, int lane)
 {
-    if (p.metric == EOSVR_METRIC_COSINE) return exact_negcos(p.probes + row * p.D, p.gal, p.gal_dtype, g * p.D, p.D, lane);
-    return exact_t(p.probes, p.P, p.D, p.rpe, row, p.gal, p.gal_dtype, g * p.D, p.lam1, p.lam2, lane);
+    if (p.metric == EOSVR_METRIC_COSINE) return exact_negcos(p.probes + row * p.D, p.gal, p.gal_dtype, g * p.D, p.D, lane, &p.ctr->n_seq);
+    return exact_t(p.probes, p.P, p.D, p.rpe, row, p.gal, p.gal_dtype, g * p.D, p.lam1, p.lam2, lane, &p.ctr->n_seq);
 }
 
 // Spill-over candidates (row lists that filled up): one warp per entry, grid-strided over the warps of the
@@ -1672,11 +1675,11 @@ k_rerank_rows(const RerankParams p)
                         const float lo = static_cast<float>(__dadd_rd(c, -dc)), hi = static_cast<float>(__dadd_ru(c, dc));
                         acc = 0.f - lo;
                         if (den > 0.0 && lo != hi)
-                            acc = exact_negcos(reinterpret_cast<const float *>(sp1), p.gal, gdt, static_cast<int64_t>(g) * p.D, p.D, lane);
+                            acc = exact_negcos(reinterpret_cast<const float *>(sp1), p.gal, gdt, static_cast<int64_t>(g) * p.D, p.D, lane, &p.ctr->n_seq);
                     } else {
                         float d0, d1, d2;
                         taps_f32(y0, y1, y2, hl, hr, reinterpret_cast<const float *>(sp0), reinterpret_cast<const float *>(sp1),
-                                 reinterpret_cast<const float *>(sp2), p.gal, gdt, static_cast<int64_t>(g) * p.D, p.D, lane, d0, d1, d2);
+                                 reinterpret_cast<const float *>(sp2), p.gal, gdt, static_cast<int64_t>(g) * p.D, p.D, lane, d0, d1, d2, &p.ctr->n_seq);
                         acc = __fmul_rn(p.lam1, d0);
                         acc = __fmaf_rn(p.lam2, d1, acc);
                         acc = __fmaf_rn(p.lam1, d2, acc);

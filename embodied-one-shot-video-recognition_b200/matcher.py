@@ -170,9 +170,10 @@ class MatchWorkspace:
         return tot.value, n.value
 
     def stats(self, stream=None) -> dict:
-        out = (ctypes.c_int64 * 9)()
-        check(lib().eosvr_match_stats_ex(self._h, _stream_ptr(stream), out, 9), "eosvr_match_stats_ex")
-        keys = ["candidates", "exact_evals", "fallback_rows", "cand_capacity", "tiles", "mma_n", "unsafe", "spilled", "f32_evals"]
+        out = (ctypes.c_int64 * 10)()
+        check(lib().eosvr_match_stats_ex(self._h, _stream_ptr(stream), out, 10), "eosvr_match_stats_ex")
+        keys = ["candidates", "exact_evals", "fallback_rows", "cand_capacity", "tiles", "mma_n", "unsafe", "spilled", "f32_evals",
+                "sequential_evals"]
         return dict(zip(keys, [int(v) for v in out]))
 
     def debug_cycles(self, stream=None) -> dict:

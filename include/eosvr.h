@@ -137,7 +137,9 @@ int eosvr_match_exact(const eosvr_gallery_t *g, eosvr_workspace_t *ws, const flo
  * the shared buffer. */
 int eosvr_match_stats(eosvr_workspace_t *ws, void *stream, int64_t out[8]);
 /* The same counters, the first n of: out[0..7] as above, out[8] candidates the re-rank evaluated in float32 (one
- * gallery row read each: the re-rank's real traffic; later counters read 0). */
+ * gallery row read each: the re-rank's real traffic), out[9] exact evaluations whose float32 rounding the fast float64
+ * sum could not decide, so that the reference's sequential summation was evaluated (about 1e-6 of them; later
+ * counters read 0). */
 int eosvr_match_stats_ex(eosvr_workspace_t *ws, void *stream, int64_t *out, int32_t n);
 
 /* ---- multi-GPU shard merge (new) --------------------------------

@@ -170,6 +170,7 @@ def test_order_sensitive_pairs(golden_dir, D):
     assert np.array_equal(r["idx"], np.arange(n)) and np.array_equal(r["idx_exact"], np.arange(n))
     assert np.array_equal(r["score"], want), int((r["score"] != want).sum())
     assert np.array_equal(r["score_exact"], want), int((r["score_exact"] != want).sum())
+    assert r["stats"]["sequential_evals"] >= n, r["stats"]     # every constructed pair took the rare path in the re-rank
     oid, oval = O.c_match(A, gal, 4)                # with taps: every tap is one of the recorded distances or near one
     r4 = _match_both(A, gal, 4)
     assert np.array_equal(r4["idx"], oid) and np.array_equal(r4["score"], oval)

@@ -195,3 +195,32 @@ def test_order_sensitive_pairs(golden_dir, D):
     assert np.array_equal(idx, np.arange(n)) and np.array_equal(val, d64.astype(np.float32))
     pred, prob, d32, order, protos = O.lib_protonet(B[:8], np.arange(8, dtype=np.float32), A[:8])
     assert np.array_equal(np.diagonal(d32), d64[:8].astype(np.float32))
+
+
+def test_filter_bound_of_the_exact_kernels(golden_dir):
+    """The CUDA kernels decide float32(sqrt(s_scipy)) from a float64 sum S taken in ANY order whenever
+    float32(sqrt(S(1-d))) == float32(sqrt(S(1+d))), d = (2D+8) 2^-53.  Checked here in numpy:
+    (1) the bound |s_scipy - S| <= d*S holds for the orders a GPU uses (pairwise, reversed, 32 lanes + butterfly), on
+    random rows of several lengths and dynamic ranges; (2) every constructed order-sensitive pair lies in the undecided
+    band, i.e. the GPU test on them exercises the sequential fallback, not the fast path."""
+    import make_order_cases as M
+    rng = np.random.RandomState(7)
+    worst = 0.0
+    for D in (7, 64, 512, 2048, 4099):
+        d = (2.0 * D + 8.0) * 2.0 ** -53
+        for scale in (1.0, 1e-3, 30.0):
+            for _ in range(60):
+                a = (rng.randn(D) * scale * 10.0 ** rng.uniform(-3, 0, size=D)).astype(np.float32)
+                b = (a + rng.randn(D).astype(np.float32) * np.float32(scale * 0.05)).astype(np.float32)
+                s_seq = M.seq_sum(a, b)
+                for s_alt in M.alt_sums(a, b).values():
+                    assert abs(s_seq - s_alt) <= d * s_alt
+                    worst = max(worst, abs(s_seq - s_alt) / (d * s_alt) if s_alt > 0 else 0.0)
+    assert worst < 0.25                                   # the bound is worst-case: typical differences are far inside it
+    fx = _load(golden_dir, "golden_order_sensitive.npz")
+    for D in (64, 512, 2048):
+        d = (2.0 * D + 8.0) * 2.0 ** -53
+        for a, b in zip(fx[f"A{D}"], fx[f"B{D}"]):
+            s_fast = M.alt_sums(a, b)["lanes32"]
+            lo, hi = np.float32(np.sqrt(s_fast * (1 - d))), np.float32(np.sqrt(s_fast * (1 + d)))
+            assert lo != hi
