@@ -1467,7 +1467,7 @@ k_rerank_rows(const RerankParams p)
     __shared__ float s_thr[kRrRowsPerBlock], s_eps[kRrRowsPerBlock];
     __shared__ double s_part64[kRrThreads / 32][3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int D = p.D, D4 = p.D >> 2;
+    const int D4 = p.D >> 2;
     unsigned long long appended = 0, done = 0, unsafe_n = 0, ev32 = 0;   // ev32: per lane-0 thread
     const float inv_lam2 = 1.0f / p.lam2;
     const float4 *probes4 = reinterpret_cast<const float4 *>(p.probes);
