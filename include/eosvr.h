@@ -254,7 +254,7 @@ int eosvr_take_rows(const float *d_src, int64_t n_src, int64_t row_elems, const 
 #define EOSVR_KERNEL_PROBE_PREP 0  /* k_probe_prep: 16-bit probe plan, norms, error bounds, row-state reset */
 #define EOSVR_KERNEL_SEED       1  /* k_match_screen over the strided seed sample                           */
 #define EOSVR_KERNEL_SCREEN     2  /* k_match_screen, main pass (the dominant kernel)                       */
-#define EOSVR_KERNEL_RERANK     3  /* k_rerank_rows: exact re-rank of the candidates                        */
+#define EOSVR_KERNEL_RERANK     3  /* k_rerank_warp / k_rerank_rows: exact re-rank of the candidates           */
 #define EOSVR_KERNEL_FINISH     4  /* k_finish: unpack winners (+ exhaustive fallback)                      */
 #define EOSVR_KERNEL_EPISODE    5  /* k_episode_partial: fused splice + ProtoNet (eosvr_episode_batch only) */
 #define EOSVR_KERNEL_COUNT      6
