@@ -543,8 +543,9 @@ def test_segment_features():
 # full bench size: size-independent properties
 # ---------------------------------------------------------------------------------------------------
 def test_full_size_properties():
-    """cfg-2 at the bench batch (E=256, P=28672, G=11200, D=2048): (1) a sample of episodes equals the
-    oracle; (2) idempotence; (3) shard invariance -- matching two gallery halves separately and merging the
+    """cfg-2 at the bench batch (E=256, P=28672, G=11200, D=2048): (1) 16 episodes spread over the batch equal the
+    CPU oracle and EVERY row equals the exhaustive exact kernel (no screening, no candidate lists: every
+    (probe, gallery) pair evaluated in float64); (2) idempotence; (3) shard invariance -- matching two gallery halves separately and merging the
     packed winners equals the un-sharded answer bit for bit; (4) planted duplicates resolve to the lowest
     index; (5) every reported score is the exact smoothed distance of its reported index."""
     E, n_way, S, D, G = 256, 14, 8, 2048, 11200
@@ -560,10 +561,12 @@ def test_full_size_properties():
     assert st["fallback_rows"] == 0, st
     idx_h, score_h = idx.cpu().numpy(), score.cpu().numpy()
     assert not (idx_h == G - 3).any()
-    for e in (0, 97, 255):
+    for e in (0, 17, 34, 51, 68, 85, 97, 119, 136, 153, 170, 187, 204, 221, 238, 255):
         oid, oval = O.c_match(A[e * rpe:(e + 1) * rpe], gal, rpe)
         assert np.array_equal(idx_h[e * rpe:(e + 1) * rpe], oid)
         assert np.array_equal(score_h[e * rpe:(e + 1) * rpe], oval)
+    idx_x, score_x = ev.match_segments_exact(cache, ws, dA, rpe)
+    assert torch.equal(idx_x, idx) and torch.equal(score_x, score)
     idx2, score2 = ev.match_segments(cache, ws, dA, rpe)
     assert torch.equal(idx, idx2) and torch.equal(score, score2)
     h = 5632
