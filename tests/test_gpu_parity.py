@@ -475,29 +475,35 @@ def test_gallery_cache_file_and_trainaug_manifest(tmp_path):
 
 
 def test_cfg3_scale_100k_gallery_fp32_and_bf16():
-    """BASELINE cfg-3: 5-way 1-shot, 4 segments/clip, D = 512, 100k-segment gallery, fp32 vs bf16 features.
-    A batch of 64 episodes; sampled episodes equal the oracle bit for bit; bf16-rounded features (oracle consumes
-    the same rounded values) through the bf16 screening copy; idempotence; no exhaustive fallback."""
-    E, n_way, S, D, G = 64, 5, 4, 512, 100000
+    """BASELINE cfg-3 at the bench batch: 5-way 1-shot, 4 segments/clip, D = 512, 100k-segment gallery, E = 1024 episodes
+    (P = 20480).  float32 features: EVERY row equals the exhaustive exact kernel (every pair in float64, no screening)
+    and 16 episodes spread over the batch equal the CPU oracle bit for bit.  bf16-rounded features (the oracle consumes
+    the same rounded values) through the bf16 screening copy on 64 episodes; idempotence; no exhaustive fallback."""
+    E, n_way, S, D, G = 1024, 5, 4, 512, 100000
     rpe = n_way * S
     A = synth.segment_features(501, E * rpe, D)
     gal = synth.segment_features(502, G, D)
     for fmt, cast in ((0, False), (1, True)):
         a, g = A, gal
         if cast:
-            a = torch.from_numpy(A).to(torch.bfloat16).to(torch.float32).numpy()
+            a = torch.from_numpy(A[:64 * rpe]).to(torch.bfloat16).to(torch.float32).numpy()
             g = torch.from_numpy(gal).to(torch.bfloat16).to(torch.float32).numpy()
+        n_ep = a.shape[0] // rpe
         cache = ev.GalleryFeatureCache(_cuda(g), screen_fmt=fmt)
-        ws = ev.MatchWorkspace(E * rpe, D)
+        ws = ev.MatchWorkspace(n_ep * rpe, D)
         idx, score = ev.match_segments(cache, ws, _cuda(a), rpe)
         st = ws.stats()
         assert st["fallback_rows"] == 0, st
-        for e in (0, 31, 63):
+        idx_h, score_h = idx.cpu().numpy(), score.cpu().numpy()
+        for e in sorted(set(int(x) for x in np.linspace(0, n_ep - 1, 16 if not cast else 3))):
             oid, oval = O.c_match(a[e * rpe:(e + 1) * rpe], g, rpe)
-            assert np.array_equal(idx.cpu().numpy()[e * rpe:(e + 1) * rpe], oid), (fmt, e, st)
-            assert np.array_equal(score.cpu().numpy()[e * rpe:(e + 1) * rpe], oval)
+            assert np.array_equal(idx_h[e * rpe:(e + 1) * rpe], oid), (fmt, e, st)
+            assert np.array_equal(score_h[e * rpe:(e + 1) * rpe], oval)
         i2, s2 = ev.match_segments(cache, ws, _cuda(a), rpe)
         assert torch.equal(i2, idx) and torch.equal(s2, score)
+        if not cast:
+            ix, sx = ev.match_segments_exact(cache, ws, _cuda(a), rpe)
+            assert torch.equal(ix, idx) and torch.equal(sx, score)
         del cache, ws
 
 
