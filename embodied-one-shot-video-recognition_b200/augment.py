@@ -69,12 +69,11 @@ def trainaug_manifest(gallery: GalleryFeatureCache, videos, seg_len: int = 2, vi
         segs.append(segment_features(f[:n].contiguous(), seg_len, l2) if n else f[:0])
         counts.append(n // seg_len)
     out = [None] * len(videos)
-    for c in sorted(set(counts)):
-        if c == 0:
-            continue
-        members = [i for i, k in enumerate(counts) if k == c]
+    groups = {c: [i for i, k in enumerate(counts) if k == c] for c in sorted(set(counts)) if c}
+    # one workspace for all length groups, sized for the largest (a workspace serves any batch up to its capacity)
+    ws = MatchWorkspace(max(c * len(m) for c, m in groups.items()), gallery.D, device=dev) if groups else None
+    for c, members in groups.items():
         probes = torch.cat([segs[i] for i in members])                  # smoothing runs over each whole video
-        ws = MatchWorkspace(probes.shape[0], gallery.D, device=dev)
         idx, _ = match_segments(gallery, ws, probes, c, lam1, lam2)
         idx = idx.view(len(members), c).cpu().numpy()
         for j, i in enumerate(members):
